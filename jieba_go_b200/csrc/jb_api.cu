@@ -1,0 +1,497 @@
+// C ABI (include/jieba_b200.h): tokenizer handle, table upload to HBM, workspace pool and the
+// host-memory batch driver.  No CPU fallback exists: without a CUDA device creation fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/jieba_b200.h"
+#include "jb_host.h"
+#include "jb_kernels.cuh"
+
+using namespace jb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) return fail(JB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct jb_dict_buf {
+  HostDict d;
+};
+struct jb_emit_buf {
+  HostEmit e;
+};
+
+struct WsSlot {
+  Workspace ws;
+  cudaStream_t stream = nullptr;
+};
+
+struct jb_tokenizer {
+  int device = 0;
+  JbTables T;
+  std::vector<void*> dev_allocs;
+  uint64_t max_batch = 256ull << 20;
+  double w_per_slot = 3.0;
+  std::mutex mu;
+  std::vector<WsSlot*> free_ws;
+  WsSlot dev_ws;  // workspace of jb_cut_device (one caller at a time per tokenizer for the device API)
+  std::mutex dev_mu;
+};
+
+struct jb_result {
+  uint64_t n_tokens = 0, ndocs = 0;
+  uint32_t* start = nullptr;
+  uint32_t* end = nullptr;
+  uint64_t* doc_tok = nullptr;
+  uint64_t cap = 0;
+};
+
+template <typename T>
+static int upload(jb_tokenizer* tk, const std::vector<T>& v, const T** out) {
+  void* p = nullptr;
+  size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  tk->dev_allocs.push_back(p);
+  if (v.size()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = (const T*)p;
+  return JB_OK;
+}
+
+extern "C" {
+
+int jb_version(void) { return JB_VERSION; }
+const char* jb_last_error(void) { return g_err.c_str(); }
+void jb_hmm_defaults(jb_hmm_desc* h) { hmm_defaults(h); }
+double jb_go_log(double x) { return go_log(x); }
+uint64_t jb_kernel_launch_count(void) { return kernel_launch_count(); }
+
+// ---- loaders ------------------------------------------------------------------------------
+int jb_dict_load_text(const uint8_t* data, uint64_t len, int mode, jb_dict_buf** out) {
+  if (!out || (len && !data) || (mode != JB_DICT_FILE_MODE && mode != JB_DICT_PREFIX_MODE)) return fail(JB_EINVAL, "bad argument");
+  jb_dict_buf* b = new jb_dict_buf();
+  std::string err;
+  int rc = load_dict_text(data, len, mode, b->d, err);
+  if (rc != JB_OK) {
+    delete b;
+    return fail(rc, err);
+  }
+  *out = b;
+  return JB_OK;
+}
+
+int jb_dict_load_file(const char* path, int mode, jb_dict_buf** out) {
+  std::vector<uint8_t> buf;
+  std::string err;
+  int rc = read_file(path, buf, err);
+  if (rc != JB_OK) return fail(rc, err);
+  return jb_dict_load_text(buf.data(), buf.size(), mode, out);
+}
+
+int jb_dict_load_gob(const uint8_t* data, uint64_t len, jb_dict_buf** out) {
+  if (!out || (len && !data)) return fail(JB_EINVAL, "bad argument");
+  jb_dict_buf* b = new jb_dict_buf();
+  std::string err;
+  int rc = load_dict_gob(data, len, b->d, err);
+  if (rc != JB_OK) {
+    delete b;
+    return fail(rc, err);
+  }
+  *out = b;
+  return JB_OK;
+}
+
+int jb_dict_load_gob_file(const char* path, jb_dict_buf** out) {
+  std::vector<uint8_t> buf;
+  std::string err;
+  int rc = read_file(path, buf, err);
+  if (rc != JB_OK) return fail(rc, err);
+  return jb_dict_load_gob(buf.data(), buf.size(), out);
+}
+
+int jb_dict_add_term(jb_dict_buf* d, const uint8_t* term, uint64_t len, int64_t freq) {
+  if (!d || (len && !term)) return fail(JB_EINVAL, "bad argument");
+  d->d.set(std::string((const char*)term, len), freq);  // termFreq[term] = freq (tokenizer.go:583)
+  d->d.size += freq;                                    // size += freq        (tokenizer.go:584)
+  return JB_OK;
+}
+
+int jb_dict_buf_lookup(const jb_dict_buf* d, const uint8_t* key, uint64_t len, int64_t* freq) {
+  auto it = d->d.index.find(std::string((const char*)key, len));
+  if (it == d->d.index.end()) return 0;
+  if (freq) *freq = d->d.freq[it->second];
+  return 1;
+}
+
+void jb_dict_buf_desc(const jb_dict_buf* d, jb_dict_desc* out) {
+  jb_dict_buf* m = const_cast<jb_dict_buf*>(d);
+  m->d.flatten();
+  out->keys = m->d.blob.data();
+  out->key_off = m->d.off.data();
+  out->freq = m->d.freq.data();
+  out->log_freq = nullptr;
+  out->n = m->d.keys.size();
+  out->size = m->d.size;
+  out->log_total = NAN;
+}
+void jb_dict_buf_set_size(jb_dict_buf* d, int64_t size) { d->d.size = size; }
+void jb_dict_buf_free(jb_dict_buf* d) { delete d; }
+
+int jb_emit_load_json(const uint8_t* data, uint64_t len, jb_emit_buf** out) {
+  if (!out || (len && !data)) return fail(JB_EINVAL, "bad argument");
+  jb_emit_buf* b = new jb_emit_buf();
+  std::string err;
+  int rc = load_emit_json(data, len, b->e, err);
+  if (rc != JB_OK) {
+    delete b;
+    return fail(rc, err);
+  }
+  *out = b;
+  return JB_OK;
+}
+int jb_emit_load_json_file(const char* path, jb_emit_buf** out) {
+  std::vector<uint8_t> buf;
+  std::string err;
+  int rc = read_file(path, buf, err);
+  if (rc != JB_OK) return fail(rc, err);
+  return jb_emit_load_json(buf.data(), buf.size(), out);
+}
+void jb_emit_buf_fill(const jb_emit_buf* e, jb_hmm_desc* hmm) {
+  hmm->emit_state = e->e.state.data();
+  hmm->emit_rune = e->e.rune.data();
+  hmm->emit_logp = e->e.logp.data();
+  hmm->n_emit = e->e.rune.size();
+}
+void jb_emit_buf_free(jb_emit_buf* e) { delete e; }
+
+// ---- tokenizer ------------------------------------------------------------------------------
+int jb_tokenizer_create(const jb_dict_desc* dict, const jb_hmm_desc* hmm, const jb_options* opt, jb_tokenizer** out) {
+  if (!dict || !hmm || !out) return fail(JB_EINVAL, "null argument");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(JB_ECUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(ce));
+  int dev = opt ? opt->device : -1;
+  if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(JB_EINVAL, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(dev));
+  TableImage img;
+  std::string err;
+  int rc = build_tables(dict, hmm, opt ? opt->unicode_version : 15, img, err);
+  if (rc != JB_OK) return fail(rc, err);
+  jb_tokenizer* tk = new jb_tokenizer();
+  tk->device = dev;
+  if (opt && opt->max_batch_bytes) tk->max_batch = opt->max_batch_bytes;
+  if (tk->max_batch > (1ull << 31) - (1ull << 20)) tk->max_batch = (1ull << 31) - (1ull << 20);
+  JbTables& T = tk->T;
+  memset(&T, 0, sizeof T);
+  rc = upload(tk, img.first, &T.first);
+  if (rc == JB_OK) rc = upload(tk, img.entries, &T.entries);
+  if (rc == JB_OK) rc = upload(tk, img.key_blob, &T.key_blob);
+  if (rc == JB_OK) rc = upload(tk, img.emit, &T.emit);
+  if (rc == JB_OK) rc = upload(tk, img.emit_supp_rune, &T.emit_supp_rune);
+  if (rc == JB_OK) rc = upload(tk, img.emit_supp, &T.emit_supp);
+  if (rc == JB_OK) rc = upload(tk, img.han_bits, &T.han_bits);
+  if (rc != JB_OK) {
+    jb_tokenizer_destroy(tk);
+    return rc;
+  }
+  T.hash_mask = (uint32_t)(img.entries.size() - 1);
+  T.n_emit_supp = (uint32_t)img.emit_supp_rune.size();
+  T.n_supp = (uint32_t)img.supp_lo.size();
+  for (uint32_t i = 0; i < T.n_supp; i++) {
+    T.supp_lo[i] = img.supp_lo[i];
+    T.supp_hi[i] = img.supp_hi[i];
+  }
+  T.neg_log_total = img.neg_log_total;
+  for (int s = 0; s < 4; s++) {
+    T.start[s] = img.start[s];
+    T.trans[s][0] = img.trans[s][0];
+    T.trans[s][1] = img.trans[s][1];
+  }
+  T.max_delta = img.max_delta;
+  *out = tk;
+  return JB_OK;
+}
+
+static int create_from_bufs(jb_dict_buf* db, const char* emit_json_path, const jb_options* opt, jb_tokenizer** out) {
+  jb_emit_buf* eb = nullptr;
+  int rc = jb_emit_load_json_file(emit_json_path, &eb);
+  if (rc != JB_OK) return rc;
+  jb_dict_desc dd;
+  jb_dict_buf_desc(db, &dd);
+  jb_hmm_desc hd;
+  jb_hmm_defaults(&hd);
+  jb_emit_buf_fill(eb, &hd);
+  rc = jb_tokenizer_create(&dd, &hd, opt, out);
+  jb_emit_buf_free(eb);
+  return rc;
+}
+
+int jb_tokenizer_create_from_files(const char* dict_path, int dict_mode, const char* emit_json_path, const jb_options* opt,
+                                   jb_tokenizer** out) {
+  if (!dict_path || !emit_json_path || !out) return fail(JB_EINVAL, "null argument");
+  jb_dict_buf* db = nullptr;
+  int rc = jb_dict_load_file(dict_path, dict_mode, &db);
+  if (rc != JB_OK) return rc;
+  rc = create_from_bufs(db, emit_json_path, opt, out);
+  jb_dict_buf_free(db);
+  return rc;
+}
+
+int jb_tokenizer_create_from_gob(const char* gob_path, int64_t size, const char* emit_json_path, const jb_options* opt,
+                                 jb_tokenizer** out) {
+  if (!gob_path || !emit_json_path || !out) return fail(JB_EINVAL, "null argument");
+  jb_dict_buf* db = nullptr;
+  int rc = jb_dict_load_gob_file(gob_path, &db);
+  if (rc != JB_OK) return rc;
+  jb_dict_buf_set_size(db, size);  // pd.size = 60_101_967 is a literal in the reference (tokenizer.go:454)
+  rc = create_from_bufs(db, emit_json_path, opt, out);
+  jb_dict_buf_free(db);
+  return rc;
+}
+
+static void free_slot(WsSlot* s) {
+  workspace_free(s->ws);
+  if (s->stream) cudaStreamDestroy(s->stream);
+}
+
+void jb_tokenizer_destroy(jb_tokenizer* tk) {
+  if (!tk) return;
+  cudaSetDevice(tk->device);
+  for (WsSlot* s : tk->free_ws) {
+    free_slot(s);
+    delete s;
+  }
+  free_slot(&tk->dev_ws);
+  for (void* p : tk->dev_allocs) cudaFree(p);
+  delete tk;
+}
+
+int jb_set_candidates_per_slot(jb_tokenizer* tk, double per_slot) {
+  if (!tk || !(per_slot >= 1.0) || per_slot > 30.0) return fail(JB_EINVAL, "per_slot must be in [1,30]");
+  tk->w_per_slot = per_slot;
+  return JB_OK;
+}
+
+// ---- Cut --------------------------------------------------------------------------------------
+uint64_t jb_result_num_tokens(const jb_result* r) { return r->n_tokens; }
+const uint32_t* jb_result_start(const jb_result* r) { return r->start; }
+const uint32_t* jb_result_end(const jb_result* r) { return r->end; }
+const uint64_t* jb_result_doc_tok_off(const jb_result* r) { return r->doc_tok; }
+void jb_result_free(jb_result* r) {
+  if (!r) return;
+  if (r->start) cudaFreeHost(r->start);
+  if (r->end) cudaFreeHost(r->end);
+  if (r->doc_tok) cudaFreeHost(r->doc_tok);
+  delete r;
+}
+
+static int result_grow(jb_result* r, uint64_t need) {
+  if (need <= r->cap) return JB_OK;
+  uint64_t ncap = r->cap ? r->cap : 1024;
+  while (ncap < need) ncap = ncap + ncap / 2 + 1024;
+  uint32_t *ns = nullptr, *ne = nullptr;
+  CUDA_TRY(cudaMallocHost(&ns, ncap * 4));
+  CUDA_TRY(cudaMallocHost(&ne, ncap * 4));
+  if (r->n_tokens) {
+    memcpy(ns, r->start, r->n_tokens * 4);
+    memcpy(ne, r->end, r->n_tokens * 4);
+  }
+  if (r->start) cudaFreeHost(r->start);
+  if (r->end) cudaFreeHost(r->end);
+  r->start = ns;
+  r->end = ne;
+  r->cap = ncap;
+  return JB_OK;
+}
+
+int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm, jb_result** out) {
+  if (!tk || !out || !doc_off || (ndocs && doc_off[ndocs] > doc_off[0] && !text)) return fail(JB_EINVAL, "null argument");
+  for (uint64_t d = 0; d < ndocs; d++) {
+    if (doc_off[d + 1] < doc_off[d]) return fail(JB_EINVAL, "doc_off must be non-decreasing");
+    if (doc_off[d + 1] - doc_off[d] > tk->max_batch)
+      return fail(JB_ELIMIT, "a document exceeds the device batch size (raise jb_options.max_batch_bytes; hard limit 2 GiB)");
+  }
+  CUDA_TRY(cudaSetDevice(tk->device));
+  WsSlot* slot = nullptr;
+  {
+    std::lock_guard<std::mutex> g(tk->mu);
+    if (!tk->free_ws.empty()) {
+      slot = tk->free_ws.back();
+      tk->free_ws.pop_back();
+    }
+  }
+  if (!slot) {
+    slot = new WsSlot();
+    if (cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete slot;
+      return fail(JB_ECUDA, "cudaStreamCreate failed");
+    }
+  }
+  jb_result* res = new jb_result();
+  res->ndocs = ndocs;
+  int rc = JB_OK;
+  auto done = [&](int code) {
+    std::lock_guard<std::mutex> g(tk->mu);
+    tk->free_ws.push_back(slot);
+    if (code != JB_OK) {
+      jb_result_free(res);
+      return code;
+    }
+    *out = res;
+    return (int)JB_OK;
+  };
+  if (cudaMallocHost(&res->doc_tok, (ndocs + 1) * 8) != cudaSuccess) return done(fail(JB_ENOMEM, "cudaMallocHost failed"));
+  res->doc_tok[0] = 0;
+  cudaStream_t st = slot->stream;
+  uint64_t d0 = 0;
+  double wps = tk->w_per_slot;
+  while (d0 < ndocs || (ndocs == 0 && d0 == 0)) {
+    if (ndocs == 0) break;
+    // greedy batch of whole documents
+    uint64_t d1 = d0 + 1;
+    while (d1 < ndocs && doc_off[d1 + 1] - doc_off[d0] <= tk->max_batch) d1++;
+    const uint64_t nb = doc_off[d1] - doc_off[d0], nd = d1 - d0;
+    for (;;) {
+      rc = workspace_reserve(slot->ws, nb, nd, wps, true);
+      if (rc != JB_OK) return done(fail(rc, "device workspace allocation failed"));
+      Workspace& ws = slot->ws;
+      if (nb) CUDA_TRY(cudaMemcpyAsync(ws.text, text + doc_off[d0], nb, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, doc_off + d0, (nd + 1) * 8, cudaMemcpyHostToDevice, st));
+      rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nb, ws.doc_off64, nd, use_hmm != 0, nullptr, nullptr, 0, ws.out_doc_tok,
+                        res->n_tokens, ws.out_ntok, st);
+      if (rc != JB_OK) return done(fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError())));
+      uint64_t cnt[2];
+      CUDA_TRY(cudaMemcpyAsync(cnt, ws.out_ntok, 16, cudaMemcpyDeviceToHost, st));
+      cudaError_t se = cudaStreamSynchronize(st);
+      if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("pipeline failed: ") + cudaGetErrorString(se)));
+      if (cnt[1] & 1) {  // candidate buffer overflow: enlarge and redo this batch
+        wps = wps * 2 > 30 ? 30 : wps * 2;
+        continue;
+      }
+      const uint64_t nt = cnt[0];
+      if (nt > ws.out_cap) {
+        uint64_t ncap = nt + nt / 8 + 1024;
+        if (ws.out_start) cudaFree(ws.out_start);
+        if (ws.out_end) cudaFree(ws.out_end);
+        ws.out_start = ws.out_end = nullptr;
+        ws.out_cap = 0;
+        if (cudaMalloc(&ws.out_start, ncap * 4) != cudaSuccess || cudaMalloc(&ws.out_end, ncap * 4) != cudaSuccess)
+          return done(fail(JB_ENOMEM, "device output allocation failed"));
+        ws.out_cap = ncap;
+      }
+      rc = run_scatter(ws, (uint32_t)nb, nd, ws.out_start, ws.out_end, ws.out_cap, ws.out_doc_tok, res->n_tokens, st);
+      if (rc != JB_OK) return done(fail(rc, "scatter launch failed"));
+      rc = result_grow(res, res->n_tokens + nt);
+      if (rc != JB_OK) return done(rc);
+      if (nt) {
+        CUDA_TRY(cudaMemcpyAsync(res->start + res->n_tokens, ws.out_start, nt * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(res->end + res->n_tokens, ws.out_end, nt * 4, cudaMemcpyDeviceToHost, st));
+      }
+      CUDA_TRY(cudaMemcpyAsync(res->doc_tok + d0, ws.out_doc_tok, (nd + 1) * 8, cudaMemcpyDeviceToHost, st));
+      se = cudaStreamSynchronize(st);
+      if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("pipeline failed: ") + cudaGetErrorString(se)));
+      res->n_tokens += nt;
+      break;
+    }
+    d0 = d1;
+  }
+  res->doc_tok[ndocs] = res->n_tokens;
+  return done(JB_OK);
+}
+
+int jb_cut(jb_tokenizer* tk, const uint8_t* text, uint64_t nbytes, int use_hmm, jb_result** out) {
+  uint64_t off[2] = {0, nbytes};
+  return jb_cut_batch(tk, text, off, 1, use_hmm, out);
+}
+
+int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, const uint64_t* d_doc_off, uint64_t ndocs, int use_hmm,
+                  uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens, uint64_t* d_doc_tok_off, uint64_t* d_n_tokens,
+                  void* cuda_stream) {
+  if (!tk || !d_doc_off || !d_n_tokens || (nbytes && !d_text)) return fail(JB_EINVAL, "null argument");
+  if (nbytes >= (1ull << 31)) return fail(JB_ELIMIT, "jb_cut_device handles < 2 GiB per call");
+  CUDA_TRY(cudaSetDevice(tk->device));
+  std::lock_guard<std::mutex> g(tk->dev_mu);
+  int rc = workspace_reserve(tk->dev_ws.ws, nbytes, ndocs, tk->w_per_slot, false);
+  if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
+  rc = run_pipeline(tk->T, tk->dev_ws.ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, d_start, d_end, cap_tokens,
+                    d_doc_tok_off, 0, d_n_tokens, (cudaStream_t)cuda_stream);
+  if (rc != JB_OK) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  return JB_OK;
+}
+
+int jb_debug_lookup(jb_tokenizer* tk, const uint8_t* key, uint64_t len, double* w) {
+  if (!tk || !key || !len) return JB_EINVAL;
+  std::vector<uint32_t> runes;
+  for (uint64_t i = 0; i < len;) {
+    uint32_t r;
+    int wd = decode_rune(key, i, len, &r);
+    runes.push_back(r);
+    i += wd;
+  }
+  if (cudaSetDevice(tk->device) != cudaSuccess) return JB_ECUDA;
+  int kind = 0;
+  double wv = 0;
+  int rc = debug_lookup(tk->T, runes.data(), (int)runes.size(), &kind, &wv);
+  if (rc != JB_OK) return rc;
+  if (w) *w = wv;
+  return kind;
+}
+
+int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, uint32_t* best_end, double* best_proba, uint64_t cap) {
+  if (!tk || !han_text || !nbytes) return fail(JB_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(tk->device));
+  std::lock_guard<std::mutex> g(tk->dev_mu);
+  WsSlot& s = tk->dev_ws;
+  int rc = workspace_reserve(s.ws, nbytes, 1, tk->w_per_slot, true);
+  if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
+  Workspace& ws = s.ws;
+  uint64_t nslots = (ws.cap_bytes / kTileBytes + 2) * kTileSlots + 64;
+  if (!ws.dbg_proba) CUDA_TRY(cudaMalloc(&ws.dbg_proba, nslots * 8));
+  uint64_t off[2] = {0, nbytes};
+  CUDA_TRY(cudaMemcpy(ws.text, han_text, nbytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(ws.doc_off64, off, 16, cudaMemcpyHostToDevice));
+  rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, nullptr, nullptr, 0, ws.out_doc_tok, 0, ws.out_ntok, 0);
+  CUDA_TRY(cudaDeviceSynchronize());
+  // read back records + probabilities and translate slots to rune indexes
+  uint64_t ns = (nbytes + 2) / 3 + 2;
+  std::vector<uint32_t> rec(ns);
+  std::vector<double> pr(ns);
+  CUDA_TRY(cudaMemcpy(rec.data(), ws.rec, ns * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(pr.data(), ws.dbg_proba, ns * 8, cudaMemcpyDeviceToHost));
+  cudaFree(ws.dbg_proba);
+  ws.dbg_proba = nullptr;
+  // rune index of every slot
+  std::vector<int64_t> rune_of_slot(ns + 64, -1);
+  uint64_t nr = 0;
+  for (uint64_t i = 0; i < nbytes;) {
+    uint32_t r;
+    int wd = decode_rune(han_text, i, nbytes, &r);
+    rune_of_slot[(i + 2) / 3] = (int64_t)nr++;
+    i += wd;
+  }
+  rune_of_slot[(nbytes + 2) / 3] = (int64_t)nr;
+  uint64_t o = 0;
+  for (uint64_t k = 0; k < ns && o < cap; k++) {
+    if (rune_of_slot[k] < 0 || (uint64_t)rune_of_slot[k] >= nr) continue;
+    best_end[o] = (uint32_t)rune_of_slot[k + (rec[k] & 0xFF)];
+    best_proba[o] = pr[k];
+    o++;
+  }
+  return (int)o;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Device-side pipeline interface (internal).  See DESIGN.md for the kernel list.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jb_common.h"
+
+namespace jb {
+
+// Tile geometry of the split/DAG kernels: a tile is 1024 slots = 3072 bytes (a multiple of 3
+// for the slot map and of 32 for the bitmaps).
+constexpr int kTileSlots = 1024;
+constexpr int kTileBytes = 3 * kTileSlots;
+constexpr int kHaloL = 16;
+constexpr int kHaloR = 144;  // >= longest Han key (90 B) + one rune + slack
+constexpr int kRegion = kHaloL + kTileBytes + kHaloR;
+// Token ranking tiles: 4096 bytes = 128 bitmap words
+constexpr int kRankWords = 128;
+constexpr int kRankBytes = kRankWords * 32;
+
+enum Counter {
+  C_N_ENDS = 0,    // number of Han blocks (entries of `ends`)
+  C_CUR_DP = 1,    // work cursor of the route-DP kernel
+  C_CUR_WALK = 2,  // work cursor of the walk kernel
+  C_STATUS = 3,    // bit0: candidate-weight buffer overflow
+  C_N_TOKENS = 4,
+  C_W_NEEDED = 5,  // max weights needed by any tile (to size a retry)
+  C_NUM = 8
+};
+
+struct Workspace {
+  // capacity
+  uint64_t cap_bytes = 0;
+  uint32_t w_per_tile = 0;  // candidate weights reserved per tile
+  // buffers
+  uint8_t* text = nullptr;      // staging for host-memory batches
+  uint64_t* doc_off64 = nullptr; // staging for host-memory batches
+  uint64_t cap_docs = 0;
+  uint32_t* doc_off32 = nullptr;
+  uint32_t* ds_bits = nullptr;   // document-start bitmap
+  uint32_t* s_bits = nullptr;    // token-start bitmap
+  uint32_t* e_bits = nullptr;    // token-end bitmap (bit at the token's last byte)
+  uint32_t* rec = nullptr;       // per-slot records
+  uint32_t* gend = nullptr;      // per 32-slot group: end offset of its weights in wbuf
+  double* wbuf = nullptr;        // candidate weights
+  uint2* ends = nullptr;         // per Han block: (last rune slot, weight end offset)
+  uint2* walks = nullptr;        // per Han block: (first rune slot, block end byte)
+  uint8_t* tile_sum = nullptr;   // per split tile: has-boundary / alnum-before / alnum-after
+  uint8_t* tile_ctx = nullptr;   // per split tile: bit0 fwd, bit1 bwd
+  uint32_t* rank_cnt = nullptr;  // per rank tile: token count, then exclusive prefix
+  uint32_t* counters = nullptr;  // Counter
+  double* dbg_proba = nullptr;   // optional: selected route value per slot
+  // outputs for host-memory batches
+  uint32_t* out_start = nullptr;
+  uint32_t* out_end = nullptr;
+  uint64_t out_cap = 0;
+  uint64_t* out_doc_tok = nullptr;
+  uint64_t* out_ntok = nullptr;  // [2]
+};
+
+int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_per_slot, bool host_staging);
+void workspace_free(Workspace& ws);
+
+// Enqueue the whole Cut pipeline for one batch on `stream`.
+//   d_text[nbytes], d_doc_off[ndocs+1] (uint64, absolute; doc_off[0] is subtracted) on device.
+//   Token (start,end) are written doc-relative into d_start/d_end (up to cap_tokens),
+//   d_doc_tok_off[ndocs+1] gets tok_base + rank, d_n_tokens[0] the batch's token count and
+//   d_n_tokens[1] the status word.
+int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_doc_off,
+                 uint64_t ndocs, bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
+                 uint64_t* d_doc_tok_off, uint64_t tok_base, uint64_t* d_n_tokens, cudaStream_t stream);
+
+// Second phase when d_start/d_end were NULL in run_pipeline (count first, then scatter).
+int run_scatter(Workspace& ws, uint32_t nbytes, uint64_t ndocs, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
+                uint64_t* d_doc_tok_off, uint64_t tok_base, cudaStream_t stream);
+
+int debug_lookup(const JbTables& T, const uint32_t* runes_host, int L, int* kind, double* w);
+
+uint64_t kernel_launch_count();
+
+}  // namespace jb

@@ -1,0 +1,210 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+inputs.  Bit-exact bar: token (start,end) lists and doc_tok_off arrays must be identical; route
+values (float64) must have identical bits."""
+import numpy as np
+import pytest
+
+from jieba_go_b200 import synth
+
+import kat_vectors as kv
+from helpers import c_oracle_tokenizer, emit_arrays, fuzz_docs, pack_docs
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_tokenizer(sd_or_lines, emit, mode=1, **kw):
+    from jieba_go_b200.tokenizer import Tokenizer
+    if isinstance(sd_or_lines, (list, tuple)):
+        data = "\n".join(sd_or_lines).encode() + b"\n"
+    else:
+        data = sd_or_lines.dict_txt()
+    return Tokenizer.from_dict_text(data, mode, emit, **kw)
+
+
+@pytest.fixture(scope="module")
+def kat_tk(kat_lines, kat_emit):
+    return _gpu_tokenizer(kat_lines, kat_emit)
+
+
+@pytest.fixture(scope="module")
+def synth_pair(small_synth):
+    sd, emit = small_synth
+    return sd, emit, _gpu_tokenizer(sd, emit), c_oracle_tokenizer(sd, emit)
+
+
+@pytest.fixture(scope="module")
+def medium_pair():
+    sd = synth.make_dictionary(n_words=60000, seed=synth.SEED_BASE + 31, total_freq=1.5e7, max_len=16)
+    emit = synth.make_emit(sd, seed=synth.SEED_BASE + 32)
+    return sd, emit, _gpu_tokenizer(sd, emit), c_oracle_tokenizer(sd, emit)
+
+
+def _assert_same(gpu, ora, text=None, off=None):
+    gs, ge, gd = gpu
+    os_, oe, _, od = ora
+    assert np.array_equal(gd, od), "doc_tok_off differs"
+    if not (np.array_equal(gs, os_) and np.array_equal(ge, oe)):
+        n = min(len(gs), len(os_))
+        bad = np.nonzero((gs[:n] != os_[:n]) | (ge[:n] != oe[:n]))[0]
+        i = int(bad[0]) if len(bad) else n
+        d = int(np.searchsorted(od, i, side="right") - 1)
+        ctx = ""
+        if text is not None:
+            doc = bytes(text[int(off[d]):int(off[d + 1])])
+            lo = max(0, int(os_[max(i - 2, int(od[d]))]) if i < len(os_) else 0)
+            ctx = repr(doc[lo:lo + 60].decode("utf-8", "replace"))
+        raise AssertionError("token %d (doc %d) differs: gpu=%s oracle=%s near %s; counts gpu=%d oracle=%d" % (
+            i, d, (gs[i:i + 4].tolist(), ge[i:i + 4].tolist()), (os_[i:i + 4].tolist(), oe[i:i + 4].tolist()), ctx, len(gs), len(os_)))
+
+
+# ---- reference vectors + micro-KATs through the GPU path ---------------------------------------
+@pytest.mark.parametrize("text,off,on", kv.KATS)
+def test_kats(kat_tk, text, off, on):
+    assert kat_tk.cut(text, False) == off
+    assert kat_tk.cut(text, True) == on
+
+
+def test_kat5_selector_is_not_argmax(kat_emit):
+    tk = _gpu_tokenizer(kv.KAT5_LINES, kat_emit)
+    assert tk.cut(kv.KAT5[0], False) == kv.KAT5[1]
+
+
+@pytest.mark.parametrize("text,want", kv.CUT_NON_ZH)  # TestCutNonZh, tokenizer_test.go:373-376
+def test_cut_non_zh(kat_tk, text, want):
+    assert kat_tk.cut(text, False) == want
+
+
+@pytest.mark.parametrize("text,want", kv.SPLIT_TEXT)  # TestSplitText: block structure seen through Cut
+def test_split_text_blocks(kat_tk, kat_lines, kat_emit, text, want):
+    ora = c_oracle_tokenizer_lines(kat_lines, kat_emit)
+    assert kat_tk.cut_offsets(text, True) == ora.cut(text, True)
+    assert kat_tk.cut_offsets(text, False) == ora.cut(text, False)
+
+
+def c_oracle_tokenizer_lines(lines, emit):
+    from oracle import c_oracle as co
+    return co.Tokenizer(co.Dict.from_lines(lines, 1), co.Hmm(emit))
+
+
+def test_cut_parallel_contract(kat_tk):
+    t = "乙丙，a1 乙丙甲甲甲x 乙\t丙丁!"
+    assert kat_tk.cut_parallel(t, True, 6, True) == kat_tk.cut(t, True)   # ordered=true == Cut (T:110-125)
+    assert sorted(kat_tk.cut_parallel(t, True, 6, False)) == sorted(kat_tk.cut(t, True))
+
+
+def test_invalid_utf8(kat_tk, kat_lines, kat_emit):
+    b = b"a\xff\xe4\xb8 \xe4\xb9\x99\x80z"
+    want = [(0, 1, False), (1, 2, True), (2, 3, True), (3, 4, True), (5, 8, False), (8, 9, True), (9, 10, False)]
+    assert kat_tk.cut_offsets(b, False) == want
+    assert kat_tk.cut(b, False) == ["a", "�", "�", "�", "乙", "�", "z"]
+
+
+# ---- dictionary table ---------------------------------------------------------------------------
+def test_device_dictionary_matches_term_freq(synth_pair):
+    sd, emit, tk, ora = synth_pair
+    from oracle import c_oracle as co
+    keys, koff, freq = ora.pd.export()
+    log_total = co.go_log(float(ora.pd.size))
+    rng = np.random.default_rng(3)
+    idx = rng.choice(len(freq), size=min(400, len(freq)), replace=False)
+    n_han = 0
+    for i in idx.tolist():
+        k = keys[koff[i]:koff[i + 1]].tobytes()
+        s = k.decode()
+        if not all(0x4E00 <= ord(ch) <= 0x9FFF for ch in s):
+            continue
+        n_han += 1
+        kind, w = tk.debug_lookup(k)
+        if freq[i] > 0:
+            assert kind == 2 and w == co.go_log(float(freq[i])) - log_total, s
+        else:
+            assert kind == 1, s
+    assert n_han > 100
+    assert tk.debug_lookup("龥龥龥")[0] == 0
+
+
+def test_route_values_bit_exact(synth_pair):
+    sd, emit, tk, ora = synth_pair
+    text, _ = synth.make_corpus(sd, "long", 40_000, synth.SEED_BASE + 40)
+    han = text.numpy()[:9000].tobytes()  # 3000 runes, Han only
+    ge, gp = tk.debug_route(han)
+    oe, op = ora.route(han)
+    assert np.array_equal(ge, oe)
+    assert np.array_equal(gp.view(np.uint64), op.view(np.uint64))
+
+
+# ---- randomised parity ---------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("hmm", [False, True])
+def test_fuzz_docs(small_synth, mode, hmm):
+    sd, emit = small_synth
+    tk = _gpu_tokenizer(sd, emit, mode)
+    ora = c_oracle_tokenizer(sd, emit, mode)
+    rng = np.random.default_rng(100 + mode)
+    docs = fuzz_docs(sd, rng, n_docs=400, max_len=150) + [b"", b"", "甲".encode(), b"\xe4", b"x"]
+    text, off = pack_docs(docs)
+    _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 2), text, off)
+
+
+@pytest.mark.parametrize("kind", ["freq", "oov", "long"])
+@pytest.mark.parametrize("hmm", [False, True])
+def test_corpora(medium_pair, kind, hmm):
+    sd, emit, tk, ora = medium_pair
+    text, doc_off = synth.make_corpus(sd, kind, 3_000_000, synth.SEED_BASE + 50)
+    t = text.numpy()
+    off = doc_off.numpy().astype(np.uint64)
+    _assert_same(tk.cut_batch(t, off, hmm), ora.cut_batch(t, off, hmm, 8), t, off)
+
+
+def test_unicode_13_vs_15(small_synth):
+    sd, emit = small_synth
+    t = "鿽鿾鿿𪛞乙".encode()  # U+9FFD..9FFF, U+2A6DE: Han only from Unicode 14/15 on
+    for ver in (13, 15):
+        tk = _gpu_tokenizer(sd, emit, 1, unicode_version=ver)
+        ora = c_oracle_tokenizer(sd, emit, 1, unicode_version=ver)
+        assert tk.cut_offsets(t, True) == ora.cut(t, True)
+        assert tk.cut_offsets(t, False) == ora.cut(t, False)
+
+
+def test_batches_and_document_boundaries(synth_pair):
+    sd, emit, _, ora = synth_pair
+    tk = _gpu_tokenizer(sd, emit, 1, max_batch_bytes=20_000)  # forces many device batches
+    text, doc_off = synth.make_corpus(sd, "oov", 300_000, synth.SEED_BASE + 60)
+    t = text.numpy()
+    # re-cut the same bytes into documents at arbitrary byte positions (splits runes and words)
+    rng = np.random.default_rng(5)
+    cuts = np.unique(np.concatenate([[0, t.size], rng.integers(0, t.size, 400)])).astype(np.uint64)
+    off = np.concatenate([cuts[:50], cuts[49:50], cuts[49:50], cuts[50:]])  # a few empty documents too
+    for hmm in (False, True):
+        _assert_same(tk.cut_batch(t, off, hmm), ora.cut_batch(t, off, hmm, 4), t, off)
+
+
+def test_add_word_rebuilds_tables(kat_lines, kat_emit):
+    tk = _gpu_tokenizer(kat_lines, kat_emit)
+    assert tk.cut("甲乙", False) == ["甲", "乙"]
+    tk.add_word("甲乙", 5000)   # addTerm: termFreq + size, no prefixes (T:580-585)
+    assert tk.lookup("甲乙") == 5000 and tk.size == 359 + 5000
+    assert tk.cut("甲乙", False) == ["甲乙"]
+
+
+def test_device_api(medium_pair):
+    import torch
+    sd, emit, tk, ora = medium_pair
+    text, doc_off = synth.make_corpus(sd, "oov", 2_000_000, synth.SEED_BASE + 70)
+    t = text.numpy()
+    off = doc_off.numpy().astype(np.uint64)
+    os_, oe, _, od = ora.cut_batch(t, off, True, 8)
+    dt, ddo = text.cuda(), doc_off.cuda()
+    cap = len(os_) + 10
+    d_start = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    d_end = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    d_dto = torch.zeros(off.size, dtype=torch.int64, device="cuda")
+    d_nt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        tk.cut_device(dt, ddo, True, d_start, d_end, d_dto, d_nt, stream=s)
+    s.synchronize()
+    assert d_nt.tolist() == [len(os_), 0]
+    assert np.array_equal(d_start[:len(os_)].cpu().numpy().astype(np.uint32), os_)
+    assert np.array_equal(d_end[:len(os_)].cpu().numpy().astype(np.uint32), oe)
+    assert np.array_equal(d_dto.cpu().numpy().astype(np.uint64), od)
