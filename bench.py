@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the Cut hot path (BASELINE.json metric: UTF-8 MB/s segmented, % of HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W [--config 2|3|4|5] [--bytes B]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port; Go is absent)
+
+A step = one pass of the whole Cut pipeline over one synthetic batch.  At N=1 the default
+workload is BASELINE.json configs[1]: 1e9 bytes sampled from the (synthetic, jieba-format)
+dictionary by frequency, HMM off.  With N>1 (torchrun, one rank per GPU) every rank cuts its own
+batch of the same size (documents shard with no data-path collective): weak scaling.
+
+`value`   device-resident input -> device-resident (start,end) arrays via jb_cut_device, CUDA events
+          on the launching stream, max over ranks.
+`e2e`     the same batch through jb_cut_batch with HOST buffers: pinned text H2D, pipeline, token
+          arrays D2H -- everything inside the timed region.
+`roofline` algorithmic bytes A = B_in + 8*T_out / duration of the dominant kernel
+          (per-kernel CUDA events recorded by the library, jb_profile_*), against the measured HBM
+          copy peak in MEASURED_PEAKS.json.  `pipeline_frac` is A / all kernels of the step.
+`cpu_baseline` the C restatement of jieba-go (oracle/, kind "port": no Go toolchain here) on all host
+          cores over a bounded sample of the same batch; the same sample is a parity check.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    2: dict(kind="freq", hmm=False, name="config2: synthetic corpus sampled from dict frequencies, HMM off"),
+    3: dict(kind="oov", hmm=True, name="config3: OOV-rich synthetic corpus (30% random Han), HMM on"),
+    4: dict(kind="long", hmm=True, name="config4: 10k-rune unpunctuated blocks, HMM on"),
+    5: dict(kind="oov", hmm=True, name="config5: OOV-rich corpus doc-sharded over GPUs, HMM on"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons DURING the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_oracle(sd, emit):
+    from oracle import c_oracle as co
+    pd = co.Dict.from_lines(sd.dict_txt(), 1)
+    hm = co.Hmm()
+    st = np.array(["BMES".index(s) for s in "BMES" for _ in emit[s]], dtype=np.uint8)
+    ru = np.array([c for s in "BMES" for c in emit[s]], dtype=np.uint32)
+    va = np.array([v for s in "BMES" for v in emit[s].values()], dtype=np.float64)
+    hm.set_emit_arrays(st, ru, va)
+    return co, co.Tokenizer(pd, hm)
+
+
+def cpu_sample(text_np, off_np, target_bytes):
+    """Leading whole documents up to ~target_bytes."""
+    d = int(np.searchsorted(off_np, target_bytes, side="right")) - 1
+    d = max(1, min(d, len(off_np) - 1))
+    return text_np[: int(off_np[d])], off_np[: d + 1]
+
+
+def run_cpu_baseline(otk, co, text_np, off_np, hmm, seconds=12.0):
+    cores = co.num_procs()
+    probe_t, probe_o = cpu_sample(text_np, off_np, min(len(text_np), 2_000_000 * max(1, cores // 8)))
+    t0 = time.perf_counter()
+    otk.cut_batch(probe_t, probe_o, hmm, cores)
+    dt = max(1e-4, time.perf_counter() - t0)
+    rate = len(probe_t) / dt
+    st, so = cpu_sample(text_np, off_np, min(len(text_np), int(rate * seconds)))
+    t0 = time.perf_counter()
+    res = otk.cut_batch(st, so, hmm, cores)
+    dt = time.perf_counter() - t0
+    return len(st) / dt / 1e6, cores, st, so, res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--bytes", type=int, default=1_000_000_000, help="bytes per GPU per step")
+    ap.add_argument("--dict-words", type=int, default=349_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import torch
+    from jieba_go_b200 import synth
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path.  The Go toolchain is absent in this image,
+        # so this is the oracle port (C restatement of tokenizer.go), all host threads, bounded sample.
+        if rank != 0:
+            return
+        sd = synth.make_dictionary(n_words=args.dict_words, seed=synth.SEED_BASE)
+        emit = synth.make_emit(sd)
+        co, otk = build_oracle(sd, emit)
+        cores = co.num_procs()
+        sample_bytes = min(args.bytes, 6_000_000 * cores)  # ~1-2 s of all-core work per step
+        text, doc_off = synth.make_corpus(sd, cfg["kind"], sample_bytes, synth.SEED_BASE + args.config, device="cpu")
+        t = text.numpy()
+        off = doc_off.numpy().astype(np.uint64)
+        for _ in range(args.warmup):
+            otk.cut_batch(t, off, cfg["hmm"], cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            otk.cut_batch(t, off, cfg["hmm"], cores)
+        dt = (time.perf_counter() - t0) / max(1, args.steps)
+        v = t.size / dt / 1e6
+        line = {
+            "impl": "reference", "metric": "UTF-8 MB/s segmented", "value": v, "unit": "MB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "bytes_per_step": int(t.size), "hmm": cfg["hmm"], "dict_words": args.dict_words},
+            "cpu_baseline": {"value": v, "unit": "MB/s", "cores": cores, "kind": "port",
+                             "sample": "%d B of the workload per step, C restatement of jieba-go (not Go), %d threads" % (t.size, cores)},
+            "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from jieba_go_b200 import _capi
+    from jieba_go_b200.tokenizer import Tokenizer
+
+    sd = synth.make_dictionary(n_words=args.dict_words, seed=synth.SEED_BASE)
+    emit = synth.make_emit(sd)
+    tk = Tokenizer.from_dict_text(sd.dict_txt(), 1, emit, device=local_rank, max_batch_bytes=(1 << 31) - (2 << 20))
+    L = _capi.lib()
+    # each rank cuts its own shard (documents are independent; no collective on the data path)
+    text, doc_off = synth.make_corpus(sd, cfg["kind"], args.bytes, synth.SEED_BASE + args.config + 1000 * rank, device=dev)
+    nbytes = text.numel()
+    ndocs = doc_off.numel() - 1
+    cap = nbytes // 3 + 4096
+    d_start = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_end = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_dto = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+    d_nt = torch.zeros(2, dtype=torch.int64, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    hmm = cfg["hmm"]
+
+    def step():
+        tk.cut_device(text, doc_off, hmm, d_start, d_end, d_dto, d_nt, stream=stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+    stream.synchronize()
+    n_tok, status = d_nt.tolist()
+    assert status == 0, "pipeline status %d" % status
+    assert n_tok <= cap, "token capacity too small"
+
+    import ctypes as C
+    L.jb_profile_enable(tk.handle, 1)
+    ms = (C.c_double * L.jb_profile_num_kernels())()
+    nsteps = C.c_uint64()
+    L.jb_profile_read(tk.handle, ms, C.byref(nsteps), 1)
+    sampler = ClockSampler(local_rank)
+    launches0 = L.jb_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+    stream.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    launches = L.jb_kernel_launch_count() - launches0
+    t_ms = ev0.elapsed_time(ev1)
+    L.jb_profile_read(tk.handle, ms, C.byref(nsteps), 1)
+    L.jb_profile_enable(tk.handle, 0)
+    kern_ms = {L.jb_profile_kernel_name(i).decode(): ms[i] / max(1, nsteps.value) for i in range(len(ms))}
+
+    # ---- e2e: host buffers in, host arrays out, copies inside the timed region -------------------
+    e2e = None
+    if not args.no_e2e:
+        h_text = text.cpu().pin_memory()
+        h_off = doc_off.cpu().numpy().astype(np.uint64)
+        h_np = h_text.numpy()
+        e_steps = max(2, min(args.steps, 3))
+        tk.cut_batch(h_np, h_off, hmm)  # warm-up (workspace allocation)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            r = tk.cut_batch(h_np, h_off, hmm)
+        torch.cuda.synchronize(dev)
+        e_dt = (time.perf_counter() - t0) / e_steps
+        assert len(r[0]) == n_tok
+        e2e = (e_dt, nbytes + 8 * (ndocs + 1), 8 * n_tok + 8 * (ndocs + 1))
+        del h_text
+
+    # ---- reductions over ranks (max time, total bytes) ---------------------------------------------
+    t_all = torch.tensor([t_ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
+    b_all = torch.tensor([float(nbytes), float(n_tok)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b_all, op=dist.ReduceOp.SUM)
+    t_ms_max, e_dt_max = t_all.tolist()
+    tot_bytes, tot_tok = b_all.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_step = t_ms_max / args.steps
+        value = tot_bytes / (ms_step * 1e-3) / 1e6
+        A = nbytes + 8 * n_tok  # algorithmic bytes of one launch on this rank
+        dom = max(kern_ms, key=lambda k: kern_ms[k])
+        t_k = sum(kern_ms.values())
+        roof = {
+            "bound": "hbm", "kernel": dom, "achieved": A / (kern_ms[dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": A / (kern_ms[dom] * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": A,
+            "pipeline_achieved": A / (t_k * 1e-3) / 1e9, "pipeline_frac": A / (t_k * 1e-3) / 1e9 / peak,
+            "kernel_ms": {k: round(v, 4) for k, v in kern_ms.items()},
+        }
+        line = {
+            "metric": "UTF-8 MB/s segmented", "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "bytes_per_gpu_per_step": nbytes, "docs_per_gpu": ndocs, "tokens_per_gpu": n_tok,
+                       "hmm": hmm, "dict_words": args.dict_words, "l2": "inputs (%.0f MB) larger than L2, no flush" % (nbytes / 1e6),
+                       "sharding": "documents, one shard per GPU, no collective"},
+            "roofline": roof, "clocks": clocks, "gpu_launches": int(launches),
+        }
+        if e2e:
+            line["e2e"] = {"value": tot_bytes / e_dt_max / 1e6, "unit": "MB/s", "h2d_bytes_per_step": int(e2e[1]),
+                           "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": e_dt_max * 1e3}
+        if not args.no_cpu:
+            co, otk = build_oracle(sd, emit)
+            t_np = text.cpu().numpy()
+            o_np = doc_off.cpu().numpy().astype(np.uint64)
+            mbps, cores, st, so, res = run_cpu_baseline(otk, co, t_np, o_np, hmm)
+            # the same sample is the parity check
+            g = tk.cut_batch(st, so, hmm)
+            same = np.array_equal(g[0], res[0]) and np.array_equal(g[1], res[1]) and np.array_equal(g[2], res[3])
+            line["cpu_baseline"] = {"value": mbps, "unit": "MB/s", "cores": cores, "kind": "port",
+                                    "sample": "first %d B (%d docs) of the batch, C restatement of jieba-go (not Go), %d threads" % (
+                                        len(st), len(so) - 1, cores)}
+            line["parity"] = "bit-exact on the cpu_baseline sample" if same else "MISMATCH on the cpu_baseline sample"
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -163,6 +163,12 @@ int jb_set_candidates_per_slot(jb_tokenizer* tk, double per_slot);
 
 /* ---- introspection (tests / bench) ------------------------------------------------------ */
 uint64_t jb_kernel_launch_count(void); /* kernels launched by this library in this process */
+/* Per-kernel timing of jb_cut_device with CUDA events on the launching stream (bench.py's roofline).
+ * jb_profile_read sums milliseconds per kernel over the steps since the last reset. */
+int jb_profile_enable(jb_tokenizer* tk, int on);
+int jb_profile_num_kernels(void);
+const char* jb_profile_kernel_name(int i);
+int jb_profile_read(jb_tokenizer* tk, double* ms_total, uint64_t* steps, int reset);
 /* Debug: per-rune route values R[i] = (end, proba) of one Han block (maxIndexProba of dagProba[i]) */
 int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, uint32_t* best_end,
                    double* best_proba, uint64_t cap);

@@ -63,6 +63,10 @@ SYMBOLS = {
     "jb_cut_device": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P, _P, C.c_uint64, _P, _P, _P]),
     "jb_set_candidates_per_slot": (C.c_int, [_P, C.c_double]),
     "jb_kernel_launch_count": (C.c_uint64, []),
+    "jb_profile_enable": (C.c_int, [_P, C.c_int]),
+    "jb_profile_num_kernels": (C.c_int, []),
+    "jb_profile_kernel_name": (C.c_char_p, [C.c_int]),
+    "jb_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "jb_debug_route": (C.c_int, [_P, C.c_char_p, C.c_uint64, _P, _P, C.c_uint64]),
     "jb_debug_lookup": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.POINTER(C.c_double)]),
 }

@@ -433,6 +433,29 @@ int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, cons
   return JB_OK;
 }
 
+int jb_profile_enable(jb_tokenizer* tk, int on) {
+  if (!tk) return JB_EINVAL;
+  std::lock_guard<std::mutex> g(tk->dev_mu);
+  tk->dev_ws.ws.prof = on != 0;
+  return JB_OK;
+}
+int jb_profile_num_kernels(void) { return kNumProfKernels; }
+const char* jb_profile_kernel_name(int i) { return (i >= 0 && i < kNumProfKernels) ? kProfKernelNames[i] : ""; }
+int jb_profile_read(jb_tokenizer* tk, double* ms_total, uint64_t* steps, int reset) {
+  if (!tk || !ms_total) return JB_EINVAL;
+  std::lock_guard<std::mutex> g(tk->dev_mu);
+  Workspace& ws = tk->dev_ws.ws;
+  cudaSetDevice(tk->device);
+  profile_collect(ws);
+  for (int i = 0; i < kNumProfKernels; i++) ms_total[i] = ws.prof_ms[i];
+  if (steps) *steps = ws.prof_steps;
+  if (reset) {
+    for (int i = 0; i < kNumProfKernels; i++) ws.prof_ms[i] = 0;
+    ws.prof_steps = 0;
+  }
+  return JB_OK;
+}
+
 int jb_debug_lookup(jb_tokenizer* tk, const uint8_t* key, uint64_t len, double* w) {
   if (!tk || !key || !len) return JB_EINVAL;
   std::vector<uint32_t> runes;

@@ -949,46 +949,63 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const JbTables T, const W
 // ------------------------------------------------------------------------------------------
 // Token ranking: start/end bitmaps -> (start,end) arrays in document order, doc-relative.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRankWords) k_rank_count(const uint32_t* __restrict__ s_bits, uint32_t nwords, uint32_t* __restrict__ cnt) {
-  __shared__ uint32_t red[kRankWords / 32];
+__global__ void __launch_bounds__(kRankWords) k_rank_count(const uint32_t* __restrict__ s_bits, const uint32_t* __restrict__ e_bits,
+                                                          uint32_t nwords, uint32_t* __restrict__ cnt) {
+  __shared__ uint32_t red[2][kRankWords / 32];
   uint32_t w = blockIdx.x * kRankWords + threadIdx.x;
-  uint32_t c = w < nwords ? __popc(s_bits[w]) : 0;
+  uint32_t c = w < nwords ? __popc(s_bits[w]) : 0, e = w < nwords ? __popc(e_bits[w]) : 0;
   c = __reduce_add_sync(FULL, c);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  e = __reduce_add_sync(FULL, e);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = c;
+    red[1][threadIdx.x >> 5] = e;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) cnt[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+  if (threadIdx.x == 0) {
+    cnt[2 * blockIdx.x] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    cnt[2 * blockIdx.x + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  }
 }
 
 __global__ void __launch_bounds__(1024) k_rank_scan(uint32_t* __restrict__ cnt, uint32_t nt, uint32_t* __restrict__ counters,
                                                     uint64_t* __restrict__ d_n_tokens, const uint32_t* __restrict__ doc_off32,
                                                     uint64_t ndocs, uint32_t n, uint64_t* __restrict__ doc_tok, uint64_t tok_base) {
-  __shared__ uint32_t part[1024];
+  __shared__ uint32_t part[2][1024];
   __shared__ uint32_t total_s;
   const int tid = threadIdx.x;
   const uint32_t per = (nt + 1023) / 1024;
   const uint32_t lo = min(nt, tid * per), hi = min(nt, lo + per);
-  uint32_t acc = 0;
-  for (uint32_t t = lo; t < hi; t++) acc += cnt[t];
-  part[tid] = acc;
+  uint32_t acc = 0, acce = 0;
+  for (uint32_t t = lo; t < hi; t++) {
+    acc += cnt[2 * t];
+    acce += cnt[2 * t + 1];
+  }
+  part[0][tid] = acc;
+  part[1][tid] = acce;
   __syncthreads();
   if (tid == 0) {
-    uint32_t a = 0;
+    uint32_t a = 0, e = 0;
     for (int j = 0; j < 1024; j++) {
-      uint32_t v = part[j];
-      part[j] = a;
+      uint32_t v = part[0][j], ve = part[1][j];
+      part[0][j] = a;
+      part[1][j] = e;
       a += v;
+      e += ve;
     }
     total_s = a;
+    if (a != e) atomicOr(&counters[C_STATUS], 4u);  // every token has one start and one end bit
     counters[C_N_TOKENS] = a;
     d_n_tokens[0] = a;
     d_n_tokens[1] = counters[C_STATUS];
   }
   __syncthreads();
-  uint32_t a = part[tid];
+  uint32_t a = part[0][tid], e = part[1][tid];
   for (uint32_t t = lo; t < hi; t++) {
-    uint32_t v = cnt[t];
-    cnt[t] = a;
+    uint32_t v = cnt[2 * t], ve = cnt[2 * t + 1];
+    cnt[2 * t] = a;
+    cnt[2 * t + 1] = e;
     a += v;
+    e += ve;
   }
   // documents that start at or after the end of the text (empty tail documents) and the sentinel
   if (doc_tok) {
@@ -1008,7 +1025,6 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
                                                             uint64_t ndocs, uint32_t* __restrict__ out_start, uint32_t* __restrict__ out_end,
                                                             uint64_t cap, uint64_t* __restrict__ doc_tok, uint64_t tok_base) {
   __shared__ uint32_t sS[kRankWords], sPS[kRankWords], sPE[kRankWords];
-  __shared__ int32_t sLD[kRankWords];
   __shared__ uint32_t wsum[2][kRankWords / 32];
   __shared__ int32_t wmax[kRankWords / 32];
   __shared__ uint32_t s_dpos0;
@@ -1063,8 +1079,7 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
     oe += wsum[1][j];
     om = max(om, wmax[j]);
   }
-  const uint32_t base = tile_base[tile];
-  const uint32_t ps = base + os + is - cs, pe = base + oe + ie - ce;
+  const uint32_t ps = tile_base[2 * tile] + os + is - cs, pe = tile_base[2 * tile + 1] + oe + ie - ce;
   // last doc start strictly before this word (tile-local), or -1
   int32_t prev_ld = __shfl_up_sync(FULL, im, 1);
   if (lane == 0) prev_ld = -1;
@@ -1072,7 +1087,6 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
   sS[tid] = S;
   sPS[tid] = ps;
   sPE[tid] = pe;
-  sLD[tid] = prev_ld;
   __syncthreads();
   const uint32_t dpos0 = s_dpos0;
   uint32_t m = S;
@@ -1189,6 +1203,8 @@ void workspace_free(Workspace& ws) {
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (auto& e : ws.ev)
+    if (e) cudaEventDestroy(e);
   ws = Workspace();
 }
 
@@ -1206,7 +1222,7 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ok = ok && dalloc(ws.wbuf, ntiles * (uint64_t)wpt + 4096);
     ok = ok && dalloc(ws.ends, ntiles * kTileSlots + 8) && dalloc(ws.walks, ntiles * kTileSlots + 8);
     ok = ok && dalloc(ws.tile_sum, ntiles + 8) && dalloc(ws.tile_ctx, ntiles + 8);
-    ok = ok && dalloc(ws.rank_cnt, cap / kRankBytes + 8);
+    ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8));
     if (!ws.counters) ok = ok && dalloc(ws.counters, (uint64_t)C_NUM);
     if (host_staging) ok = ok && dalloc(ws.text, cap + 64);
     if (!ws.out_ntok) ok = ok && dalloc(ws.out_ntok, 2);
@@ -1230,6 +1246,25 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
   return JB_OK;
 }
 
+const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset", "k_split<summary>", "k_tile_scan", "k_split<dag>",
+                                                       "k_route_dp",        "k_walk",           "k_rank_count", "k_rank_scan",
+                                                       "k_rank_scatter"};
+
+void profile_collect(Workspace& ws) {
+  if (!ws.prof || !ws.prof_pending) return;
+  cudaEventSynchronize(ws.ev[kNumProfKernels]);
+  for (int i = 0; i < kNumProfKernels; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ws.ev[i], ws.ev[i + 1]) == cudaSuccess) ws.prof_ms[i] += ms;
+  }
+  ws.prof_steps++;
+  ws.prof_pending = false;
+}
+#define PROF(i)                                    \
+  do {                                             \
+    if (ws.prof) cudaEventRecord(ws.ev[i], st);    \
+  } while (0)
+
 static int g_num_sms = 0;
 
 static bool g_attr_done = false;
@@ -1251,11 +1286,18 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
   const uint32_t nwords = (n + 31) / 32;
   const uint32_t ntiles = (n + kTileBytes - 1) / kTileBytes;
   const uint32_t nrt = (n + kRankBytes - 1) / kRankBytes;
+  if (ws.prof) {
+    profile_collect(ws);
+    for (int i = 0; i <= kNumProfKernels; i++)
+      if (!ws.ev[i]) cudaEventCreate(&ws.ev[i]);
+  }
+  PROF(0);
   cudaMemsetAsync(ws.counters, 0, C_NUM * sizeof(uint32_t), st);
   cudaMemsetAsync(ws.ds_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.s_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.e_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   JB_LAUNCH(k_docstart, (unsigned)((ndocs + 1 + 255) / 256), 256, 0, st, d_doc_off, ndocs, n, ws.doc_off32, ws.ds_bits);
+  PROF(1);
   if (n > 0) {
     SplitArgs sa;
     sa.text = d_text;
@@ -1272,8 +1314,11 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
     sa.tile_ctx = ws.tile_ctx;
     sa.tile_sum = ws.tile_sum;
     JB_LAUNCH(k_split<true>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
+    PROF(2);
     JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles);
+    PROF(3);
     JB_LAUNCH(k_split<false>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
+    PROF(4);
     DpArgs da;
     da.text = d_text;
     da.rec = ws.rec;
@@ -1287,6 +1332,7 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
     if (T.max_delta + 1 <= 8) JB_LAUNCH(k_route_dp<8>, pgrid, kDpThreads, 0, st, da);
     else if (T.max_delta + 1 <= 16) JB_LAUNCH(k_route_dp<16>, pgrid, kDpThreads, 0, st, da);
     else JB_LAUNCH(k_route_dp<32>, pgrid, kDpThreads, 0, st, da);
+    PROF(5);
     WalkArgs wa;
     wa.text = d_text;
     wa.rec = ws.rec;
@@ -1296,11 +1342,18 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
     wa.e_bits = ws.e_bits;
     if (use_hmm) JB_LAUNCH(k_walk<true>, pgrid, kWalkThreads, 0, st, T, wa);
     else JB_LAUNCH(k_walk<false>, pgrid, kWalkThreads, 0, st, T, wa);
-    JB_LAUNCH(k_rank_count, nrt, kRankWords, 0, st, ws.s_bits, nwords, ws.rank_cnt);
+    PROF(6);
+    JB_LAUNCH(k_rank_count, nrt, kRankWords, 0, st, ws.s_bits, ws.e_bits, nwords, ws.rank_cnt);
+  } else {
+    for (int i = 2; i <= 6; i++) PROF(i);
   }
+  PROF(7);
   JB_LAUNCH(k_rank_scan, 1, 1024, 0, st, ws.rank_cnt, n ? nrt : 0u, ws.counters, d_n_tokens, ws.doc_off32, ndocs, n, d_doc_tok_off,
             tok_base);
+  PROF(8);
   if (d_start && d_end) return run_scatter(ws, n, ndocs, d_start, d_end, cap_tokens, d_doc_tok_off, tok_base, st);
+  PROF(9);
+  if (ws.prof) ws.prof_pending = true;
   return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ECUDA;
 }
 
@@ -1311,6 +1364,8 @@ int run_scatter(Workspace& ws, uint32_t n, uint64_t ndocs, uint32_t* d_start, ui
   if (n > 0)
     JB_LAUNCH(k_rank_scatter, nrt, kRankWords, 0, st, ws.s_bits, ws.e_bits, ws.ds_bits, nwords, n, ws.rank_cnt, ws.doc_off32, ndocs,
               d_start, d_end, cap_tokens, d_doc_tok_off, tok_base);
+  PROF(9);
+  if (ws.prof) ws.prof_pending = true;
   return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ECUDA;
 }
 

@@ -28,7 +28,16 @@ enum Counter {
   C_NUM = 8
 };
 
+constexpr int kNumProfKernels = 9;
+extern const char* const kProfKernelNames[kNumProfKernels];
+
 struct Workspace {
+  // per-kernel CUDA-event timing (jb_profile_*): ev[i] is recorded before kernel i, ev[9] after the last
+  bool prof = false;
+  bool prof_pending = false;
+  cudaEvent_t ev[kNumProfKernels + 1] = {};
+  double prof_ms[kNumProfKernels] = {};
+  uint64_t prof_steps = 0;
   // capacity
   uint64_t cap_bytes = 0;
   uint32_t w_per_tile = 0;  // candidate weights reserved per tile
@@ -77,5 +86,6 @@ int run_scatter(Workspace& ws, uint32_t nbytes, uint64_t ndocs, uint32_t* d_star
 int debug_lookup(const JbTables& T, const uint32_t* runes_host, int L, int* kind, double* w);
 
 uint64_t kernel_launch_count();
+void profile_collect(Workspace& ws);
 
 }  // namespace jb
