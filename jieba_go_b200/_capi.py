@@ -62,6 +62,7 @@ SYMBOLS = {
     "jb_result_free": (None, [_P]),
     "jb_cut_device": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P, _P, C.c_uint64, _P, _P, _P]),
     "jb_set_candidates_per_slot": (C.c_int, [_P, C.c_double]),
+    "jb_set_general_only": (C.c_int, [_P, C.c_int]),
     "jb_kernel_launch_count": (C.c_uint64, []),
     "jb_profile_enable": (C.c_int, [_P, C.c_int]),
     "jb_profile_num_kernels": (C.c_int, []),

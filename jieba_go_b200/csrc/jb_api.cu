@@ -45,6 +45,7 @@ struct jb_tokenizer {
   std::vector<void*> dev_allocs;
   uint64_t max_batch = 256ull << 20;
   double w_per_slot = 3.0;
+  int force_general = 0;  // 1: skip the fused fast path (tests / debugging)
   std::mutex mu;
   std::vector<WsSlot*> free_ws;
   WsSlot dev_ws;  // workspace of jb_cut_device (one caller at a time per tokenizer for the device API)
@@ -372,7 +373,7 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
       if (nb) CUDA_TRY(cudaMemcpyAsync(ws.text, text + doc_off[d0], nb, cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, doc_off + d0, (nd + 1) * 8, cudaMemcpyHostToDevice, st));
       rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nb, ws.doc_off64, nd, use_hmm != 0, nullptr, nullptr, 0, ws.out_doc_tok,
-                        res->n_tokens, ws.out_ntok, st);
+                        res->n_tokens, ws.out_ntok, st, tk->force_general != 0);
       if (rc != JB_OK) return done(fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError())));
       uint64_t cnt[2];
       CUDA_TRY(cudaMemcpyAsync(cnt, ws.out_ntok, 16, cudaMemcpyDeviceToHost, st));
@@ -428,11 +429,16 @@ int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, cons
   int rc = workspace_reserve(tk->dev_ws.ws, nbytes, ndocs, tk->w_per_slot, false);
   if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
   rc = run_pipeline(tk->T, tk->dev_ws.ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, d_start, d_end, cap_tokens,
-                    d_doc_tok_off, 0, d_n_tokens, (cudaStream_t)cuda_stream);
+                    d_doc_tok_off, 0, d_n_tokens, (cudaStream_t)cuda_stream, tk->force_general != 0);
   if (rc != JB_OK) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   return JB_OK;
 }
 
+int jb_set_general_only(jb_tokenizer* tk, int on) {
+  if (!tk) return JB_EINVAL;
+  tk->force_general = on != 0;
+  return JB_OK;
+}
 int jb_profile_enable(jb_tokenizer* tk, int on) {
   if (!tk) return JB_EINVAL;
   std::lock_guard<std::mutex> g(tk->dev_mu);
@@ -487,7 +493,7 @@ int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, u
   uint64_t off[2] = {0, nbytes};
   CUDA_TRY(cudaMemcpy(ws.text, han_text, nbytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(ws.doc_off64, off, 16, cudaMemcpyHostToDevice));
-  rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, nullptr, nullptr, 0, ws.out_doc_tok, 0, ws.out_ntok, 0);
+  rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, nullptr, nullptr, 0, ws.out_doc_tok, 0, ws.out_ntok, 0, true);
   CUDA_TRY(cudaDeviceSynchronize());
   // read back records + probabilities and translate slots to rune indexes
   uint64_t ns = (nbytes + 2) / 3 + 2;

@@ -1,0 +1,720 @@
+// Fused tile kernel (fast path) -- see jb_fused.cuh for the contract.
+// Reference functions restated here: Cut/splitText T:151-210, cutNonZh T:289-310, buildDag T:462-497,
+// calcDagProba T:502-548, maxIndexProba T:565-578, findDagPath T:552-562, cutZh T:221-255,
+// viterbi T:668-730, stateTransitionRoute T:736-756, cutHMM T:273-285  (T = /root/reference/tokenizer.go).
+#include "jb_fused.cuh"
+
+#include "../../include/jieba_b200.h"
+
+namespace jb {
+
+#define FULL 0xFFFFFFFFu
+
+// rune-info word per slot
+#define RI_CP(x) ((x) & 0xFFFFu)
+#define RI_PHI(x) (((x) >> 16) & 3u)
+#define RI_CLS(x) (((x) >> 18) & 3u)  // 0 none, 1 Han, 2 other 3-byte rune, 3 3-byte space
+#define RI_DS 0x00100000u             // a document starts at this rune's lead byte
+
+enum : uint32_t { PCL_HAN = 1, PCL_ALNUM = 2, PCL_SPACE = 3, PCL_OTHER = 4, PCL_INVALID = 5 };
+#define PCLS(c, len) (uint8_t)(((c) << 3) | (len))
+
+struct FusedSmem {
+  uint8_t sb[kFtRegion];
+  uint32_t ri[kFtSlots + 8];  // index = local slot + 1 (slot -1 lives at 0)
+  uint32_t dsw[kFtRegion / 32 + 3];
+  uint32_t BND[kFtWords + 1], ALN[kFtWords + 1];
+  uint32_t S[kFtWords + 2], E[kFtWords + 2];
+  uint32_t GS[kFtTileWords + 1], GE[kFtTileWords + 2];
+  uint32_t CW[4];
+  uint32_t HS[kFtSlots / 32 + 1], HE[kFtSlots / 32 + 1];
+  uint32_t cmask[kFtSlots];
+  uint16_t woff[kFtSlots];
+  uint16_t blk[kFtSlots];
+  double wbuf[kFtWCap];
+  double R[kFtSlots + 2];
+  uint8_t wcls[kFtThreads / 32][40];
+  uint32_t nblk, wcnt, overflow;
+};
+
+__device__ __forceinline__ bool f_is_alnum(uint32_t c) { return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u); }
+__device__ __forceinline__ bool f_is_space(uint32_t cp) {
+  if (cp <= 0xFF) return (cp - 9u < 5u) || cp == 0x20 || cp == 0x85 || cp == 0xA0;
+  return cp == 0x1680 || (cp - 0x2000u <= 0xAu) || cp == 0x2028 || cp == 0x2029 || cp == 0x202F || cp == 0x205F || cp == 0x3000;
+}
+__device__ __forceinline__ bool f_is_han(uint32_t cp, const JbTables& T) {
+  if (cp < 0x10000) return (__ldg(T.han_bits + (cp >> 5)) >> (cp & 31)) & 1;
+  for (uint32_t i = 0; i < T.n_supp; i++)
+    if (cp >= T.supp_lo[i] && cp <= T.supp_hi[i]) return true;
+  return false;
+}
+
+struct FCtx {
+  const FusedSmem* s;
+  uint32_t t0, n;
+  // is region index i a document start, or at/after the end of the text?
+  __device__ __forceinline__ bool ds_at(int i) const {
+    int64_t P = (int64_t)t0 - kFtLeft + i;
+    if (P >= (int64_t)n) return true;
+    if (P < 0) return false;
+    return (s->dsw[(i + 16) >> 5] >> ((i + 16) & 31)) & 1;
+  }
+};
+
+// validated length (2..4) of the UTF-8 sequence whose lead byte is at region index i, 0 if ill-formed
+__device__ __forceinline__ int f_seqlen(const FusedSmem& S, const FCtx& cx, int i) {
+  uint32_t b = S.sb[i];
+  int len = 0;
+  if (b >= 0xC2 && b <= 0xDF) len = 2;
+  else if (b >= 0xE0 && b <= 0xEF) len = 3;
+  else if (b >= 0xF0 && b <= 0xF4) len = 4;
+  if (!len || i + len > kFtRegion) return 0;
+  uint32_t b1 = S.sb[i + 1], lo = 0x80, hi = 0xBF;
+  if (b == 0xE0) lo = 0xA0;
+  if (b == 0xED) hi = 0x9F;
+  if (b == 0xF0) lo = 0x90;
+  if (b == 0xF4) hi = 0x8F;
+  if (b1 < lo || b1 > hi || cx.ds_at(i + 1)) return 0;
+  if (len >= 3 && ((S.sb[i + 2] & 0xC0) != 0x80 || cx.ds_at(i + 2))) return 0;
+  if (len == 4 && ((S.sb[i + 3] & 0xC0) != 0x80 || cx.ds_at(i + 3))) return 0;
+  return len;
+}
+__device__ __forceinline__ uint32_t f_decode(const uint8_t* b, int len) {
+  uint32_t b0 = b[0];
+  if (len == 1) return b0;
+  if (len == 2) return ((b0 & 0x1F) << 6) | (b[1] & 0x3F);
+  if (len == 3) return ((b0 & 0x0F) << 12) | ((b[1] & 0x3Fu) << 6) | (b[2] & 0x3F);
+  return ((b0 & 0x07) << 18) | ((b[1] & 0x3Fu) << 12) | ((b[2] & 0x3Fu) << 6) | (b[3] & 0x3F);
+}
+// exact per-byte class under Go's decoding rules (same rules as classify_tile in jb_kernels.cu)
+__device__ uint8_t f_pb_cls(const FusedSmem& S, const FCtx& cx, const JbTables& T, int i) {
+  uint32_t b = S.sb[i];
+  if (b < 0x80) return f_is_alnum(b) ? PCLS(PCL_ALNUM, 1) : (f_is_space(b) ? PCLS(PCL_SPACE, 1) : PCLS(PCL_OTHER, 1));
+  if ((b & 0xC0) == 0x80) {
+    for (int k = 1; k <= 3 && i - k >= 0; k++) {
+      if ((S.sb[i - k] & 0xC0) != 0x80) return f_seqlen(S, cx, i - k) > k ? 0 : PCLS(PCL_INVALID, 1);
+    }
+    return PCLS(PCL_INVALID, 1);
+  }
+  int len = f_seqlen(S, cx, i);
+  if (!len) return PCLS(PCL_INVALID, 1);
+  uint32_t cp = f_decode(&S.sb[i], len);
+  return f_is_han(cp, T) ? PCLS(PCL_HAN, len) : (f_is_space(cp) ? PCLS(PCL_SPACE, len) : PCLS(PCL_OTHER, len));
+}
+
+// Does the non-Han block around tile-local byte q hold an ASCII alnum (cutNonZh T:290-293)?
+// returns 1 yes, 0 no, else (2 | need_fwd<<2 | need_bwd<<3) when the block leaves the staged region.
+__device__ uint32_t f_block_alnum(const uint32_t* BND, const uint32_t* ALN, int q) {
+  int w = q >> 5, b = q & 31;
+  uint32_t lowmask = (b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u);
+  bool found = false;
+  uint32_t m = BND[w] & lowmask;
+  if (m) {
+    int bb = 31 - __clz(m);
+    if (ALN[w] & lowmask & ~((1u << bb) - 1u)) return 1;
+    found = true;
+  } else {
+    if (ALN[w] & lowmask) return 1;
+    for (int ww = w - 1; ww >= 0; --ww) {
+      m = BND[ww];
+      if (m) {
+        int bb = 31 - __clz(m);
+        if (ALN[ww] & ~((1u << bb) - 1u)) return 1;
+        found = true;
+        break;
+      } else if (ALN[ww])
+        return 1;
+    }
+  }
+  uint32_t need = found ? 0u : 4u;
+  uint32_t highmask = ~lowmask;
+  found = false;
+  m = BND[w] & highmask;
+  if (m) {
+    int bb = __ffs(m) - 1;
+    if (ALN[w] & highmask & ((1u << bb) - 1u)) return 1;
+    found = true;
+  } else {
+    if (ALN[w] & highmask) return 1;
+    for (int ww = w + 1; ww < kFtWords; ++ww) {
+      m = BND[ww];
+      if (m) {
+        int bb = __ffs(m) - 1;
+        if (ALN[ww] & ((1u << bb) - 1u)) return 1;
+        found = true;
+        break;
+      } else if (ALN[ww])
+        return 1;
+    }
+  }
+  if (!found) need |= 8u;
+  return need ? (2u | need) : 0u;
+}
+
+__device__ __forceinline__ void f_set(uint32_t* bits, int q) { atomicOr(&bits[q >> 5], 1u << (q & 31)); }
+
+// first set bit of HE at index >= kk, or -1
+__device__ __forceinline__ int f_find_end(const uint32_t* HE, int kk) {
+  int w = kk >> 5;
+  uint32_t m = HE[w] & ~((1u << (kk & 31)) - 1u);
+  for (;;) {
+    if (m) return w * 32 + __ffs(m) - 1;
+    if (++w >= kFtSlots / 32) return -1;
+    m = HE[w];
+  }
+}
+// last set bit of HS at index <= kk, or -1
+__device__ __forceinline__ int f_find_start(const uint32_t* HS, int kk) {
+  int w = kk >> 5, b = kk & 31;
+  uint32_t m = HS[w] & ((b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u));
+  for (;;) {
+    if (m) return w * 32 + 31 - __clz(m);
+    if (--w < 0) return -1;
+    m = HS[w];
+  }
+}
+
+struct FProbe {
+  double w;
+  uint32_t child, meta;
+};
+// keys reachable from the fused path are BMP-only (3-byte runes); long-form entries only for > 8 runes
+__device__ __forceinline__ FProbe f_probe(const JbTables& T, uint32_t h, uint64_t h64, bool inl, uint64_t k0, uint64_t k1, uint32_t L,
+                                          const uint32_t* ri_first) {
+  uint32_t slot = jb_hash_fin(h) & T.hash_mask;
+  FProbe r;
+  r.meta = 0;
+  r.child = 0;
+  r.w = 0;
+  for (;;) {
+    const uint4* ep = reinterpret_cast<const uint4*>(T.entries + slot);
+    uint4 b = __ldg(ep + 1);
+    uint32_t meta = b.w;
+    if (!(meta & JB_E_USED)) return r;
+    if (((meta >> 8) & 0xFF) == L) {
+      uint4 a = __ldg(ep);
+      uint64_t e0 = ((uint64_t)a.y << 32) | a.x, e1 = ((uint64_t)a.w << 32) | a.z;
+      bool hit = false;
+      if (inl) {
+        hit = !(meta & JB_E_LONG) && e0 == k0 && e1 == k1;
+      } else if ((meta & JB_E_LONG) && e0 == h64) {
+        hit = true;
+        for (uint32_t j = 0; j < L; j++)
+          if (__ldg(T.key_blob + e1 + j) != RI_CP(ri_first[j])) {
+            hit = false;
+            break;
+          }
+      }
+      if (hit) {
+        r.w = __longlong_as_double(((long long)b.y << 32) | (long long)b.x);
+        r.child = b.z;
+        r.meta = meta;
+        return r;
+      }
+    }
+    slot = (slot + 1) & T.hash_mask;
+  }
+}
+
+template <bool HMM>
+__global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const FusedArgs A) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  FusedSmem& S = *reinterpret_cast<FusedSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t t0 = tile * (uint32_t)kFtTileBytes;
+  const uint32_t n = A.n;
+  FCtx cx{&S, t0, n};
+
+  // ---- stage bytes + document-start words, clear bit words --------------------------------
+  {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(A.text) & 15) == 0);
+    for (int c = tid; c < kFtRegion / 16; c += kFtThreads) {
+      int64_t P = (int64_t)t0 - kFtLeft + c * 16;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (aligned && P >= 0 && P + 16 <= (int64_t)n) {
+        v = __ldg(reinterpret_cast<const uint4*>(A.text + P));
+      } else if (P + 16 > 0 && P < (int64_t)n) {
+        uint8_t* vb = reinterpret_cast<uint8_t*>(&v);
+        for (int j = 0; j < 16; j++) {
+          int64_t q = P + j;
+          vb[j] = (q >= 0 && q < (int64_t)n) ? __ldg(A.text + q) : 0;
+        }
+      }
+      *reinterpret_cast<uint4*>(&S.sb[c * 16]) = v;
+    }
+    const uint32_t nwords = (n + 31) / 32;
+    for (int j = tid; j < kFtRegion / 32 + 3; j += kFtThreads) {
+      int64_t gw = (int64_t)(t0 / 32) - 1 + j;
+      S.dsw[j] = (gw >= 0 && gw < (int64_t)nwords) ? __ldg(A.ds_bits + gw) : 0;
+    }
+    for (int j = tid; j < kFtWords + 2; j += kFtThreads) {
+      S.S[j] = 0;
+      S.E[j] = 0;
+      if (j <= kFtWords) {
+        S.BND[j] = 0;
+        S.ALN[j] = 0;
+      }
+      if (j <= kFtTileWords + 1) S.GE[j] = 0;
+      if (j <= kFtTileWords) S.GS[j] = 0;
+      if (j < 4) S.CW[j] = 0;
+    }
+    if (tid == 0) {
+      S.nblk = 0;
+      S.wcnt = 0;
+      S.overflow = 0;
+    }
+  }
+  __syncthreads();
+
+  // ---- A: slot-centric decode of 3-byte runes ---------------------------------------------
+  // slot kk (kk = -1 .. kFtSlots-1) owns the rune whose lead byte is at tile-local 3kk-2 .. 3kk
+  for (int s = tid; s <= kFtSlots; s += kFtThreads) {
+    const int i0 = kFtLeft + 3 * (s - 1) - 2;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(S.sb + (i0 & ~3));
+    const uint32_t lo = wp[0], hi = wp[1], sh = (i0 & 3) * 8;
+    const uint32_t x0 = __funnelshift_r(lo, hi, sh), x1 = hi >> sh;
+    uint32_t info = 0;
+    uint32_t mm = (x0 & 0x00F0F0F0u) ^ 0x00E0E0E0u;
+    uint32_t z = (mm - 0x00010101u) & ~mm & 0x00808080u;  // bytes equal to 0xE? (exact: nibble values)
+    while (z) {
+      const uint32_t j = (__ffs(z) - 1) >> 3;
+      z &= z - 1;
+      const uint32_t y = __funnelshift_r(x0, x1, 8 * j);
+      const uint32_t L = y & 0xFF, c1 = (y >> 8) & 0xFF, c2 = (y >> 16) & 0xFF;
+      bool valid = ((y & 0x00C0C000u) == 0x00808000u) && !(L == 0xE0 && c1 < 0xA0) && !(L == 0xED && c1 > 0x9F);
+      if (valid) {
+        const uint32_t cp = ((L & 0xF) << 12) | ((c1 & 0x3F) << 6) | (c2 & 0x3F);
+        const uint32_t cl = f_is_han(cp, T) ? 1u : (f_is_space(cp) ? 3u : 2u);
+        info = cp | (j << 16) | (cl << 18);
+        break;
+      }
+    }
+    S.ri[s] = info;
+  }
+  __syncthreads();
+  // document starts: flag the rune that starts there, kill a "rune" that a boundary cuts through
+  for (int j = tid; j < kFtRegion / 32 + 3; j += kFtThreads) {
+    uint32_t m = S.dsw[j];
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      int q = 32 * j + b - 32;  // tile-local byte of the document start
+      if (q < -4 || q >= kFtTileBytes + kFtHaloBytes) continue;
+      int kk = (q + 5) / 3 - 1;  // floor((q+2)/3) for q >= -5
+      for (int s = kk + 1; s >= kk && s >= 0; --s) {  // s = slot index + 1 of slots kk and kk-1
+        if (s > kFtSlots) continue;
+        uint32_t info = S.ri[s];
+        if (!RI_CLS(info)) continue;
+        int lead = 3 * (s - 1) - 2 + (int)RI_PHI(info);
+        if (lead == q) atomicOr(&S.ri[s], RI_DS);
+        else if (lead < q && q <= lead + 2) {
+          S.ri[s] = 0;
+          if (q >= 0) atomicOr(&S.CW[(q >> 5) >> 5], 1u << ((q >> 5) & 31));
+        }
+      }
+    }
+  }
+  if (tid == 0 && n >= t0 && n - t0 < (uint32_t)(kFtTileBytes + kFtHaloBytes)) f_set(S.BND, (int)(n - t0));  // end of text
+  __syncthreads();
+
+  // ---- B: seams, block boundaries ------------------------------------------------------------
+  for (int base = 0; base < kFtSlots; base += kFtThreads) {
+    const int kk = base + tid;
+    const uint32_t cur = S.ri[kk + 1], prev = S.ri[kk], next = (kk + 1 < kFtSlots) ? S.ri[kk + 2] : 0u;
+    const uint32_t ccl = RI_CLS(cur), pcl = RI_CLS(prev), ncl = RI_CLS(next);
+    const bool seam_prev = !(ccl && pcl && RI_PHI(cur) == RI_PHI(prev));
+    const bool seam_next = !(ccl && ncl && RI_PHI(cur) == RI_PHI(next));
+    const int q = 3 * kk - 2 + (int)RI_PHI(cur);
+    if (seam_prev) {  // something other than back-to-back 3-byte runes: exact per-byte rules for these words
+      int qa = 3 * kk - 5, qb = 3 * kk;
+      if (qa < 0) qa = 0;
+      if (qb >= 0 && qa < kFtWords * 32) {
+        if (qb >= kFtWords * 32) qb = kFtWords * 32 - 1;
+        atomicOr(&S.CW[(qa >> 5) >> 5], 1u << ((qa >> 5) & 31));
+        atomicOr(&S.CW[(qb >> 5) >> 5], 1u << ((qb >> 5) & 31));
+      }
+    }
+    const bool han = ccl == 1, ds = cur & RI_DS;
+    const bool bstart = han && (ds || seam_prev || pcl != 1);
+    bool bend = han && (seam_next || ncl != 1 || (next & RI_DS));
+    if (kk == kFtSlots - 1) bend = false;  // the region ends here: an open block is "long"
+    const bool bnd = ccl && (ds || (han && seam_prev) || (!seam_prev && ((pcl == 1) != han)));
+    if (bnd && q >= 0 && q < kFtWords * 32) f_set(S.BND, q);
+    uint32_t hs = __ballot_sync(FULL, bstart), he = __ballot_sync(FULL, bend);
+    if (lane == 0) {
+      S.HS[kk >> 5] = hs;
+      S.HE[kk >> 5] = he;
+    }
+  }
+  __syncthreads();
+
+  // ---- C: exact per-byte rules on the words that need them (ASCII, 2/4-byte runes, ill-formed) ----
+  for (int g = warp; g < kFtWords; g += kFtThreads / 32) {
+    if (!((S.CW[g >> 5] >> (g & 31)) & 1)) continue;  // warp-uniform
+    const int q = 32 * g + lane, i = q + kFtLeft;
+    const uint8_t c = f_pb_cls(S, cx, T, i);
+    S.wcls[warp][4 + lane] = c;
+    if (lane < 4) S.wcls[warp][lane] = f_pb_cls(S, cx, T, i - 4);
+    __syncwarp();
+    const uint32_t P = t0 + q;
+    const uint32_t cl = c >> 3, len = c & 7;
+    const bool start = c != 0 && P < n;
+    const bool han = cl == PCL_HAN;
+    uint32_t pc = PCL_OTHER;
+    for (int k = 1; k <= 4; k++) {
+      uint8_t c2 = S.wcls[warp][4 + lane - k];
+      if (c2) {
+        pc = c2 >> 3;
+        break;
+      }
+    }
+    __syncwarp();
+    if (start && han && len == 4) atomicOr(&A.counters[C_FLAGS], 1u);  // 4-byte Han: general pipeline redoes the batch
+    const bool dsq = start && (P == 0 || cx.ds_at(i));
+    const bool bnd = start && (dsq || (han != (pc == PCL_HAN)));
+    const bool aln = start && cl == PCL_ALNUM;
+    bool nsa = false, nea = false, gs = false;
+    if (start && !han && q < kFtTileBytes) {
+      if (cl == PCL_ALNUM) {  // alnum run = one token (T:298-299)
+        nsa = dsq || !f_is_alnum(S.sb[i - 1]);
+        nea = P + 1 >= n || cx.ds_at(i + 1) || !f_is_alnum(S.sb[i + 1]);
+      } else if (cl != PCL_SPACE) {  // any other rune is its own token, spaces are skipped (T:301-306)
+        gs = true;
+        f_set(S.GE, q + (int)len - 1);
+      }
+    }
+    uint32_t wb = __ballot_sync(FULL, bnd), wa = __ballot_sync(FULL, aln), w1 = __ballot_sync(FULL, nsa), w2 = __ballot_sync(FULL, nea),
+             w3 = __ballot_sync(FULL, gs);
+    if (lane == 0) {
+      if (wb) atomicOr(&S.BND[g], wb);
+      if (wa) atomicOr(&S.ALN[g], wa);
+      if (g < kFtTileWords) {
+        if (w1) atomicOr(&S.S[g], w1);
+        if (w2) atomicOr(&S.E[g], w2);
+        if (w3) atomicOr(&S.GS[g], w3);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- D: gated single-rune tokens (cutNonZh drops a block without [a-zA-Z0-9], T:290-293) ----
+  // (1) 3-byte non-Han runes in clean words, straight from the slot table
+  for (int base = 0; base < kFtSlots; base += kFtThreads) {
+    const int kk = base + tid;
+    const uint32_t cur = S.ri[kk + 1];
+    if (RI_CLS(cur) != 2) continue;
+    const int q = 3 * kk - 2 + (int)RI_PHI(cur);
+    if (q < 0 || q >= kFtTileBytes) continue;
+    if ((S.CW[(q >> 5) >> 5] >> ((q >> 5) & 31)) & 1) continue;  // that word went through C
+    uint32_t r = f_block_alnum(S.BND, S.ALN, q);
+    if (r == 1) {
+      f_set(S.S, q);
+      f_set(S.E, q + 2);
+    } else if (r & 2) {
+      uint32_t idx = atomicAdd(&A.counters[C_N_DEFER], 1u);
+      if (idx < A.deferred_cap) A.deferred[idx] = make_uint4(t0 + q, 3u, (r >> 2) & 3u, tile);
+      else atomicOr(&A.counters[C_FLAGS], 1u);
+    }
+  }
+  // (2) tokens found by the per-byte pass
+  for (int g = warp; g < kFtTileWords; g += kFtThreads / 32) {
+    const uint32_t gsw = S.GS[g];
+    if (!gsw) continue;
+    if ((gsw >> lane) & 1) {
+      const int q = 32 * g + lane;
+      // its end bit: first GE bit at or after q
+      int w = q >> 5;
+      uint32_t m = S.GE[w] & ~((1u << (q & 31)) - 1u);
+      if (!m) m = S.GE[++w];
+      const int qe = w * 32 + __ffs(m) - 1;
+      uint32_t r = f_block_alnum(S.BND, S.ALN, q);
+      if (r == 1) {
+        f_set(S.S, q);
+        f_set(S.E, qe);
+      } else if (r & 2) {
+        uint32_t idx = atomicAdd(&A.counters[C_N_DEFER], 1u);
+        if (idx < A.deferred_cap) A.deferred[idx] = make_uint4(t0 + q, (uint32_t)(qe - q + 1), (r >> 2) & 3u, tile);
+        else atomicOr(&A.counters[C_FLAGS], 1u);
+      }
+    }
+  }
+  // tile summary for k_tile_scan (same encoding as k_split<true>)
+  if (warp == 0) {
+    int firstw = kFtTileWords, lastw = -1;
+    for (int j = lane; j < kFtTileWords; j += 32)
+      if (S.BND[j]) {
+        firstw = min(firstw, j);
+        lastw = max(lastw, j);
+      }
+    firstw = __reduce_min_sync(FULL, firstw);
+    lastw = __reduce_max_sync(FULL, lastw);
+    bool pre = false, post = false;
+    if (lastw < 0) {
+      for (int j = lane; j < kFtTileWords; j += 32) pre |= S.ALN[j] != 0;
+      post = pre;
+    } else {
+      uint32_t fb = __ffs(S.BND[firstw]) - 1, lb = 31 - __clz(S.BND[lastw]);
+      for (int j = lane; j < kFtTileWords; j += 32) {
+        uint32_t a = S.ALN[j];
+        if (j < firstw) pre |= a != 0;
+        if (j == firstw) pre |= (a & ((1u << fb) - 1u)) != 0;
+        if (j > lastw) post |= a != 0;
+        if (j == lastw) post |= (a & ~((1u << lb) - 1u)) != 0;
+      }
+    }
+    pre = __any_sync(FULL, pre);
+    post = __any_sync(FULL, post);
+    if (lane == 0) A.tile_sum[tile] = (uint8_t)((lastw >= 0 ? 1 : 0) | (pre ? 2 : 0) | (post ? 4 : 0));
+  }
+
+  // ---- E: blocks owned by this tile (start rune's lead byte inside the tile) -------------------
+  for (int base = 0; base < kFtSlots; base += kFtThreads) {
+    const int kk = base + tid;
+    const uint32_t cur = S.ri[kk + 1];
+    const int q = 3 * kk - 2 + (int)RI_PHI(cur);
+    const bool owned = ((S.HS[kk >> 5] >> (kk & 31)) & 1) && q >= 0 && q < kFtTileBytes;
+    uint32_t bm = __ballot_sync(FULL, owned);
+    uint32_t wbase = 0;
+    if (lane == 0 && bm) wbase = atomicAdd(&S.nblk, (uint32_t)__popc(bm));
+    wbase = __shfl_sync(FULL, wbase, 0);
+    if (owned) S.blk[wbase + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)kk;
+  }
+
+  // ---- F: DAG probe (buildDag T:462-497) for every Han slot of an owned, closed block ---------
+  for (int base = 0; base < kFtSlots; base += kFtThreads) {
+    const int kk = base + tid;
+    const uint32_t cur = S.ri[kk + 1];
+    bool act = RI_CLS(cur) == 1;
+    int ke = -1;
+    if (act) {
+      const int ks = f_find_start(S.HS, kk);
+      const int qs = ks < 0 ? -1 : 3 * ks - 2 + (int)RI_PHI(S.ri[ks + 1]);
+      ke = f_find_end(S.HE, kk);
+      act = ks >= 0 && qs >= 0 && qs < kFtTileBytes && ke >= 0;
+    }
+    uint32_t mask = 0, cnt = 0;
+    double wv[4];
+    bool over4 = false;
+    if (act) {
+      const uint32_t r0 = RI_CP(cur);
+      const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));  // termFreq[string(iRune)] (T:468-472)
+      wv[0] = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
+      mask = 1;
+      cnt = 1;
+      uint32_t child = f.w;
+      if (!(f.z & JB_FIRST_GATE)) {
+        uint32_t maxlen = (f.z >> 8) & 0xFF;
+        if (maxlen > (uint32_t)(ke - kk + 1)) maxlen = ke - kk + 1;
+        uint32_t h = jb_hash_init(r0);
+        uint64_t h64 = jb_hash64_step(JB_HASH64_INIT, r0), k0 = r0, k1 = 0;
+        uint32_t L = 1;
+        while (L < maxlen) {  // for j := range textRunes[i:], break on the first missing prefix (T:473-482)
+          const uint32_t rl = RI_CP(S.ri[kk + 1 + L]);
+          if (!((child >> jb_bloom_bit(rl)) & 1)) break;
+          h = jb_hash_step(h, rl);
+          h64 = jb_hash64_step(h64, rl);
+          if (L < 4) k0 |= (uint64_t)rl << (16 * L);
+          else if (L < 8) k1 |= (uint64_t)rl << (16 * (L - 4));
+          L++;
+          FProbe pr = f_probe(T, h, h64, L <= 8, k0, k1, L, &S.ri[kk + 1]);
+          if (!(pr.meta & JB_E_USED)) break;
+          if (pr.meta & JB_E_POS) {
+            mask |= 1u << (L - 1);
+            if (cnt < 4) wv[cnt] = pr.w;
+            else over4 = true;
+            cnt++;
+          }
+          child = pr.child;
+        }
+      }
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    uint32_t gbase = 0;
+    if (lane == 0 && total) gbase = atomicAdd(&S.wcnt, total);
+    gbase = __shfl_sync(FULL, gbase, 0);
+    const uint32_t off = gbase + incl - cnt;
+    if (act) {
+      S.cmask[kk] = mask;
+      S.woff[kk] = (uint16_t)off;
+      if (off + cnt <= (uint32_t)kFtWCap) {
+        if (!over4) {
+          for (uint32_t j = 0; j < cnt; j++) S.wbuf[off + j] = wv[j];
+        } else {  // rare: more than 4 candidates -- walk the chain again and store as we go
+          S.wbuf[off] = wv[0];
+          const uint32_t r0 = RI_CP(cur);
+          uint32_t h = jb_hash_init(r0), L = 1, o = 1;
+          uint64_t h64 = jb_hash64_step(JB_HASH64_INIT, r0), k0 = r0, k1 = 0;
+          while (o < cnt) {
+            const uint32_t rl = RI_CP(S.ri[kk + 1 + L]);
+            h = jb_hash_step(h, rl);
+            h64 = jb_hash64_step(h64, rl);
+            if (L < 4) k0 |= (uint64_t)rl << (16 * L);
+            else if (L < 8) k1 |= (uint64_t)rl << (16 * (L - 4));
+            L++;
+            FProbe pr = f_probe(T, h, h64, L <= 8, k0, k1, L, &S.ri[kk + 1]);
+            if (pr.meta & JB_E_POS) S.wbuf[off + o++] = pr.w;
+          }
+        }
+      } else {
+        S.overflow = 1;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- G: per block: route DP, path walk, HMM -------------------------------------------------
+  const uint32_t nblk = S.nblk;
+  const bool tile_overflow = S.overflow != 0;
+  for (uint32_t b = tid; b < nblk; b += kFtThreads) {
+    const int ks = S.blk[b];
+    const int ke = f_find_end(S.HE, ks);
+    const uint32_t phi = RI_PHI(S.ri[ks + 1]);
+    if (ke < 0 || tile_overflow) {  // long block (or this tile's weights did not fit): general kernels take it
+      uint32_t idx = atomicAdd(&A.counters[C_N_LONG], 1u);
+      if (idx < A.long_cap) A.long_seeds[idx] = t0 + 3 * ks - 2 + phi;
+      else atomicOr(&A.counters[C_FLAGS], 1u);
+      continue;
+    }
+    // calcDagProba (T:502-548) right to left with maxIndexProba (T:565-578): each candidate is compared
+    // with the PREVIOUS candidate; the last one >= its predecessor wins, else the last candidate.
+    for (int k = ke; k >= ks; --k) {
+      uint32_t m = S.cmask[k];
+      const uint32_t o = S.woff[k];
+      double prev = JB_MINF, best_v = 0.0, v = 0.0;
+      uint32_t best_d = 0, d = 0, j = 0;
+      while (m) {
+        d = __ffs(m);
+        m &= m - 1;
+        const double nxt = (k + (int)d > ke) ? 0.0 : S.R[k + d];  // {j, 0.0} when j == len (T:522)
+        v = S.wbuf[o + j] + nxt;                                   // pieceFreq + nextBestPiece.proba (T:529)
+        j++;
+        if (v >= prev) {
+          best_d = d;
+          best_v = v;
+        }
+        prev = v;
+      }
+      if (best_d == 0) {
+        best_d = d;
+        best_v = v;
+      }
+      S.R[k] = best_v;
+      S.cmask[k] = best_d;
+    }
+    // findDagPath (T:552-562) + cutZh (T:221-255)
+    const int qbase = -2 + (int)phi;  // tile-local byte of slot k's lead = 3k + qbase
+    int k = ks;
+    uint32_t run_n = 0;
+    int run_s = 0;
+    double V[4];
+    while (k <= ke) {
+      const uint32_t d = S.cmask[k] & 0xFF;
+      if (HMM && d == 1) {
+        // collect singletons (T:233-234): one Viterbi step per rune (T:688-719)
+        const uint32_t cp = RI_CP(S.ri[k + 1]);
+        const double2* ep = reinterpret_cast<const double2*>(T.emit + (size_t)cp * 4);
+        const double2 ea = __ldg(ep), eb = __ldg(ep + 1);
+        const double em[4] = {ea.x, ea.y, eb.x, eb.y};
+        if (run_n == 0) {
+          run_s = k;
+#pragma unroll
+          for (int s = 0; s < 4; s++) V[s] = T.start[s] + em[s];
+        } else {
+          double W[4];
+          uint32_t code = 0;
+#pragma unroll
+          for (int s = 0; s < 4; s++) {  // stateTransitionRoute (T:736-756): strict > from minFloat, list order
+            const int pa = (s == 0 || s == 3) ? 2 : 0, pb = (s == 0 || s == 3) ? 3 : 1;
+            const double r0 = V[pa] + T.trans[s][0], r1 = V[pb] + T.trans[s][1];
+            double best = JB_MINF;
+            uint32_t from = 0;
+            if (r0 > best) {
+              best = r0;
+              from = 1;
+            }
+            if (r1 > best) {
+              best = r1;
+              from = 2;
+            }
+            W[s] = best + em[s];
+            code |= from << (2 * s);
+          }
+#pragma unroll
+          for (int s = 0; s < 4; s++) V[s] = W[s];
+          S.cmask[k] = 1u | (code << 16);
+        }
+        run_n++;
+      }
+      const bool single = HMM && d == 1;
+      if (!single || k + 1 > ke) {
+        if (HMM && run_n) {
+          // flush the run [run_s, run_s + run_n): viterbi's tail (T:723-729) + cutHMM (T:273-285)
+          const int kl = run_s + (int)run_n - 1;
+          if (run_n == 1) {
+            f_set(S.S, 3 * run_s + qbase);
+            f_set(S.E, 3 * run_s + qbase + 2);
+          } else {
+            int st = V[2] > V[3] ? 2 : 3;
+            int kb = kl;
+            uint32_t plen = 0;
+            for (;;) {  // back-trace; stops early where route.from == "" (T:715-716)
+              const uint32_t r = S.cmask[kb];
+              S.cmask[kb] = (r & ~JB_REC_ES) | (st >= 2 ? JB_REC_ES : 0u);
+              plen++;
+              if (kb == run_s) break;
+              const int c = (r >> (16 + 2 * st)) & 3;
+              if (c == 0) break;
+              st = (st == 0 || st == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
+              kb--;
+            }
+            // path[j] applies to rune j (T:277-283): a short path drops the run's tail
+            const int shift = (int)(run_n - plen);
+            bool prev_es = true;
+            for (uint32_t j2 = 0; j2 < plen; j2++) {
+              const bool es = S.cmask[run_s + shift + j2] & JB_REC_ES;
+              const int qq = 3 * (run_s + (int)j2) + qbase;
+              if (prev_es) f_set(S.S, qq);
+              if (es) f_set(S.E, qq + 2);
+              prev_es = es;
+            }
+          }
+          run_n = 0;
+        }
+        if (!single) {
+          f_set(S.S, 3 * k + qbase);
+          f_set(S.E, 3 * (k + (int)d) + qbase - 1);
+        }
+      }
+      k += d;
+    }
+  }
+  __syncthreads();
+  // ---- H: publish token bits ----------------------------------------------------------------------
+  const uint32_t w0 = t0 / 32;
+  for (int j = tid; j < kFtWords + 1; j += kFtThreads) {
+    const uint32_t sbits = S.S[j], ebits = S.E[j];
+    if (sbits) atomicOr(&A.s_bits[w0 + j], sbits);
+    if (ebits) atomicOr(&A.e_bits[w0 + j], ebits);
+  }
+}
+
+int launch_fused(const JbTables& T, const FusedArgs& A, uint32_t ntiles, bool hmm, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem));
+    attr_done = true;
+  }
+  if (hmm) k_fused<true><<<ntiles, kFtThreads, sizeof(FusedSmem), st>>>(T, A);
+  else k_fused<false><<<ntiles, kFtThreads, sizeof(FusedSmem), st>>>(T, A);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace jb

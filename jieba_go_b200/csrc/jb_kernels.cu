@@ -12,6 +12,7 @@
 //                   viterbi, cutHMM) -> token start/end bits
 //   k_rank_*        bitmap rank + scatter: token offsets in document order (the appends of Cut)
 #include "jb_kernels.cuh"
+#include "jb_fused.cuh"
 
 #include <stdio.h>
 
@@ -202,6 +203,9 @@ struct SplitArgs {
   uint32_t* counters;
   const uint8_t* tile_ctx;
   uint8_t* tile_sum;
+  const uint8_t* tile_dirty;
+  int mode;  // 0: whole general pipeline; 1: DAG records only, on tiles overlapped by a long block;
+             // 2: whole general pipeline, but only if the batch was flagged for it (C_FLAGS bit0)
 };
 
 // Does the non-Han block around tile-local byte `pos` contain an ASCII alnum?  (cutNonZh's
@@ -322,6 +326,9 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
   const uint32_t tile = blockIdx.x;
   const uint32_t t0 = tile * (uint32_t)kTileBytes;
   const uint32_t n = A.n;
+  if (A.mode == 2 && !(A.counters[C_FLAGS] & 1u)) return;
+  if (A.mode == 1 && !A.tile_dirty[tile]) return;
+  const bool dag_only = A.mode == 1;
   classify_tile<kSplitThreads>(S.t, A.text, n, A.ds_bits, t0, T);
   TileCtx cx{&S.t, t0, n};
   const int NW = kTileBytes / 32;
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
     return;
   }
   // ---- cutNonZh gating: other-rune tokens survive only if their block has an alnum ---------
-  const uint8_t ctx = A.tile_ctx[tile];
+  const uint8_t ctx = dag_only ? 0 : A.tile_ctx[tile];
   const bool fwd_in = ctx & 1, bwd_in = ctx & 2;
   for (int g = warp; g < NW; g += kSplitThreads / 32) {
     uint32_t so = S.NSO[g];
@@ -423,8 +430,8 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
   for (int j = tid; j < NW + 1; j += kSplitThreads) {
     uint32_t sbits = j < NW ? (S.NSA[j] | S.NSO[j]) : 0;
     uint32_t ebits = (j < NW ? S.NEA[j] : 0) | S.NEO[j];
-    if (sbits) atomicOr(&A.s_bits[w0 + j], sbits);
-    if (ebits) atomicOr(&A.e_bits[w0 + j], ebits);
+    if (sbits && !dag_only) atomicOr(&A.s_bits[w0 + j], sbits);
+    if (ebits && !dag_only) atomicOr(&A.e_bits[w0 + j], ebits);
   }
   // ---- Han slots: block start/end flags and the DAG probe (buildDag, tokenizer.go:462-497) ----
   const uint32_t slot0 = tile * (uint32_t)kTileSlots;
@@ -554,7 +561,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
         }
       }
       A.rec[k] = mask | (bstart ? JB_REC_START : 0u);
-      if (bend) {
+      if (bend && !dag_only) {
         uint32_t e = atomicAdd(&S.n_ends_local, 1u);
         uint32_t wend = min(excl + cnt, cap + 1024u);
         S.ends_local[e] = make_uint2(k, (uint32_t)(tile * (uint64_t)A.w_per_tile) + wend);
@@ -640,6 +647,8 @@ struct DpArgs {
   uint2* walks;
   uint32_t* counters;
   double* dbg_proba;
+  int count_idx, cursor_idx;  // which counters hold the block count and the work cursor
+  int require_flag;           // run only if C_FLAGS bit0 is set
 };
 
 __device__ __forceinline__ uint32_t lead_of_slot(const uint8_t* __restrict__ text, uint32_t k) {
@@ -651,13 +660,14 @@ __device__ __forceinline__ uint32_t lead_of_slot(const uint8_t* __restrict__ tex
 __device__ __forceinline__ uint32_t han_len(uint8_t lead) { return lead >= 0xF0 ? 4u : 3u; }
 
 constexpr int kDpThreads = 128;
-constexpr int kQueueBatch = 256;
+constexpr int kQueueBatch = 32;
 
 template <int RING>
 __global__ void __launch_bounds__(kDpThreads) k_route_dp(const DpArgs A) {
   __shared__ double ring[RING * kDpThreads];
   const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t nblocks = A.counters[C_N_ENDS];
+  if (A.require_flag && !(A.counters[C_FLAGS] & 1u)) return;
+  const uint32_t nblocks = A.counters[A.count_idx];
   uint32_t qh = 0, qt = 0;
   bool exhausted = false, active = false;
   uint32_t k = 0, wp = 0, grp = 0, idx = 0, pend = 0;
@@ -666,7 +676,7 @@ __global__ void __launch_bounds__(kDpThreads) k_route_dp(const DpArgs A) {
     if (need && !exhausted) {
       if (qh == qt) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&A.counters[C_CUR_DP], (uint32_t)kQueueBatch);
+        if (lane == 0) base = atomicAdd(&A.counters[A.cursor_idx], (uint32_t)kQueueBatch);
         base = __shfl_sync(FULL, base, 0);
         if (base >= nblocks) exhausted = true;
         else {
@@ -763,6 +773,7 @@ struct WalkArgs {
   uint32_t* counters;
   uint32_t* s_bits;
   uint32_t* e_bits;
+  int count_idx, cursor_idx, require_flag;
 };
 
 __device__ __forceinline__ void set_bit(uint32_t* bits, uint32_t p) { atomicOr(&bits[p >> 5], 1u << (p & 31)); }
@@ -840,7 +851,8 @@ constexpr int kWalkThreads = 128;
 template <bool HMM>
 __global__ void __launch_bounds__(kWalkThreads) k_walk(const JbTables T, const WalkArgs A) {
   const int lane = threadIdx.x & 31;
-  const uint32_t nblocks = A.counters[C_N_ENDS];
+  if (A.require_flag && !(A.counters[C_FLAGS] & 1u)) return;
+  const uint32_t nblocks = A.counters[A.count_idx];
   uint32_t qh = 0, qt = 0;
   bool exhausted = false, active = false;
   uint32_t k = 0, pend = 0, kvend = 0, pcur = 0;
@@ -851,7 +863,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const JbTables T, const W
     if (need && !exhausted) {
       if (qh == qt) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&A.counters[C_CUR_WALK], (uint32_t)kQueueBatch);
+        if (lane == 0) base = atomicAdd(&A.counters[A.cursor_idx], (uint32_t)kQueueBatch);
         base = __shfl_sync(FULL, base, 0);
         if (base >= nblocks) exhausted = true;
         else {
@@ -1120,6 +1132,92 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// Helpers around the fused fast path (jb_fused.cu)
+// ------------------------------------------------------------------------------------------
+// gated non-Han tokens whose block left the tile: keep them iff the scan found an alnum on an open side
+__global__ void k_resolve_deferred(const uint4* __restrict__ deferred, const uint32_t* __restrict__ counters, uint32_t cap,
+                                   const uint8_t* __restrict__ ctx, uint32_t* __restrict__ s_bits, uint32_t* __restrict__ e_bits) {
+  uint32_t nd = min(counters[C_N_DEFER], cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += gridDim.x * blockDim.x) {
+    uint4 d = deferred[i];
+    uint8_t c = ctx[d.w];
+    if (((d.z & 1u) && (c & 1)) || ((d.z & 2u) && (c & 2))) {
+      atomicOr(&s_bits[d.x >> 5], 1u << (d.x & 31));
+      uint32_t q = d.x + d.y - 1;
+      atomicOr(&e_bits[q >> 5], 1u << (q & 31));
+    }
+  }
+}
+
+// One warp per long block: walk forward over back-to-back 3-byte Han runes to find the block's last
+// rune, mark the split tiles it overlaps.  (A 4-byte Han rune flags the whole batch elsewhere.)
+__global__ void k_long_extent(const JbTables T, const uint8_t* __restrict__ text, uint32_t n, const uint32_t* __restrict__ ds_bits,
+                              const uint32_t* __restrict__ seeds, uint32_t cap, const uint32_t* __restrict__ counters,
+                              uint2* __restrict__ ends, uint8_t* __restrict__ dirty) {
+  const uint32_t nl = min(counters[C_N_LONG], cap);
+  const int lane = threadIdx.x & 31;
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = wid; i < nl; i += nw) {
+    const uint32_t P0 = seeds[i];
+    uint32_t cnt = 0;  // runes in the block
+    for (uint32_t it = 0;; it++) {
+      uint32_t P = P0 + 3u * (32u * it + lane);
+      bool ok = P + 2 < n;
+      if (ok) {
+        uint32_t L = text[P], c1 = text[P + 1], c2 = text[P + 2];
+        ok = (L & 0xF0) == 0xE0 && (c1 & 0xC0) == 0x80 && (c2 & 0xC0) == 0x80 && !(L == 0xE0 && c1 < 0xA0) && !(L == 0xED && c1 > 0x9F);
+        if (ok) {
+          uint32_t cp = ((L & 0xF) << 12) | ((c1 & 0x3F) << 6) | (c2 & 0x3F);
+          ok = (__ldg(T.han_bits + (cp >> 5)) >> (cp & 31)) & 1;
+        }
+        // a document boundary at or inside the rune ends the block (the block's own first byte may be one)
+        for (uint32_t j = (it == 0 && lane == 0) ? 1u : 0u; ok && j < 3; j++) {
+          uint32_t q = P + j;
+          if ((ds_bits[q >> 5] >> (q & 31)) & 1) ok = false;
+        }
+      }
+      uint32_t good = __ballot_sync(FULL, ok);
+      if (good != FULL) {
+        cnt = 32u * it + (uint32_t)(__ffs(~good) - 1);
+        break;
+      }
+    }
+    if (cnt == 0) cnt = 1;
+    const uint32_t Plast = P0 + 3u * (cnt - 1);
+    const uint32_t ks = d_slot(P0), ke = d_slot(Plast);
+    if (lane == 0) ends[i] = make_uint2(ke, 0u);
+    for (uint32_t t = ks / kTileSlots + lane; t <= ke / kTileSlots; t += 32) dirty[t] = 1;
+  }
+}
+
+// weight end offset of every long block's last rune (before the DP starts rewriting records)
+__global__ void k_long_wp(uint2* __restrict__ ends, const uint32_t* __restrict__ counters, uint32_t cap, const uint32_t* __restrict__ rec,
+                          const uint32_t* __restrict__ gend) {
+  const uint32_t nl = min(counters[C_N_LONG], cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += gridDim.x * blockDim.x) {
+    const uint32_t k = ends[i].x;
+    uint32_t wp = gend[k >> 5];
+    for (uint32_t j = k + 1; j <= (k | 31u); j++) wp -= __popc(rec[j] & JB_REC_MASK);
+    ends[i].y = wp;
+  }
+}
+
+// the batch was flagged for the general pipeline: forget what the fast path produced
+__global__ void k_fallback_reset(uint32_t* __restrict__ counters, uint32_t* __restrict__ s_bits, uint32_t* __restrict__ e_bits,
+                                 uint32_t nwords) {
+  if (!(counters[C_FLAGS] & 1u)) return;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) {
+    s_bits[i] = 0;
+    e_bits[i] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counters[C_N_ENDS] = 0;
+    counters[C_CUR_DP] = 0;
+    counters[C_CUR_WALK] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // debug: one dictionary lookup through the device tables
 // ------------------------------------------------------------------------------------------
 __global__ void k_debug_lookup(const JbTables T, const uint32_t* runes, int L, int* kind, double* w) {
@@ -1199,7 +1297,7 @@ static bool dalloc(T*& p, uint64_t count) {
 
 void workspace_free(Workspace& ws) {
   void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.rec, ws.gend, ws.wbuf, ws.ends,
-                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
+                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.tile_dirty, ws.long_seeds, ws.deferred, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1221,7 +1319,10 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ok = ok && dalloc(ws.rec, ntiles * kTileSlots + 64) && dalloc(ws.gend, ntiles * (kTileSlots / 32) + 8);
     ok = ok && dalloc(ws.wbuf, ntiles * (uint64_t)wpt + 4096);
     ok = ok && dalloc(ws.ends, ntiles * kTileSlots + 8) && dalloc(ws.walks, ntiles * kTileSlots + 8);
-    ok = ok && dalloc(ws.tile_sum, ntiles + 8) && dalloc(ws.tile_ctx, ntiles + 8);
+    ok = ok && dalloc(ws.tile_sum, ntiles + 8) && dalloc(ws.tile_ctx, ntiles + 8) && dalloc(ws.tile_dirty, ntiles + 8);
+    ws.long_cap = (uint32_t)(cap / 64 + 4096);
+    ws.deferred_cap = (uint32_t)(cap / 64 + 4096);
+    ok = ok && dalloc(ws.long_seeds, (uint64_t)ws.long_cap) && dalloc(ws.deferred, (uint64_t)ws.deferred_cap);
     ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8));
     if (!ws.counters) ok = ok && dalloc(ws.counters, (uint64_t)C_NUM);
     if (host_staging) ok = ok && dalloc(ws.text, cap + 64);
@@ -1246,9 +1347,9 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
   return JB_OK;
 }
 
-const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset", "k_split<summary>", "k_tile_scan", "k_split<dag>",
-                                                       "k_route_dp",        "k_walk",           "k_rank_count", "k_rank_scan",
-                                                       "k_rank_scatter"};
+const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset", "k_fused",      "k_tile_scan+k_resolve_deferred",
+                                                       "long-block kernels", "general pipeline (flagged batches)",
+                                                       "k_rank_count",      "k_rank_scan",  "k_rank_scatter"};
 
 void profile_collect(Workspace& ws) {
   if (!ws.prof || !ws.prof_pending) return;
@@ -1271,7 +1372,7 @@ static bool g_attr_done = false;
 
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t n, const uint64_t* d_doc_off, uint64_t ndocs,
                  bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens, uint64_t* d_doc_tok_off, uint64_t tok_base,
-                 uint64_t* d_n_tokens, cudaStream_t st) {
+                 uint64_t* d_n_tokens, cudaStream_t st, bool force_general) {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1296,9 +1397,11 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
   cudaMemsetAsync(ws.ds_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.s_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.e_bits, 0, ((uint64_t)nwords + 4) * 4, st);
+  if (n > 0 && !force_general) cudaMemsetAsync(ws.tile_dirty, 0, (uint64_t)ntiles + 2, st);
   JB_LAUNCH(k_docstart, (unsigned)((ndocs + 1 + 255) / 256), 256, 0, st, d_doc_off, ndocs, n, ws.doc_off32, ws.ds_bits);
   PROF(1);
   if (n > 0) {
+    const unsigned pgrid = (unsigned)g_num_sms * 8;
     SplitArgs sa;
     sa.text = d_text;
     sa.n = n;
@@ -1313,12 +1416,7 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
     sa.counters = ws.counters;
     sa.tile_ctx = ws.tile_ctx;
     sa.tile_sum = ws.tile_sum;
-    JB_LAUNCH(k_split<true>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
-    PROF(2);
-    JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles);
-    PROF(3);
-    JB_LAUNCH(k_split<false>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
-    PROF(4);
+    sa.tile_dirty = ws.tile_dirty;
     DpArgs da;
     da.text = d_text;
     da.rec = ws.rec;
@@ -1328,11 +1426,6 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
     da.walks = ws.walks;
     da.counters = ws.counters;
     da.dbg_proba = ws.dbg_proba;
-    const unsigned pgrid = (unsigned)g_num_sms * 8;
-    if (T.max_delta + 1 <= 8) JB_LAUNCH(k_route_dp<8>, pgrid, kDpThreads, 0, st, da);
-    else if (T.max_delta + 1 <= 16) JB_LAUNCH(k_route_dp<16>, pgrid, kDpThreads, 0, st, da);
-    else JB_LAUNCH(k_route_dp<32>, pgrid, kDpThreads, 0, st, da);
-    PROF(5);
     WalkArgs wa;
     wa.text = d_text;
     wa.rec = ws.rec;
@@ -1340,19 +1433,80 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
     wa.counters = ws.counters;
     wa.s_bits = ws.s_bits;
     wa.e_bits = ws.e_bits;
-    if (use_hmm) JB_LAUNCH(k_walk<true>, pgrid, kWalkThreads, 0, st, T, wa);
-    else JB_LAUNCH(k_walk<false>, pgrid, kWalkThreads, 0, st, T, wa);
-    PROF(6);
+    auto launch_dp = [&]() {
+      if (T.max_delta + 1 <= 8) JB_LAUNCH(k_route_dp<8>, pgrid, kDpThreads, 0, st, da);
+      else if (T.max_delta + 1 <= 16) JB_LAUNCH(k_route_dp<16>, pgrid, kDpThreads, 0, st, da);
+      else JB_LAUNCH(k_route_dp<32>, pgrid, kDpThreads, 0, st, da);
+    };
+    auto launch_walk = [&]() {
+      if (use_hmm) JB_LAUNCH(k_walk<true>, pgrid, kWalkThreads, 0, st, T, wa);
+      else JB_LAUNCH(k_walk<false>, pgrid, kWalkThreads, 0, st, T, wa);
+    };
+    if (!force_general) {
+      // ---- fast path: one fused kernel; leftovers (long blocks, deferred tokens) to small kernels ----
+      FusedArgs fa;
+      fa.text = d_text;
+      fa.n = n;
+      fa.ds_bits = ws.ds_bits;
+      fa.s_bits = ws.s_bits;
+      fa.e_bits = ws.e_bits;
+      fa.tile_sum = ws.tile_sum;
+      fa.counters = ws.counters;
+      fa.long_seeds = ws.long_seeds;
+      fa.long_cap = ws.long_cap;
+      fa.deferred = ws.deferred;
+      fa.deferred_cap = ws.deferred_cap;
+      launch_fused(T, fa, ntiles, use_hmm, st);
+      g_launches.fetch_add(1);
+      PROF(2);
+      JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles);
+      JB_LAUNCH(k_resolve_deferred, (unsigned)g_num_sms, 256, 0, st, ws.deferred, ws.counters, ws.deferred_cap, ws.tile_ctx, ws.s_bits,
+                ws.e_bits);
+      PROF(3);
+      JB_LAUNCH(k_long_extent, (unsigned)g_num_sms * 4, 256, 0, st, T, d_text, n, ws.ds_bits, ws.long_seeds, ws.long_cap, ws.counters,
+                ws.ends, ws.tile_dirty);
+      sa.mode = 1;
+      JB_LAUNCH(k_split<false>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
+      JB_LAUNCH(k_long_wp, (unsigned)g_num_sms, 256, 0, st, ws.ends, ws.counters, ws.long_cap, ws.rec, ws.gend);
+      da.count_idx = C_N_LONG;
+      da.cursor_idx = C_CUR_LDP;
+      da.require_flag = 0;
+      launch_dp();
+      wa.count_idx = C_N_LONG;
+      wa.cursor_idx = C_CUR_LWALK;
+      wa.require_flag = 0;
+      launch_walk();
+      PROF(4);
+      // ---- batch flagged (4-byte Han rune, list overflow): the general pipeline redoes it -----------
+      JB_LAUNCH(k_fallback_reset, (unsigned)g_num_sms * 4, 256, 0, st, ws.counters, ws.s_bits, ws.e_bits, nwords + 4);
+    } else {
+      PROF(2);
+      PROF(3);
+      PROF(4);
+    }
+    sa.mode = force_general ? 0 : 2;
+    da.count_idx = C_N_ENDS;
+    da.cursor_idx = C_CUR_DP;
+    da.require_flag = force_general ? 0 : 1;
+    wa.count_idx = C_N_ENDS;
+    wa.cursor_idx = C_CUR_WALK;
+    wa.require_flag = force_general ? 0 : 1;
+    JB_LAUNCH(k_split<true>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
+    JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles);
+    JB_LAUNCH(k_split<false>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
+    launch_dp();
+    launch_walk();
+    PROF(5);
     JB_LAUNCH(k_rank_count, nrt, kRankWords, 0, st, ws.s_bits, ws.e_bits, nwords, ws.rank_cnt);
   } else {
-    for (int i = 2; i <= 6; i++) PROF(i);
+    for (int i = 2; i <= 5; i++) PROF(i);
   }
-  PROF(7);
+  PROF(6);
   JB_LAUNCH(k_rank_scan, 1, 1024, 0, st, ws.rank_cnt, n ? nrt : 0u, ws.counters, d_n_tokens, ws.doc_off32, ndocs, n, d_doc_tok_off,
             tok_base);
-  PROF(8);
+  PROF(7);
   if (d_start && d_end) return run_scatter(ws, n, ndocs, d_start, d_end, cap_tokens, d_doc_tok_off, tok_base, st);
-  PROF(9);
+  PROF(8);
   if (ws.prof) ws.prof_pending = true;
   return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ECUDA;
 }
@@ -1364,7 +1518,7 @@ int run_scatter(Workspace& ws, uint32_t n, uint64_t ndocs, uint32_t* d_start, ui
   if (n > 0)
     JB_LAUNCH(k_rank_scatter, nrt, kRankWords, 0, st, ws.s_bits, ws.e_bits, ws.ds_bits, nwords, n, ws.rank_cnt, ws.doc_off32, ndocs,
               d_start, d_end, cap_tokens, d_doc_tok_off, tok_base);
-  PROF(9);
+  PROF(8);
   if (ws.prof) ws.prof_pending = true;
   return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ECUDA;
 }

@@ -25,10 +25,15 @@ enum Counter {
   C_STATUS = 3,    // bit0: candidate-weight buffer overflow
   C_N_TOKENS = 4,
   C_W_NEEDED = 5,  // max weights needed by any tile (to size a retry)
-  C_NUM = 8
+  C_N_LONG = 6,    // Han blocks the fused kernel handed to the general kernels
+  C_N_DEFER = 7,   // gated non-Han tokens waiting for the tile-summary scan
+  C_FLAGS = 8,     // bit0: the batch must be redone by the general pipeline
+  C_CUR_LDP = 9,   // work cursors of the long-block DP / walk
+  C_CUR_LWALK = 10,
+  C_NUM = 16
 };
 
-constexpr int kNumProfKernels = 9;
+constexpr int kNumProfKernels = 8;
 extern const char* const kProfKernelNames[kNumProfKernels];
 
 struct Workspace {
@@ -56,6 +61,11 @@ struct Workspace {
   uint2* walks = nullptr;        // per Han block: (first rune slot, block end byte)
   uint8_t* tile_sum = nullptr;   // per split tile: has-boundary / alnum-before / alnum-after
   uint8_t* tile_ctx = nullptr;   // per split tile: bit0 fwd, bit1 bwd
+  uint8_t* tile_dirty = nullptr; // per split tile: overlapped by a long block (k_split<dag-only> runs there)
+  uint32_t* long_seeds = nullptr;
+  uint32_t long_cap = 0;
+  uint4* deferred = nullptr;
+  uint32_t deferred_cap = 0;
   uint32_t* rank_cnt = nullptr;  // per rank tile: token count, then exclusive prefix
   uint32_t* counters = nullptr;  // Counter
   double* dbg_proba = nullptr;   // optional: selected route value per slot
@@ -75,9 +85,11 @@ void workspace_free(Workspace& ws);
 //   Token (start,end) are written doc-relative into d_start/d_end (up to cap_tokens),
 //   d_doc_tok_off[ndocs+1] gets tok_base + rank, d_n_tokens[0] the batch's token count and
 //   d_n_tokens[1] the status word.
+//   force_general: skip the fused fast path and run the general kernels on everything.
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_doc_off,
                  uint64_t ndocs, bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
-                 uint64_t* d_doc_tok_off, uint64_t tok_base, uint64_t* d_n_tokens, cudaStream_t stream);
+                 uint64_t* d_doc_tok_off, uint64_t tok_base, uint64_t* d_n_tokens, cudaStream_t stream,
+                 bool force_general = false);
 
 // Second phase when d_start/d_end were NULL in run_pipeline (count first, then scatter).
 int run_scatter(Workspace& ws, uint32_t nbytes, uint64_t ndocs, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,

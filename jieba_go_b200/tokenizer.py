@@ -79,6 +79,8 @@ class Tokenizer:
         old, self._h = self._h, h
         if old:
             L.jb_tokenizer_destroy(old)
+        if getattr(self, "_general_only", False):
+            L.jb_set_general_only(self._h, 1)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -93,6 +95,11 @@ class Tokenizer:
             self.close()
         except Exception:
             pass
+
+    def set_general_only(self, on: bool):
+        """Bypass the fused fast path (the general kernels then cut every block); for tests."""
+        self._general_only = bool(on)
+        check(self._L.jb_set_general_only(self._h, int(bool(on))), "jb_set_general_only")
 
     @property
     def handle(self):

@@ -12,18 +12,24 @@ from helpers import c_oracle_tokenizer, emit_arrays, fuzz_docs, pack_docs
 pytestmark = pytest.mark.gpu
 
 
-def _gpu_tokenizer(sd_or_lines, emit, mode=1, **kw):
+PATHS = ["fused", "general"]  # default fast path (fused tile kernel + leftovers) / general kernels only
+
+
+def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="fused", **kw):
     from jieba_go_b200.tokenizer import Tokenizer
     if isinstance(sd_or_lines, (list, tuple)):
         data = "\n".join(sd_or_lines).encode() + b"\n"
     else:
         data = sd_or_lines.dict_txt()
-    return Tokenizer.from_dict_text(data, mode, emit, **kw)
+    tk = Tokenizer.from_dict_text(data, mode, emit, **kw)
+    if path == "general":
+        tk.set_general_only(True)
+    return tk
 
 
-@pytest.fixture(scope="module")
-def kat_tk(kat_lines, kat_emit):
-    return _gpu_tokenizer(kat_lines, kat_emit)
+@pytest.fixture(scope="module", params=PATHS)
+def kat_tk(request, kat_lines, kat_emit):
+    return _gpu_tokenizer(kat_lines, kat_emit, path=request.param)
 
 
 @pytest.fixture(scope="module")
@@ -32,11 +38,11 @@ def synth_pair(small_synth):
     return sd, emit, _gpu_tokenizer(sd, emit), c_oracle_tokenizer(sd, emit)
 
 
-@pytest.fixture(scope="module")
-def medium_pair():
+@pytest.fixture(scope="module", params=PATHS)
+def medium_pair(request):
     sd = synth.make_dictionary(n_words=60000, seed=synth.SEED_BASE + 31, total_freq=1.5e7, max_len=16)
     emit = synth.make_emit(sd, seed=synth.SEED_BASE + 32)
-    return sd, emit, _gpu_tokenizer(sd, emit), c_oracle_tokenizer(sd, emit)
+    return sd, emit, _gpu_tokenizer(sd, emit, path=request.param), c_oracle_tokenizer(sd, emit)
 
 
 def _assert_same(gpu, ora, text=None, off=None):
@@ -134,11 +140,12 @@ def test_route_values_bit_exact(synth_pair):
 
 
 # ---- randomised parity ---------------------------------------------------------------------------
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("mode", [1, 0])
 @pytest.mark.parametrize("hmm", [False, True])
-def test_fuzz_docs(small_synth, mode, hmm):
+def test_fuzz_docs(small_synth, mode, hmm, path):
     sd, emit = small_synth
-    tk = _gpu_tokenizer(sd, emit, mode)
+    tk = _gpu_tokenizer(sd, emit, mode, path=path)
     ora = c_oracle_tokenizer(sd, emit, mode)
     rng = np.random.default_rng(100 + mode)
     docs = fuzz_docs(sd, rng, n_docs=400, max_len=150) + [b"", b"", "甲".encode(), b"\xe4", b"x"]
@@ -156,19 +163,21 @@ def test_corpora(medium_pair, kind, hmm):
     _assert_same(tk.cut_batch(t, off, hmm), ora.cut_batch(t, off, hmm, 8), t, off)
 
 
-def test_unicode_13_vs_15(small_synth):
+@pytest.mark.parametrize("path", PATHS)
+def test_unicode_13_vs_15(small_synth, path):
     sd, emit = small_synth
     t = "鿽鿾鿿𪛞乙".encode()  # U+9FFD..9FFF, U+2A6DE: Han only from Unicode 14/15 on
     for ver in (13, 15):
-        tk = _gpu_tokenizer(sd, emit, 1, unicode_version=ver)
+        tk = _gpu_tokenizer(sd, emit, 1, path=path, unicode_version=ver)
         ora = c_oracle_tokenizer(sd, emit, 1, unicode_version=ver)
         assert tk.cut_offsets(t, True) == ora.cut(t, True)
         assert tk.cut_offsets(t, False) == ora.cut(t, False)
 
 
-def test_batches_and_document_boundaries(synth_pair):
+@pytest.mark.parametrize("path", PATHS)
+def test_batches_and_document_boundaries(synth_pair, path):
     sd, emit, _, ora = synth_pair
-    tk = _gpu_tokenizer(sd, emit, 1, max_batch_bytes=20_000)  # forces many device batches
+    tk = _gpu_tokenizer(sd, emit, 1, path=path, max_batch_bytes=20_000)  # forces many device batches
     text, doc_off = synth.make_corpus(sd, "oov", 300_000, synth.SEED_BASE + 60)
     t = text.numpy()
     # re-cut the same bytes into documents at arbitrary byte positions (splits runes and words)
@@ -208,3 +217,45 @@ def test_device_api(medium_pair):
     assert np.array_equal(d_start[:len(os_)].cpu().numpy().astype(np.uint32), os_)
     assert np.array_equal(d_end[:len(os_)].cpu().numpy().astype(np.uint32), oe)
     assert np.array_equal(d_dto.cpu().numpy().astype(np.uint64), od)
+
+
+# ---- routes specific to the fused fast path -----------------------------------------------------
+def _mixed_corpus(sd, rng, nbytes):
+    """Dictionary words with every kind of interruption the fast path hands over or defers: long
+    unpunctuated blocks, Japanese/Korean runs (gated tokens across tile edges), ASCII, 2- and 4-byte
+    runes, ill-formed bytes, a 4-byte Han rune far into the text."""
+    words = [w for w in sd.words if all(0x4E00 <= ord(c) <= 0x9FA5 for c in w.decode())]
+    parts, size = [], 0
+    kana = "ステーションかきくけこ번역하다".encode()
+    while size < nbytes:
+        r = rng.random()
+        if r < 0.02:      # long block: 400-3000 runes without a separator
+            p = b"".join(words[int(i)] for i in rng.integers(0, len(words), int(rng.integers(150, 1200))))
+        elif r < 0.06:    # long non-Han, non-alnum run (crosses tiles, no alnum => dropped)
+            p = kana * int(rng.integers(5, 200))
+        elif r < 0.10:    # same with one alnum somewhere far away => kept
+            p = kana * int(rng.integers(5, 150)) + b"x" + kana * int(rng.integers(0, 150))
+        elif r < 0.14:
+            p = [" a1b2 ", "é", "€", "\U0001F600", "\n", "\t", "　", "+=", "ＡＢ"][int(rng.integers(0, 9))].encode()
+        elif r < 0.15:
+            p = [b"\xff", b"\xe4\xb8", b"\x80", b"\xf0\x9f"][int(rng.integers(0, 4))]
+        elif r < 0.30:
+            p = ["，", "。", "！", "？", "；"][int(rng.integers(0, 5))].encode()
+        else:
+            p = words[int(rng.integers(0, len(words)))]
+        parts.append(p)
+        size += len(p)
+    return b"".join(parts)
+
+
+@pytest.mark.parametrize("hmm", [False, True])
+def test_fused_handover_routes(medium_pair, hmm):
+    sd, emit, tk, ora = medium_pair
+    rng = np.random.default_rng(77)
+    docs = [_mixed_corpus(sd, rng, 150_000) for _ in range(6)]
+    text, off = pack_docs(docs)
+    _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 8), text, off)
+    # a 4-byte Han rune flags the whole batch for the general pipeline; results must not change
+    docs2 = docs[:2] + ["甲\U00020000乙".encode() + docs[2]] + docs[3:]
+    text, off = pack_docs(docs2)
+    _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 8), text, off)
