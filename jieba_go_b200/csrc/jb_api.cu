@@ -200,7 +200,6 @@ int jb_tokenizer_create(const jb_dict_desc* dict, const jb_hmm_desc* hmm, const 
   memset(&T, 0, sizeof T);
   rc = upload(tk, img.first, &T.first);
   if (rc == JB_OK) rc = upload(tk, img.entries, &T.entries);
-  if (rc == JB_OK) rc = upload(tk, img.key_blob, &T.key_blob);
   if (rc == JB_OK) rc = upload(tk, img.emit, &T.emit);
   if (rc == JB_OK) rc = upload(tk, img.emit_supp_rune, &T.emit_supp_rune);
   if (rc == JB_OK) rc = upload(tk, img.emit_supp, &T.emit_supp);

@@ -25,25 +25,28 @@ struct __attribute__((aligned(16))) JbFirst {
 #define JB_FIRST_GATE 1u
 
 // ---------------------------------------------------------------------------------------
-// Rune-prefix hash: open addressing, linear probing, 32-byte entries (one L2 sector each).
-// Key = exact rune sequence.  Inline form: up to 8 BMP runes packed 16 bits each in k0,k1
-// (Han code units are never 0, so the length is implicit).  Long form (more than 8 runes, or
-// any supplementary-plane rune): k0 = 64-bit hash, k1 = blob offset | length, verified against
-// the key blob.
+// Rune-prefix hash: open addressing, linear probing, 16-byte entries (two per 32-byte L2 sector).
+// A key is stored as a TRIE EDGE: (id of the entry of the key minus its last rune, last rune).
+// Matching a probe is two integer compares and is exact -- no key bytes, no fingerprints -- and it
+// mirrors how buildDag reaches a key: only through all of its prefixes (tokenizer.go:473-482), so a key
+// whose proper prefix is missing is unreachable in the reference too and is simply not stored.
+//   parent id: slot index of the parent entry (< 0x80000000)
+//              0x80000000 | r0   for 2-rune keys whose first rune r0 is in the BMP (first-rune table)
+//              0xC0000000        for 1-rune keys outside the BMP (root)
+//   rb       : bits 0..20 last rune, bits 21..31 an 11-bit Bloom filter of the next rune over the
+//              keys that extend this key by one rune (a miss ends the loop without a memory access)
+//   w        : log(freq) - log(size); -Inf marks a key with freq 0 (prefix-only, tokenizer.go:360)
 // ---------------------------------------------------------------------------------------
-struct __attribute__((aligned(32))) JbEntry {
-  uint64_t k0;
-  uint64_t k1;
-  double w;        // log(freq) - log(size)   (only meaningful when POSITIVE)
-  uint32_t child;  // Bloom of the next rune over keys that extend this key by one rune
-  uint32_t meta;   // bit0 USED, bit1 POSITIVE (freq > 0), bit2 LONG form, bits 8..15 length in runes
+struct __attribute__((aligned(16))) JbEntry {
+  double w;
+  uint32_t parent;
+  uint32_t rb;
 };
-#define JB_E_USED 1u
-#define JB_E_POS 2u
-#define JB_E_LONG 4u
+#define JB_PARENT_EMPTY 0xFFFFFFFFu
+#define JB_PARENT_ROOT 0xC0000000u
+#define JB_PARENT_FIRST(r0) (0x80000000u | (r0))
+#define JB_RB_RUNE(rb) ((rb) & 0x1FFFFFu)
 
-JB_HD uint32_t jb_hash_init(uint32_t r0) { return (r0 ^ 0x811C9DC5u) * 0x01000193u; }
-JB_HD uint32_t jb_hash_step(uint32_t h, uint32_t r) { return (h ^ r) * 0x01000193u + 0x9E3779B9u; }
 JB_HD uint32_t jb_hash_fin(uint32_t h) {
   h ^= h >> 15;
   h *= 0x2C1B3C6Du;
@@ -52,15 +55,14 @@ JB_HD uint32_t jb_hash_fin(uint32_t h) {
   h ^= h >> 15;
   return h;
 }
-JB_HD uint32_t jb_bloom_bit(uint32_t r) { return ((r * 0x9E3779B1u) >> 27) & 31u; }
-// second, independent 64-bit hash used as the long-form key tag
-JB_HD uint64_t jb_hash64_step(uint64_t h, uint32_t r) {
-  h ^= r;
-  h *= 0x100000001B3ull;
-  h ^= h >> 29;
-  return h;
+JB_HD uint32_t jb_hash_edge(uint32_t parent, uint32_t rune) { return jb_hash_fin((parent * 0x9E3779B1u) ^ (rune * 0x85EBCA6Bu)); }
+JB_HD uint32_t jb_bloom_bit(uint32_t r) { return ((r * 0x9E3779B1u) >> 27) & 31u; }  // first-rune table, 32 bits
+JB_HD uint32_t jb_bloom11(uint32_t r) {                                                // hash entries, 11 bits
+  uint32_t b = (r * 0x9E3779B1u) >> 28;
+  return b >= 11u ? b - 5u : b;
 }
-#define JB_HASH64_INIT 0xCBF29CE484222325ull
+// +/-Inf test on the bits (w is -Inf exactly for freq-0 keys)
+JB_HD bool jb_w_positive(double w) { return w > -1.0e308; }
 
 // ---------------------------------------------------------------------------------------
 // Per-slot record (uint32), slot(p) = floor((p+2)/3) for the lead byte p of a Han rune: every
@@ -80,11 +82,29 @@ JB_HD uint64_t jb_hash64_step(uint64_t h, uint32_t r) {
 
 #define JB_MAX_SUPP_RANGES 16
 
+#if defined(__CUDACC__)
+// One trie-edge lookup: termFreq[prefix + rune] where `parent` identifies termFreq[prefix].
+// Returns the slot (>= 0) and fills w / rb, or -1 when the key is missing.  One 16-byte load per step.
+__device__ __forceinline__ int jb_probe_edge(const JbEntry* __restrict__ entries, uint32_t mask, uint32_t parent, uint32_t rune,
+                                             double* w, uint32_t* rb) {
+  uint32_t slot = jb_hash_edge(parent, rune) & mask;
+  for (;;) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(entries + slot));
+    if (e.z == JB_PARENT_EMPTY) return -1;
+    if (e.z == parent && JB_RB_RUNE(e.w) == rune) {
+      *w = __longlong_as_double(((long long)e.y << 32) | (long long)e.x);
+      *rb = e.w;
+      return (int)slot;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+#endif
+
 struct JbTables {
   const JbFirst* first;        // [65536]
   const JbEntry* entries;      // [hash_cap]
   uint32_t hash_mask;          // hash_cap - 1
-  const uint32_t* key_blob;    // code points of long-form keys
   const double* emit;          // [65536][4] B,M,E,S; missing = JB_MINF (tokenizer.go:690-692)
   const uint32_t* emit_supp_rune;  // sorted supplementary-plane runes with an emission
   const double* emit_supp;         // [n][4]

@@ -30,11 +30,13 @@ struct FusedSmem {
   uint32_t HS[kFtSlots / 32 + 1], HE[kFtSlots / 32 + 1];
   uint32_t cmask[kFtSlots];
   uint16_t woff[kFtSlots];
-  uint16_t blk[kFtSlots];
+  uint16_t blk[kFtMaxBlocks];      // owned blocks: first slot
+  int16_t blk_end[kFtMaxBlocks];   //               last slot, or -1 when the block does not end inside the region
   double wbuf[kFtWCap];
   double R[kFtSlots + 2];
   uint8_t wcls[kFtThreads / 32][40];
   uint32_t nblk, wcnt, overflow;
+  int first_ks, act_limit;
 };
 
 __device__ __forceinline__ bool f_is_alnum(uint32_t c) { return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u); }
@@ -174,48 +176,6 @@ __device__ __forceinline__ int f_find_start(const uint32_t* HS, int kk) {
   }
 }
 
-struct FProbe {
-  double w;
-  uint32_t child, meta;
-};
-// keys reachable from the fused path are BMP-only (3-byte runes); long-form entries only for > 8 runes
-__device__ __forceinline__ FProbe f_probe(const JbTables& T, uint32_t h, uint64_t h64, bool inl, uint64_t k0, uint64_t k1, uint32_t L,
-                                          const uint32_t* ri_first) {
-  uint32_t slot = jb_hash_fin(h) & T.hash_mask;
-  FProbe r;
-  r.meta = 0;
-  r.child = 0;
-  r.w = 0;
-  for (;;) {
-    const uint4* ep = reinterpret_cast<const uint4*>(T.entries + slot);
-    uint4 b = __ldg(ep + 1);
-    uint32_t meta = b.w;
-    if (!(meta & JB_E_USED)) return r;
-    if (((meta >> 8) & 0xFF) == L) {
-      uint4 a = __ldg(ep);
-      uint64_t e0 = ((uint64_t)a.y << 32) | a.x, e1 = ((uint64_t)a.w << 32) | a.z;
-      bool hit = false;
-      if (inl) {
-        hit = !(meta & JB_E_LONG) && e0 == k0 && e1 == k1;
-      } else if ((meta & JB_E_LONG) && e0 == h64) {
-        hit = true;
-        for (uint32_t j = 0; j < L; j++)
-          if (__ldg(T.key_blob + e1 + j) != RI_CP(ri_first[j])) {
-            hit = false;
-            break;
-          }
-      }
-      if (hit) {
-        r.w = __longlong_as_double(((long long)b.y << 32) | (long long)b.x);
-        r.child = b.z;
-        r.meta = meta;
-        return r;
-      }
-    }
-    slot = (slot + 1) & T.hash_mask;
-  }
-}
-
 template <bool HMM>
 __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const FusedArgs A) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -263,6 +223,8 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
       S.nblk = 0;
       S.wcnt = 0;
       S.overflow = 0;
+      S.first_ks = kFtSlots;
+      S.act_limit = -1;
     }
   }
   __syncthreads();
@@ -478,103 +440,126 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
     uint32_t wbase = 0;
     if (lane == 0 && bm) wbase = atomicAdd(&S.nblk, (uint32_t)__popc(bm));
     wbase = __shfl_sync(FULL, wbase, 0);
-    if (owned) S.blk[wbase + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)kk;
-  }
-
-  // ---- F: DAG probe (buildDag T:462-497) for every Han slot of an owned, closed block ---------
-  for (int base = 0; base < kFtSlots; base += kFtThreads) {
-    const int kk = base + tid;
-    const uint32_t cur = S.ri[kk + 1];
-    bool act = RI_CLS(cur) == 1;
-    int ke = -1;
-    if (act) {
-      const int ks = f_find_start(S.HS, kk);
-      const int qs = ks < 0 ? -1 : 3 * ks - 2 + (int)RI_PHI(S.ri[ks + 1]);
-      ke = f_find_end(S.HE, kk);
-      act = ks >= 0 && qs >= 0 && qs < kFtTileBytes && ke >= 0;
-    }
-    uint32_t mask = 0, cnt = 0;
-    double wv[4];
-    bool over4 = false;
-    if (act) {
-      const uint32_t r0 = RI_CP(cur);
-      const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));  // termFreq[string(iRune)] (T:468-472)
-      wv[0] = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
-      mask = 1;
-      cnt = 1;
-      uint32_t child = f.w;
-      if (!(f.z & JB_FIRST_GATE)) {
-        uint32_t maxlen = (f.z >> 8) & 0xFF;
-        if (maxlen > (uint32_t)(ke - kk + 1)) maxlen = ke - kk + 1;
-        uint32_t h = jb_hash_init(r0);
-        uint64_t h64 = jb_hash64_step(JB_HASH64_INIT, r0), k0 = r0, k1 = 0;
-        uint32_t L = 1;
-        while (L < maxlen) {  // for j := range textRunes[i:], break on the first missing prefix (T:473-482)
-          const uint32_t rl = RI_CP(S.ri[kk + 1 + L]);
-          if (!((child >> jb_bloom_bit(rl)) & 1)) break;
-          h = jb_hash_step(h, rl);
-          h64 = jb_hash64_step(h64, rl);
-          if (L < 4) k0 |= (uint64_t)rl << (16 * L);
-          else if (L < 8) k1 |= (uint64_t)rl << (16 * (L - 4));
-          L++;
-          FProbe pr = f_probe(T, h, h64, L <= 8, k0, k1, L, &S.ri[kk + 1]);
-          if (!(pr.meta & JB_E_USED)) break;
-          if (pr.meta & JB_E_POS) {
-            mask |= 1u << (L - 1);
-            if (cnt < 4) wv[cnt] = pr.w;
-            else over4 = true;
-            cnt++;
-          }
-          child = pr.child;
-        }
-      }
-    }
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t v = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    uint32_t gbase = 0;
-    if (lane == 0 && total) gbase = atomicAdd(&S.wcnt, total);
-    gbase = __shfl_sync(FULL, gbase, 0);
-    const uint32_t off = gbase + incl - cnt;
-    if (act) {
-      S.cmask[kk] = mask;
-      S.woff[kk] = (uint16_t)off;
-      if (off + cnt <= (uint32_t)kFtWCap) {
-        if (!over4) {
-          for (uint32_t j = 0; j < cnt; j++) S.wbuf[off + j] = wv[j];
-        } else {  // rare: more than 4 candidates -- walk the chain again and store as we go
-          S.wbuf[off] = wv[0];
-          const uint32_t r0 = RI_CP(cur);
-          uint32_t h = jb_hash_init(r0), L = 1, o = 1;
-          uint64_t h64 = jb_hash64_step(JB_HASH64_INIT, r0), k0 = r0, k1 = 0;
-          while (o < cnt) {
-            const uint32_t rl = RI_CP(S.ri[kk + 1 + L]);
-            h = jb_hash_step(h, rl);
-            h64 = jb_hash64_step(h64, rl);
-            if (L < 4) k0 |= (uint64_t)rl << (16 * L);
-            else if (L < 8) k1 |= (uint64_t)rl << (16 * (L - 4));
-            L++;
-            FProbe pr = f_probe(T, h, h64, L <= 8, k0, k1, L, &S.ri[kk + 1]);
-            if (pr.meta & JB_E_POS) S.wbuf[off + o++] = pr.w;
-          }
-        }
+    if (owned) {
+      const int ke = f_find_end(S.HE, kk);
+      const uint32_t bi = wbase + __popc(bm & ((1u << lane) - 1u));
+      if (bi < (uint32_t)kFtMaxBlocks) {
+        S.blk[bi] = (uint16_t)kk;
+        S.blk_end[bi] = (int16_t)ke;
+        atomicMin(&S.first_ks, kk);
+        if (ke >= 0) atomicMax(&S.act_limit, ke);
       } else {
-        S.overflow = 1;
+        atomicOr(&A.counters[C_FLAGS], 1u);  // absurdly fragmented tile: the general pipeline redoes the batch
       }
     }
   }
   __syncthreads();
 
+  // ---- F: DAG probe (buildDag T:462-497) for every Han slot of an owned, closed block.  Lanes are
+  // persistent: a lane whose prefix chain ends picks up the next slot of its warp's range at once, so
+  // chains of different length do not leave lanes idle. ----------------------------------------------
+  {
+    const int first_ks = S.first_ks, act_limit = S.act_limit;
+    const int wend = (warp + 1) * (kFtSlots / (kFtThreads / 32));
+    int next = warp * (kFtSlots / (kFtThreads / 32));
+    bool active = false;
+    int kk = 0;
+    uint32_t L = 0, parent = 0, child = 0, mask = 0, cnt = 0, maxlen = 0, r0 = 0;
+    double wv[4];
+    bool over4 = false;
+    for (;;) {
+      const unsigned idle = __ballot_sync(FULL, !active);
+      bool fin = false;
+      if (idle && next < wend) {
+        const int cand = next + __popc(idle & ((1u << lane) - 1u));
+        next += __popc(idle);
+        if (!active && cand < wend && cand >= first_ks && cand <= act_limit) {
+          const uint32_t cur = S.ri[cand + 1];
+          if (RI_CLS(cur) == 1) {
+            kk = cand;
+            r0 = RI_CP(cur);
+            const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));  // termFreq[string(iRune)] (T:468-472)
+            wv[0] = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
+            mask = 1;
+            cnt = 1;
+            over4 = false;
+            child = f.w;
+            parent = JB_PARENT_FIRST(r0);
+            L = 1;
+            maxlen = (f.z >> 8) & 0xFF;
+            if ((f.z & JB_FIRST_GATE) || maxlen <= 1) fin = true;
+            else active = true;
+          }
+        }
+      }
+      if (active) {  // one step of `for j := range textRunes[i:]`, break on the first missing prefix (T:473-482)
+        const int last = kk + (int)L - 1;
+        bool stop = ((S.HE[last >> 5] >> (last & 31)) & 1) || L >= maxlen;
+        if (!stop) {
+          const uint32_t rl = RI_CP(S.ri[kk + 1 + L]);
+          const bool may = (L == 1) ? ((child >> jb_bloom_bit(rl)) & 1) : ((child >> jb_bloom11(rl)) & 1);
+          if (!may) {
+            stop = true;
+          } else {
+            double pw;
+            uint32_t prb;
+            const int ps = jb_probe_edge(T.entries, T.hash_mask, parent, rl, &pw, &prb);
+            if (ps < 0) {
+              stop = true;
+            } else {
+              L++;
+              if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481)
+                mask |= 1u << (L - 1);
+                if (cnt < 4) wv[cnt] = pw;
+                else over4 = true;
+                cnt++;
+              }
+              parent = (uint32_t)ps;
+              child = prb >> 21;
+            }
+          }
+        }
+        if (stop) {
+          active = false;
+          fin = true;
+        }
+      }
+      if (fin) {
+        const uint32_t off = atomicAdd(&S.wcnt, cnt);
+        S.cmask[kk] = mask;
+        S.woff[kk] = (uint16_t)off;
+        if (off + cnt <= (uint32_t)kFtWCap) {
+          if (!over4) {
+            for (uint32_t j = 0; j < cnt; j++) S.wbuf[off + j] = wv[j];
+          } else {  // rare: more than 4 candidates -- walk the chain again and store as we go
+            S.wbuf[off] = wv[0];
+            uint32_t pp = JB_PARENT_FIRST(r0), o = 1, LL = 1;
+            while (o < cnt) {
+              double pw;
+              uint32_t prb;
+              const int ps = jb_probe_edge(T.entries, T.hash_mask, pp, RI_CP(S.ri[kk + 1 + LL]), &pw, &prb);
+              if (ps < 0) break;
+              LL++;
+              if (jb_w_positive(pw)) S.wbuf[off + o++] = pw;
+              pp = (uint32_t)ps;
+            }
+          }
+        } else {
+          S.overflow = 1;
+        }
+      }
+      if (next >= wend && !__any_sync(FULL, active)) break;
+    }
+  }
+  __syncthreads();
+
   // ---- G: per block: route DP, path walk, HMM -------------------------------------------------
-  const uint32_t nblk = S.nblk;
+  const uint32_t nblk = min(S.nblk, (uint32_t)kFtMaxBlocks);
   const bool tile_overflow = S.overflow != 0;
-  for (uint32_t b = tid; b < nblk; b += kFtThreads) {
+  // block b runs on lane b/8 of warp b%8: the serial per-block chains are spread over all warps
+  for (uint32_t b = (uint32_t)lane * (kFtThreads / 32) + warp; b < nblk; b += kFtThreads) {
     const int ks = S.blk[b];
-    const int ke = f_find_end(S.HE, ks);
+    const int ke = S.blk_end[b];
     const uint32_t phi = RI_PHI(S.ri[ks + 1]);
     if (ke < 0 || tile_overflow) {  // long block (or this tile's weights did not fit): general kernels take it
       uint32_t idx = atomicAdd(&A.counters[C_N_LONG], 1u);

@@ -27,8 +27,9 @@ constexpr int kFtRegion = kFtLeft + kFtTileBytes + kFtHaloBytes + kFtRightPad;  
 constexpr int kFtSlots = (kFtTileBytes + kFtHaloBytes) / 3;                    // 1280
 constexpr int kFtWords = (kFtTileBytes + kFtHaloBytes) / 32;                   // 120
 constexpr int kFtTileWords = kFtTileBytes / 32;                                // 96
-constexpr int kFtWCap = 2816;                                                  // candidate weights per tile in smem
+constexpr int kFtWCap = 2560;                                                  // candidate weights per tile in smem
 constexpr int kFtThreads = 256;
+constexpr int kFtMaxBlocks = 768;  // owned Han blocks per tile (a block needs >= 4 bytes)
 
 struct FusedArgs {
   const uint8_t* text;

@@ -493,87 +493,11 @@ void hmm_defaults(jb_hmm_desc* h) {
 namespace {
 struct HanKey {
   std::vector<uint32_t> runes;
+  std::string bytes_key;
   uint32_t bytes;
+  uint32_t last_len;  // byte length of the last rune
   int64_t freq;
   double w;
-};
-
-static uint32_t probe_hash(const std::vector<uint32_t>& r, size_t L) {
-  uint32_t h = jb_hash_init(r[0]);
-  for (size_t j = 1; j < L; j++) h = jb_hash_step(h, r[j]);
-  return jb_hash_fin(h);
-}
-static uint64_t tag_hash(const std::vector<uint32_t>& r, size_t L) {
-  uint64_t h = JB_HASH64_INIT;
-  for (size_t j = 0; j < L; j++) h = jb_hash64_step(h, r[j]);
-  return h;
-}
-static bool inline_form(const std::vector<uint32_t>& r, size_t L) {
-  if (L > 8) return false;
-  for (size_t j = 0; j < L; j++)
-    if (r[j] >= 0x10000) return false;
-  return true;
-}
-static void pack_inline(const std::vector<uint32_t>& r, size_t L, uint64_t* k0, uint64_t* k1) {
-  *k0 = 0;
-  *k1 = 0;
-  for (size_t j = 0; j < L; j++) {
-    if (j < 4)
-      *k0 |= (uint64_t)r[j] << (16 * j);
-    else
-      *k1 |= (uint64_t)r[j] << (16 * (j - 4));
-  }
-}
-
-struct Builder {
-  TableImage& img;
-  uint32_t mask;
-  explicit Builder(TableImage& i) : img(i), mask(0) {}
-
-  JbEntry* find(const std::vector<uint32_t>& r, size_t L) {
-    uint32_t s = probe_hash(r, L) & mask;
-    bool inl = inline_form(r, L);
-    uint64_t k0, k1;
-    if (inl)
-      pack_inline(r, L, &k0, &k1);
-    else
-      k0 = tag_hash(r, L);
-    for (;;) {
-      JbEntry& e = img.entries[s];
-      if (!(e.meta & JB_E_USED)) return nullptr;
-      if (((e.meta >> 8) & 0xFF) == L) {
-        if (inl && !(e.meta & JB_E_LONG) && e.k0 == k0 && e.k1 == k1) return &e;
-        if (!inl && (e.meta & JB_E_LONG) && e.k0 == k0) {
-          bool same = true;
-          for (size_t j = 0; j < L; j++)
-            if (img.key_blob[e.k1 + j] != r[j]) {
-              same = false;
-              break;
-            }
-          if (same) return &e;
-        }
-      }
-      s = (s + 1) & mask;
-    }
-  }
-
-  void insert(const HanKey& k) {
-    size_t L = k.runes.size();
-    uint32_t s = probe_hash(k.runes, L) & mask;
-    while (img.entries[s].meta & JB_E_USED) s = (s + 1) & mask;
-    JbEntry& e = img.entries[s];
-    e.meta = JB_E_USED | (k.freq > 0 ? JB_E_POS : 0) | ((uint32_t)L << 8);
-    e.child = 0;
-    e.w = k.freq > 0 ? k.w : -INFINITY;
-    if (inline_form(k.runes, L)) {
-      pack_inline(k.runes, L, &e.k0, &e.k1);
-    } else {
-      e.meta |= JB_E_LONG;
-      e.k0 = tag_hash(k.runes, L);
-      e.k1 = img.key_blob.size();
-      img.key_blob.insert(img.key_blob.end(), k.runes.begin(), k.runes.end());
-    }
-  }
 };
 }  // namespace
 
@@ -616,11 +540,13 @@ int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int ver, Tabl
     uint64_t kl = dict->key_off[i + 1] - dict->key_off[i];
     HanKey hk;
     bool han = kl > 0;
+    hk.last_len = 0;
     for (uint64_t j = 0; j < kl && han;) {
       uint32_t r;
       int w = decode_rune(kp, j, kl, &r);
       if ((r == 0xFFFD && w == 1) || !is_han(r, ver)) han = false;
       hk.runes.push_back(r);
+      hk.last_len = (uint32_t)w;
       j += w;
     }
     if (!han) {
@@ -638,6 +564,7 @@ int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int ver, Tabl
       hk.w = NAN;  // math.Log(negative) = NaN in Go; negative counts never occur in jieba data
     }
     std::string ks((const char*)kp, kl);
+    hk.bytes_key = ks;
     auto it = seen.find(ks);
     if (it != seen.end())
       keys[it->second] = hk;
@@ -682,26 +609,49 @@ int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int ver, Tabl
     }
   }
 
-  // hash table
+  // hash table of trie edges: insert shorter keys first so that every parent id is known
   size_t cap = 64;
-  while (cap < 2 * n_hash + 16) cap <<= 1;
-  JbEntry empty;
-  memset(&empty, 0, sizeof empty);
-  img.entries.assign(cap, empty);
-  Builder b(img);
-  b.mask = (uint32_t)(cap - 1);
-  for (auto& k : keys) {
-    if (k.runes.size() == 1 && k.runes[0] < 0x10000) continue;
-    b.insert(k);
-  }
-  // child Blooms: key K of length L >= 3 marks its parent K[:L-1] (if that parent is a key);
-  // supplementary-plane first runes (L == 2) mark their 1-rune hash entry
-  for (auto& k : keys) {
-    size_t L = k.runes.size();
-    if (L < 2) continue;
-    if (L == 2 && k.runes[0] < 0x10000) continue;  // handled by first[].child
-    JbEntry* p = b.find(k.runes, L - 1);
-    if (p) p->child |= 1u << jb_bloom_bit(k.runes[L - 1]);
+  while (cap < 3 * n_hash + 16) cap <<= 1;
+  img.entries.assign(cap, JbEntry{0.0, JB_PARENT_EMPTY, 0u});
+  const uint32_t hmask = (uint32_t)(cap - 1);
+  std::vector<uint32_t> order(keys.size());
+  for (uint32_t i = 0; i < keys.size(); i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a2, uint32_t b2) { return keys[a2].runes.size() < keys[b2].runes.size(); });
+  std::unordered_map<std::string, uint32_t> slot_of;  // key bytes -> slot (hash-resident keys only)
+  slot_of.reserve(n_hash * 2);
+  std::vector<uint8_t> is_single(65536, 0);
+  for (auto& k : keys)
+    if (k.runes.size() == 1 && k.runes[0] < 0x10000) is_single[k.runes[0]] = 1;
+  for (uint32_t oi : order) {
+    HanKey& k = keys[oi];
+    const size_t L = k.runes.size();
+    if (L == 1 && k.runes[0] < 0x10000) continue;  // lives in the first-rune table
+    uint32_t parent;
+    if (L == 1) {
+      parent = JB_PARENT_ROOT;
+    } else if (L == 2 && k.runes[0] < 0x10000) {
+      if (!is_single[k.runes[0]]) {  // buildDag never probes past a missing first rune (tokenizer.go:468-472)
+        img.n_unreachable_keys++;
+        continue;
+      }
+      parent = JB_PARENT_FIRST(k.runes[0]);
+    } else {
+      auto it = slot_of.find(k.bytes_key.substr(0, k.bytes_key.size() - k.last_len));
+      if (it == slot_of.end()) {  // a proper prefix is not a key: the loop breaks before reaching this key (tokenizer.go:476-478)
+        img.n_unreachable_keys++;
+        continue;
+      }
+      parent = it->second;
+    }
+    const uint32_t rune = k.runes[L - 1];
+    uint32_t sidx = jb_hash_edge(parent, rune) & hmask;
+    while (img.entries[sidx].parent != JB_PARENT_EMPTY) sidx = (sidx + 1) & hmask;
+    img.entries[sidx].w = k.freq > 0 ? k.w : -INFINITY;
+    img.entries[sidx].parent = parent;
+    img.entries[sidx].rb = rune;
+    slot_of.emplace(k.bytes_key, sidx);
+    // Bloom of the parent: first-rune table for 2-rune keys with a BMP first rune (set above), else the parent entry
+    if (L >= 2 && !(L == 2 && k.runes[0] < 0x10000)) img.entries[parent].rb |= 1u << (21 + jb_bloom11(rune));
   }
 
   // HMM

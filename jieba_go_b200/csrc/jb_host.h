@@ -37,7 +37,6 @@ struct HostEmit {
 struct TableImage {
   std::vector<JbFirst> first;
   std::vector<JbEntry> entries;
-  std::vector<uint32_t> key_blob;
   std::vector<double> emit;
   std::vector<uint32_t> emit_supp_rune;
   std::vector<double> emit_supp;
@@ -47,7 +46,7 @@ struct TableImage {
   double start[4];
   double trans[4][2];
   uint32_t max_delta = 1;
-  uint64_t n_han_keys = 0, n_dropped_keys = 0;
+  uint64_t n_han_keys = 0, n_dropped_keys = 0, n_unreachable_keys = 0;
 };
 
 double go_log(double x);

@@ -258,54 +258,6 @@ __device__ bool block_has_alnum(const uint32_t* BND, const uint32_t* ALN, int po
   return false;
 }
 
-// Probe the rune-prefix hash for the key runes[0..L) whose running hashes are (h, h64) and
-// inline packing (k0,k1).  Returns the entry's second half (w, child, meta) or meta==0 when
-// missing.  One 32-byte sector per probe step.
-struct ProbeResult {
-  double w;
-  uint32_t child, meta;
-};
-__device__ __forceinline__ ProbeResult probe_hash(const JbTables& T, uint32_t h, uint64_t h64, bool inl, uint64_t k0, uint64_t k1,
-                                                  uint32_t L, const uint8_t* sb_key /*smem bytes of the key*/) {
-  uint32_t slot = jb_hash_fin(h) & T.hash_mask;
-  ProbeResult r;
-  r.meta = 0;
-  r.child = 0;
-  r.w = 0;
-  for (;;) {
-    const uint4* ep = reinterpret_cast<const uint4*>(T.entries + slot);
-    uint4 b = __ldg(ep + 1);
-    uint32_t meta = b.w;
-    if (!(meta & JB_E_USED)) return r;
-    if (((meta >> 8) & 0xFF) == L) {
-      uint4 a = __ldg(ep);
-      uint64_t e0 = ((uint64_t)a.y << 32) | a.x, e1 = ((uint64_t)a.w << 32) | a.z;
-      bool hit = false;
-      if (inl) {
-        hit = !(meta & JB_E_LONG) && e0 == k0 && e1 == k1;
-      } else if ((meta & JB_E_LONG) && e0 == h64) {
-        hit = true;  // verify against the key blob
-        const uint8_t* p = sb_key;
-        for (uint32_t j = 0; j < L; j++) {
-          int len = (*p >= 0xF0) ? 4 : 3;
-          if (__ldg(T.key_blob + e1 + j) != d_decode(p, len)) {
-            hit = false;
-            break;
-          }
-          p += len;
-        }
-      }
-      if (hit) {
-        r.w = __longlong_as_double(((long long)b.y << 32) | (long long)b.x);
-        r.child = b.z;
-        r.meta = meta;
-        return r;
-      }
-    }
-    slot = (slot + 1) & T.hash_mask;
-  }
-}
-
 constexpr int kSplitThreads = 256;
 struct SplitSmem {
   TileSmem t;
@@ -463,31 +415,30 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
       uint32_t d1 = d_slot(P0 + len0) - k;
       mask = 1u << (d1 - 1);
       // first probe: termFreq[string(iRune)] (tokenizer.go:468-472)
-      uint32_t info, child;
-      uint32_t h = jb_hash_init(r0);
-      uint64_t h64 = jb_hash64_step(JB_HASH64_INIT, r0);
+      uint32_t info, child, parent;
       if (r0 < 0x10000) {
         const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));
         wv[0] = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
         info = f.z;
         child = f.w;
+        parent = JB_PARENT_FIRST(r0);
       } else {
-        ProbeResult pr = probe_hash(T, h, h64, false, 0, 0, 1, &S.t.sb[i]);
-        if (pr.meta & JB_E_POS) {
-          wv[0] = pr.w;
+        double pw;
+        uint32_t prb;
+        int ps = jb_probe_edge(T.entries, T.hash_mask, JB_PARENT_ROOT, r0, &pw, &prb);
+        if (ps >= 0 && jb_w_positive(pw)) {
+          wv[0] = pw;
           info = (uint32_t)JB_MAX_DELTA << 8;
-          child = pr.child;
         } else {
-          wv[0] = (pr.meta & JB_E_USED) ? pr.w : T.neg_log_total;  // freq 0: -Inf; missing: log(1)-total
+          wv[0] = ps >= 0 ? pw : T.neg_log_total;  // freq 0: -Inf; missing: log(1)-total
           info = JB_FIRST_GATE;
-          child = 0;
         }
+        child = ps >= 0 ? (prb >> 21) : 0u;
+        parent = (uint32_t)ps;
       }
       cnt = 1;
       if (!(info & JB_FIRST_GATE) && !bend) {
         const uint32_t maxlen = (info >> 8) & 0xFF;
-        uint64_t k0 = r0, k1 = 0;
-        bool inl = r0 < 0x10000;
         uint32_t L = 1;
         int qi = q;
         // for j := range textRunes[i:] ... break on the first missing prefix (tokenizer.go:473-482)
@@ -497,24 +448,24 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
           if ((c >> 3) != CL_HAN) break;
           int len = c & 7;
           uint32_t rl = d_decode(&S.t.sb[qi], len);
-          if (!((child >> jb_bloom_bit(rl)) & 1)) break;  // no key extends the current prefix by this rune
-          h = jb_hash_step(h, rl);
-          h64 = jb_hash64_step(h64, rl);
-          if (rl >= 0x10000 || L >= 8) inl = false;
-          else if (L < 4) k0 |= (uint64_t)rl << (16 * L);
-          else k1 |= (uint64_t)rl << (16 * (L - 4));
+          // Bloom of the next rune: 32 bits in the first-rune table, 11 bits in hash entries
+          const bool may = (L == 1 && r0 < 0x10000) ? ((child >> jb_bloom_bit(rl)) & 1) : ((child >> jb_bloom11(rl)) & 1);
+          if (!may) break;
+          double pw;
+          uint32_t prb;
+          int ps = jb_probe_edge(T.entries, T.hash_mask, parent, rl, &pw, &prb);
+          if (ps < 0) break;  // !found -> break (tokenizer.go:476-478)
           L++;
           qi += len;
-          ProbeResult pr = probe_hash(T, h, h64, inl, k0, k1, L, &S.t.sb[i]);
-          if (!(pr.meta & JB_E_USED)) break;  // !found -> break (tokenizer.go:476-478)
-          if (pr.meta & JB_E_POS) {           // val > 0 -> edge (tokenizer.go:479-481)
+          if (jb_w_positive(pw)) {  // val > 0 -> edge (tokenizer.go:479-481)
             uint32_t d = d_slot(t0 - kHaloL + qi) - k;
             mask |= 1u << (d - 1);
-            if (cnt < 4) wv[cnt] = pr.w;
+            if (cnt < 4) wv[cnt] = pw;
             else overflow4 = true;
             cnt++;
           }
-          child = pr.child;
+          parent = (uint32_t)ps;
+          child = prb >> 21;
         }
       }
     }
@@ -539,24 +490,23 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
           // rare: more than 4 candidates -- walk the chain again and store as we go
           wtile[excl] = wv[0];
           uint32_t o = 1;
-          uint32_t h = jb_hash_init(r0);
-          uint64_t h64 = jb_hash64_step(JB_HASH64_INIT, r0);
-          uint64_t k0 = r0, k1 = 0;
-          bool inl = r0 < 0x10000;
-          uint32_t L = 1;
+          uint32_t parent = JB_PARENT_FIRST(r0);
+          if (r0 >= 0x10000) {
+            double pw;
+            uint32_t prb;
+            parent = (uint32_t)jb_probe_edge(T.entries, T.hash_mask, JB_PARENT_ROOT, r0, &pw, &prb);
+          }
           int qi = i + len0;
           while (o < cnt) {
             int len = S.t.cls[qi] & 7;
             uint32_t rl = d_decode(&S.t.sb[qi], len);
-            h = jb_hash_step(h, rl);
-            h64 = jb_hash64_step(h64, rl);
-            if (rl >= 0x10000 || L >= 8) inl = false;
-            else if (L < 4) k0 |= (uint64_t)rl << (16 * L);
-            else k1 |= (uint64_t)rl << (16 * (L - 4));
-            L++;
+            double pw;
+            uint32_t prb;
+            int ps = jb_probe_edge(T.entries, T.hash_mask, parent, rl, &pw, &prb);
+            if (ps < 0) break;
             qi += len;
-            ProbeResult pr = probe_hash(T, h, h64, inl, k0, k1, L, &S.t.sb[i]);
-            if (pr.meta & JB_E_POS) wtile[excl + o++] = pr.w;
+            if (jb_w_positive(pw)) wtile[excl + o++] = pw;
+            parent = (uint32_t)ps;
           }
         }
       }
@@ -1221,51 +1171,31 @@ __global__ void k_fallback_reset(uint32_t* __restrict__ counters, uint32_t* __re
 // debug: one dictionary lookup through the device tables
 // ------------------------------------------------------------------------------------------
 __global__ void k_debug_lookup(const JbTables T, const uint32_t* runes, int L, int* kind, double* w) {
+  // walks the key the way buildDag reaches it: through every prefix (a key whose prefix is missing is unreachable)
   uint32_t r0 = runes[0];
-  if (L == 1 && r0 < 0x10000) {
+  uint32_t parent;
+  double cw = 0;
+  int k = 0;
+  if (r0 < 0x10000) {
     JbFirst f = T.first[r0];
-    if (!(f.info & JB_FIRST_GATE)) *kind = 2;
-    else *kind = (f.w == T.neg_log_total) ? 0 : 1;
-    *w = f.w;
-    return;
+    if (!(f.info & JB_FIRST_GATE)) k = 2;
+    else k = (f.w == T.neg_log_total) ? 0 : 1;
+    cw = f.w;
+    parent = JB_PARENT_FIRST(r0);
+  } else {
+    uint32_t rb;
+    int ps = jb_probe_edge(T.entries, T.hash_mask, JB_PARENT_ROOT, r0, &cw, &rb);
+    k = ps < 0 ? 0 : (jb_w_positive(cw) ? 2 : 1);
+    parent = (uint32_t)ps;
   }
-  uint32_t h = jb_hash_init(r0);
-  uint64_t h64 = jb_hash64_step(JB_HASH64_INIT, r0);
-  uint64_t k0 = r0, k1 = 0;
-  bool inl = r0 < 0x10000;
-  for (int j = 1; j < L; j++) {
-    uint32_t rl = runes[j];
-    h = jb_hash_step(h, rl);
-    h64 = jb_hash64_step(h64, rl);
-    if (rl >= 0x10000 || j >= 8) inl = false;
-    else if (j < 4) k0 |= (uint64_t)rl << (16 * j);
-    else k1 |= (uint64_t)rl << (16 * (j - 4));
+  for (int j = 1; j < L && k != 0; j++) {
+    uint32_t rb;
+    int ps = jb_probe_edge(T.entries, T.hash_mask, parent, runes[j], &cw, &rb);
+    k = ps < 0 ? 0 : (jb_w_positive(cw) ? 2 : 1);
+    parent = (uint32_t)ps;
   }
-  if (L > 8) inl = false;
-  uint32_t slot = jb_hash_fin(h) & T.hash_mask;
-  for (;;) {
-    JbEntry e = T.entries[slot];
-    if (!(e.meta & JB_E_USED)) {
-      *kind = 0;
-      *w = 0;
-      return;
-    }
-    if (((e.meta >> 8) & 0xFF) == (uint32_t)L) {
-      bool hit = false;
-      if (inl) hit = !(e.meta & JB_E_LONG) && e.k0 == k0 && e.k1 == k1;
-      else if ((e.meta & JB_E_LONG) && e.k0 == h64) {
-        hit = true;
-        for (int j = 0; j < L; j++)
-          if (T.key_blob[e.k1 + j] != runes[j]) hit = false;
-      }
-      if (hit) {
-        *kind = (e.meta & JB_E_POS) ? 2 : 1;
-        *w = e.w;
-        return;
-      }
-    }
-    slot = (slot + 1) & T.hash_mask;
-  }
+  *kind = k;
+  *w = k ? cw : 0.0;
 }
 
 int debug_lookup(const JbTables& T, const uint32_t* runes_host, int L, int* kind, double* w) {
