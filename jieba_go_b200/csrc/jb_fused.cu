@@ -33,9 +33,10 @@ struct FusedSmem {
   uint16_t blk[kFtMaxBlocks];      // owned blocks: first slot
   int16_t blk_end[kFtMaxBlocks];   //               last slot, or -1 when the block does not end inside the region
   double wbuf[kFtWCap];
-  double R[kFtSlots + 2];
   uint8_t wcls[kFtThreads / 32][40];
-  uint32_t nblk, wcnt, overflow;
+  uint16_t pofs[kFtSlots + 2];  // exclusive prefix of stream record sizes
+  uint32_t wsum[kFtThreads / 32];
+  uint32_t nblk, wcnt, overflow, npacked, npacked2, sbase, bbase;
   int first_ks, act_limit;
 };
 
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
       S.nblk = 0;
       S.wcnt = 0;
       S.overflow = 0;
+      S.npacked = 0;
       S.first_ks = kFtSlots;
       S.act_limit = -1;
     }
@@ -553,60 +555,216 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
   }
   __syncthreads();
 
-  // ---- G: per block: route DP, path walk, HMM -------------------------------------------------
+  // ---- G: hand the owned blocks to k_block_dp: pack every block's candidates into one stream -------
+  // Stream unit = 8 bytes.  Per position: header (low 32 bits candidate-length mask, bits 32..47 the
+  // rune) followed by one float64 weight per candidate in ascending length.  The tile's positions are
+  // stored in REVERSE slot order, so a block's records are contiguous and start with its last rune --
+  // the order the right-to-left route DP consumes them.
   const uint32_t nblk = min(S.nblk, (uint32_t)kFtMaxBlocks);
   const bool tile_overflow = S.overflow != 0;
-  // block b runs on lane b/8 of warp b%8: the serial per-block chains are spread over all warps
-  for (uint32_t b = (uint32_t)lane * (kFtThreads / 32) + warp; b < nblk; b += kFtThreads) {
+  for (uint32_t b = tid; b < nblk; b += kFtThreads) {
     const int ks = S.blk[b];
     const int ke = S.blk_end[b];
-    const uint32_t phi = RI_PHI(S.ri[ks + 1]);
-    if (ke < 0 || tile_overflow) {  // long block (or this tile's weights did not fit): general kernels take it
+    if (ke < 0 || tile_overflow || ke - ks + 1 > kFtMaxBlockLen) {
+      // long block, or this tile's weights did not fit in shared memory: the general kernels take it
       uint32_t idx = atomicAdd(&A.counters[C_N_LONG], 1u);
-      if (idx < A.long_cap) A.long_seeds[idx] = t0 + 3 * ks - 2 + phi;
+      if (idx < A.long_cap) A.long_seeds[idx] = t0 + 3 * ks - 2 + RI_PHI(S.ri[ks + 1]);
       else atomicOr(&A.counters[C_FLAGS], 1u);
-      continue;
+      S.blk_end[b] = -1;
+      if (ke >= 0 && !tile_overflow)
+        for (int k = ks; k <= ke; k++) S.woff[k] = 0xFFFFu;  // not packed
+    } else {
+      atomicAdd(&S.npacked, 1u);
     }
-    // calcDagProba (T:502-548) right to left with maxIndexProba (T:565-578): each candidate is compared
-    // with the PREVIOUS candidate; the last one >= its predecessor wins, else the last candidate.
-    for (int k = ke; k >= ks; --k) {
-      uint32_t m = S.cmask[k];
-      const uint32_t o = S.woff[k];
+  }
+  __syncthreads();
+  {
+    // exclusive scan of record sizes over the slots (5 consecutive slots per thread)
+    const int first_ks = S.first_ks, act_limit = tile_overflow ? -1 : S.act_limit;
+    uint32_t sz[kFtSlots / kFtThreads], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kFtSlots / kFtThreads; j++) {
+      const int kk = tid * (kFtSlots / kFtThreads) + j;
+      uint32_t v = 0;
+      if (kk >= first_ks && kk <= act_limit && RI_CLS(S.ri[kk + 1]) == 1 && S.woff[kk] != 0xFFFFu) v = 1u + __popc(S.cmask[kk]);
+      sz[j] = v;
+      sum += v;
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) S.wsum[warp] = incl;
+    __syncthreads();
+    uint32_t pre = incl - sum;
+    for (int w = 0; w < warp; w++) pre += S.wsum[w];
+#pragma unroll
+    for (int j = 0; j < kFtSlots / kFtThreads; j++) {
+      S.pofs[tid * (kFtSlots / kFtThreads) + j] = (uint16_t)pre;
+      pre += sz[j];
+    }
+    if (tid == kFtThreads - 1) {
+      S.pofs[kFtSlots] = (uint16_t)pre;
+      // reserve stream space and block descriptors for this tile
+      const uint32_t total = pre, np = S.npacked;
+      uint32_t sbase = 0, bbase = 0;
+      if (np) {
+        sbase = atomicAdd(&A.counters[C_STREAM], total);
+        bbase = atomicAdd(&A.counters[C_N_FBLK], np);
+        if (sbase + total > A.stream_cap || bbase + np > A.fblk_cap) {
+          atomicOr(&A.counters[C_FLAGS], 1u);  // out of stream space: the general pipeline redoes the batch
+          S.npacked = 0;
+        }
+      }
+      S.sbase = sbase;
+      S.bbase = bbase;
+      S.npacked2 = 0;
+    }
+    __syncthreads();
+    if (S.npacked) {
+      const uint32_t total = S.pofs[kFtSlots], sbase = S.sbase;
+      unsigned long long* __restrict__ st = A.stream + sbase;
+#pragma unroll
+      for (int j = 0; j < kFtSlots / kFtThreads; j++) {
+        const int kk = tid * (kFtSlots / kFtThreads) + j;
+        if (!sz[j]) continue;
+        const uint32_t off = total - S.pofs[kk + 1];
+        const uint32_t m = S.cmask[kk];
+        st[off] = (unsigned long long)m | ((unsigned long long)RI_CP(S.ri[kk + 1]) << 32);
+        const uint32_t wo = S.woff[kk];
+        for (uint32_t c = 0; c + 1 < sz[j]; c++) st[off + 1 + c] = (unsigned long long)__double_as_longlong(S.wbuf[wo + c]);
+      }
+      for (uint32_t b = tid; b < nblk; b += kFtThreads) {
+        const int ke = S.blk_end[b];
+        if (ke < 0) continue;
+        const int ks = S.blk[b];
+        const uint32_t bi = S.bbase + atomicAdd(&S.npacked2, 1u);
+        A.fblocks[bi] = make_uint4(sbase + total - S.pofs[ke + 1], t0 + 3 * ks - 2 + RI_PHI(S.ri[ks + 1]), (uint32_t)(ke - ks + 1), 0u);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- H: publish token bits ----------------------------------------------------------------------
+  const uint32_t w0 = t0 / 32;
+  for (int j = tid; j < kFtWords + 1; j += kFtThreads) {
+    const uint32_t sbits = S.S[j], ebits = S.E[j];
+    if (sbits) atomicOr(&A.s_bits[w0 + j], sbits);
+    if (ebits) atomicOr(&A.e_bits[w0 + j], ebits);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_block_dp: one lane per packed Han block, lanes refilled from a warp-level queue (every lane of
+// every warp busy, whatever the block lengths).  Per block: route DP right to left over the packed
+// stream (calcDagProba T:502-548 + maxIndexProba T:565-578), then the forward walk (findDagPath
+// T:552-562), the HMM glue (cutZh T:221-255), Viterbi (T:668-756) and cutHMM (T:273-285).
+// Shared memory per lane: a ring of RING route values and one chosen length per rune.
+// ------------------------------------------------------------------------------------------
+constexpr int kBdThreads = 128;
+constexpr int kBdQueue = 32;
+
+struct BitAcc {  // token bits of one lane, flushed one 32-byte word at a time (positions only grow)
+  uint32_t* bits;
+  uint32_t w, m;
+  __device__ __forceinline__ void init(uint32_t* b) {
+    bits = b;
+    w = 0xFFFFFFFFu;
+    m = 0;
+  }
+  __device__ __forceinline__ void set(uint32_t p) {
+    const uint32_t pw = p >> 5;
+    if (pw != w) {
+      if (m) atomicOr(&bits[w], m);
+      w = pw;
+      m = 0;
+    }
+    m |= 1u << (p & 31);
+  }
+  __device__ __forceinline__ void flush() {
+    if (m) atomicOr(&bits[w], m);
+    m = 0;
+    w = 0xFFFFFFFFu;
+  }
+};
+
+template <bool HMM, int RING>
+__global__ void __launch_bounds__(kBdThreads) k_block_dp(const JbTables T, const BlockDpArgs A) {
+  extern __shared__ __align__(16) uint8_t bd_smem[];
+  double* ring = reinterpret_cast<double*>(bd_smem);                           // [RING][kBdThreads]
+  uint8_t* path = bd_smem + (size_t)RING * kBdThreads * sizeof(double);       // [kFtMaxBlockLen][kBdThreads]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t nblocks = min(A.counters[C_N_FBLK], A.fblk_cap);
+  uint32_t qh = 0, qt = 0;
+  bool exhausted = false;
+  BitAcc sa, ea;
+  sa.init(A.s_bits);
+  ea.init(A.e_bits);
+  for (;;) {
+    // ---- take the next block (one global atomic per 32 blocks per warp) ----
+    uint32_t idx = 0xFFFFFFFFu;
+    if (qh == qt && !exhausted) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&A.counters[C_CUR_FBLK], (uint32_t)kBdQueue);
+      base = __shfl_sync(FULL, base, 0);
+      if (base >= nblocks) exhausted = true;
+      else {
+        qh = base;
+        qt = min(base + (uint32_t)kBdQueue, nblocks);
+      }
+    }
+    if (exhausted) break;
+    if (qh + lane < qt) idx = qh + lane;
+    qh = qt;
+    if (idx == 0xFFFFFFFFu) continue;
+    // NOTE: a warp takes 32 blocks at a time and each lane runs its block to completion; lanes of a
+    // warp therefore finish together only as well as their block lengths match (sentence-sized blocks).
+    const uint4 desc = A.fblocks[idx];
+    const unsigned long long* __restrict__ st = A.stream + desc.x;
+    const uint32_t P0 = desc.y;
+    const int npos = (int)desc.z;
+    // ---- route DP, right to left ----
+    uint32_t p = 0;
+    for (int k = npos - 1; k >= 0; --k) {
+      const unsigned long long hdr = st[p++];
+      uint32_t m = (uint32_t)hdr;
       double prev = JB_MINF, best_v = 0.0, v = 0.0;
-      uint32_t best_d = 0, d = 0, j = 0;
+      uint32_t best_d = 0, d = 0;
       while (m) {
         d = __ffs(m);
         m &= m - 1;
-        const double nxt = (k + (int)d > ke) ? 0.0 : S.R[k + d];  // {j, 0.0} when j == len (T:522)
-        v = S.wbuf[o + j] + nxt;                                   // pieceFreq + nextBestPiece.proba (T:529)
-        j++;
-        if (v >= prev) {
+        const double w = __longlong_as_double((long long)st[p++]);
+        const double nxt = (k + (int)d >= npos) ? 0.0 : ring[((k + d) & (RING - 1)) * kBdThreads + tid];  // {j,0.0} at the end (T:522)
+        v = w + nxt;  // pieceFreq + nextBestPiece.proba (T:529)
+        if (v >= prev) {  // maxIndexProba: compare with the PREVIOUS candidate (T:569)
           best_d = d;
           best_v = v;
         }
         prev = v;
       }
-      if (best_d == 0) {
+      if (best_d == 0) {  // best.index == -1 -> return prev (T:574-576)
         best_d = d;
         best_v = v;
       }
-      S.R[k] = best_v;
-      S.cmask[k] = best_d;
+      ring[(k & (RING - 1)) * kBdThreads + tid] = best_v;
+      path[k * kBdThreads + tid] = (uint8_t)best_d;
     }
-    // findDagPath (T:552-562) + cutZh (T:221-255)
-    const int qbase = -2 + (int)phi;  // tile-local byte of slot k's lead = 3k + qbase
-    int k = ks;
+    // ---- forward walk + HMM ----
+    uint8_t* bp = reinterpret_cast<uint8_t*>(A.stream + desc.x);  // the block's stream is dead now: Viterbi back-pointers
+    int k = 0;
     uint32_t run_n = 0;
     int run_s = 0;
     double V[4];
-    while (k <= ke) {
-      const uint32_t d = S.cmask[k] & 0xFF;
-      if (HMM && d == 1) {
-        // collect singletons (T:233-234): one Viterbi step per rune (T:688-719)
-        const uint32_t cp = RI_CP(S.ri[k + 1]);
+    while (k < npos) {
+      const uint32_t d = path[k * kBdThreads + tid] & 0x7F;
+      const bool single = HMM && d == 1;
+      if (single) {  // collect singletons (T:233-234): one Viterbi step per rune (T:688-719)
+        const uint8_t* tp = A.text + P0 + 3u * (uint32_t)k;
+        const uint32_t cp = ((tp[0] & 0xFu) << 12) | ((tp[1] & 0x3Fu) << 6) | (tp[2] & 0x3Fu);
         const double2* ep = reinterpret_cast<const double2*>(T.emit + (size_t)cp * 4);
-        const double2 ea = __ldg(ep), eb = __ldg(ep + 1);
-        const double em[4] = {ea.x, ea.y, eb.x, eb.y};
+        const double2 e0 = __ldg(ep), e1 = __ldg(ep + 1);
+        const double em[4] = {e0.x, e0.y, e1.x, e1.y};
         if (run_n == 0) {
           run_s = k;
 #pragma unroll
@@ -633,61 +791,76 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
           }
 #pragma unroll
           for (int s = 0; s < 4; s++) V[s] = W[s];
-          S.cmask[k] = 1u | (code << 16);
+          bp[k] = (uint8_t)code;
         }
         run_n++;
       }
-      const bool single = HMM && d == 1;
-      if (!single || k + 1 > ke) {
-        if (HMM && run_n) {
-          // flush the run [run_s, run_s + run_n): viterbi's tail (T:723-729) + cutHMM (T:273-285)
-          const int kl = run_s + (int)run_n - 1;
+      if (!single || k + 1 >= npos) {
+        if (HMM && run_n) {  // flush the run: viterbi's tail (T:723-729) + cutHMM (T:273-285)
           if (run_n == 1) {
-            f_set(S.S, 3 * run_s + qbase);
-            f_set(S.E, 3 * run_s + qbase + 2);
+            sa.set(P0 + 3u * run_s);
+            ea.set(P0 + 3u * run_s + 2);
           } else {
-            int st = V[2] > V[3] ? 2 : 3;
-            int kb = kl;
+            int st2 = V[2] > V[3] ? 2 : 3;
+            int kb = run_s + (int)run_n - 1;
             uint32_t plen = 0;
             for (;;) {  // back-trace; stops early where route.from == "" (T:715-716)
-              const uint32_t r = S.cmask[kb];
-              S.cmask[kb] = (r & ~JB_REC_ES) | (st >= 2 ? JB_REC_ES : 0u);
+              uint8_t& pk = path[kb * kBdThreads + tid];
+              pk = (uint8_t)((pk & 0x7F) | (st2 >= 2 ? 0x80 : 0));
               plen++;
               if (kb == run_s) break;
-              const int c = (r >> (16 + 2 * st)) & 3;
+              const int c = (bp[kb] >> (2 * st2)) & 3;
               if (c == 0) break;
-              st = (st == 0 || st == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
+              st2 = (st2 == 0 || st2 == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
               kb--;
             }
             // path[j] applies to rune j (T:277-283): a short path drops the run's tail
             const int shift = (int)(run_n - plen);
             bool prev_es = true;
             for (uint32_t j2 = 0; j2 < plen; j2++) {
-              const bool es = S.cmask[run_s + shift + j2] & JB_REC_ES;
-              const int qq = 3 * (run_s + (int)j2) + qbase;
-              if (prev_es) f_set(S.S, qq);
-              if (es) f_set(S.E, qq + 2);
+              const bool es = path[(run_s + shift + (int)j2) * kBdThreads + tid] & 0x80;
+              const uint32_t qq = P0 + 3u * (uint32_t)(run_s + (int)j2);
+              if (prev_es) sa.set(qq);
+              if (es) ea.set(qq + 2);
               prev_es = es;
             }
           }
           run_n = 0;
         }
         if (!single) {
-          f_set(S.S, 3 * k + qbase);
-          f_set(S.E, 3 * (k + (int)d) + qbase - 1);
+          sa.set(P0 + 3u * (uint32_t)k);
+          ea.set(P0 + 3u * (uint32_t)(k + (int)d) - 1);
         }
       }
       k += d;
     }
+    sa.flush();
+    ea.flush();
   }
-  __syncthreads();
-  // ---- H: publish token bits ----------------------------------------------------------------------
-  const uint32_t w0 = t0 / 32;
-  for (int j = tid; j < kFtWords + 1; j += kFtThreads) {
-    const uint32_t sbits = S.S[j], ebits = S.E[j];
-    if (sbits) atomicOr(&A.s_bits[w0 + j], sbits);
-    if (ebits) atomicOr(&A.e_bits[w0 + j], ebits);
+}
+
+int launch_block_dp(const JbTables& T, const BlockDpArgs& A, bool hmm, int num_sms, cudaStream_t st) {
+  static bool attr_done = false;
+  const size_t sm16 = (size_t)16 * kBdThreads * 8 + (size_t)kFtMaxBlockLen * kBdThreads;
+  const size_t sm32 = (size_t)32 * kBdThreads * 8 + (size_t)kFtMaxBlockLen * kBdThreads;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_block_dp<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
+    cudaFuncSetAttribute(k_block_dp<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
+    cudaFuncSetAttribute(k_block_dp<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32);
+    cudaFuncSetAttribute(k_block_dp<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32);
+    attr_done = true;
   }
+  // RING >= max_delta is enough: R[k+d] is read before R[k] overwrites the same ring cell
+  const bool r16 = T.max_delta <= 16;
+  const unsigned grid = (unsigned)num_sms * (r16 ? 4u : 3u);
+  if (r16) {
+    if (hmm) k_block_dp<true, 16><<<grid, kBdThreads, sm16, st>>>(T, A);
+    else k_block_dp<false, 16><<<grid, kBdThreads, sm16, st>>>(T, A);
+  } else {
+    if (hmm) k_block_dp<true, 32><<<grid, kBdThreads, sm32, st>>>(T, A);
+    else k_block_dp<false, 32><<<grid, kBdThreads, sm32, st>>>(T, A);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 int launch_fused(const JbTables& T, const FusedArgs& A, uint32_t ntiles, bool hmm, cudaStream_t st) {

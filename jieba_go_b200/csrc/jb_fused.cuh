@@ -29,7 +29,8 @@ constexpr int kFtWords = (kFtTileBytes + kFtHaloBytes) / 32;                   /
 constexpr int kFtTileWords = kFtTileBytes / 32;                                // 96
 constexpr int kFtWCap = 2560;                                                  // candidate weights per tile in smem
 constexpr int kFtThreads = 256;
-constexpr int kFtMaxBlocks = 768;  // owned Han blocks per tile (a block needs >= 4 bytes)
+constexpr int kFtMaxBlocks = 768;
+constexpr int kFtMaxBlockLen = 256;  // longest Han block (runes) the block-DP kernel takes; longer ones go the general way  // owned Han blocks per tile (a block needs >= 4 bytes)
 
 struct FusedArgs {
   const uint8_t* text;
@@ -43,7 +44,22 @@ struct FusedArgs {
   uint32_t long_cap;
   uint4* deferred;        // (byte pos, len, flags: 1 need fwd 2 need bwd, tile)
   uint32_t deferred_cap;
+  unsigned long long* stream;  // packed candidate records of the owned blocks
+  uint32_t stream_cap;         // in 8-byte units
+  uint4* fblocks;              // per packed block: (stream offset, byte position of its first rune, runes, 0)
+  uint32_t fblk_cap;
 };
+
+struct BlockDpArgs {
+  const uint8_t* text;
+  unsigned long long* stream;
+  const uint4* fblocks;
+  uint32_t fblk_cap;
+  uint32_t* counters;
+  uint32_t* s_bits;
+  uint32_t* e_bits;
+};
+int launch_block_dp(const JbTables& T, const BlockDpArgs& A, bool hmm, int num_sms, cudaStream_t st);
 
 int launch_fused(const JbTables& T, const FusedArgs& A, uint32_t ntiles, bool hmm, cudaStream_t st);
 

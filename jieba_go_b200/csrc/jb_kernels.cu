@@ -16,6 +16,7 @@
 
 #include <stdio.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "../../include/jieba_b200.h"
@@ -1227,7 +1228,7 @@ static bool dalloc(T*& p, uint64_t count) {
 
 void workspace_free(Workspace& ws) {
   void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.rec, ws.gend, ws.wbuf, ws.ends,
-                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.tile_dirty, ws.long_seeds, ws.deferred, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
+                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.tile_dirty, ws.long_seeds, ws.deferred, ws.stream, ws.fblocks, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1253,6 +1254,9 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ws.long_cap = (uint32_t)(cap / 64 + 4096);
     ws.deferred_cap = (uint32_t)(cap / 64 + 4096);
     ok = ok && dalloc(ws.long_seeds, (uint64_t)ws.long_cap) && dalloc(ws.deferred, (uint64_t)ws.deferred_cap);
+    ws.stream_cap = (uint32_t)std::min<uint64_t>(cap + cap / 2 + 65536, 0xFFFF0000ull);  // 8-byte units: 12 B per input byte
+    ws.fblk_cap = (uint32_t)(cap / 4 + 4096);
+    ok = ok && dalloc(ws.stream, (uint64_t)ws.stream_cap) && dalloc(ws.fblocks, (uint64_t)ws.fblk_cap);
     ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8));
     if (!ws.counters) ok = ok && dalloc(ws.counters, (uint64_t)C_NUM);
     if (host_staging) ok = ok && dalloc(ws.text, cap + 64);
@@ -1277,9 +1281,14 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
   return JB_OK;
 }
 
-const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset", "k_fused",      "k_tile_scan+k_resolve_deferred",
-                                                       "long-block kernels", "general pipeline (flagged batches)",
-                                                       "k_rank_count",      "k_rank_scan",  "k_rank_scatter"};
+const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset",
+                                                       "k_fused",
+                                                       "k_block_dp",
+                                                       "k_tile_scan+k_resolve_deferred+long-block kernels",
+                                                       "general pipeline (flagged batches)",
+                                                       "k_rank_count",
+                                                       "k_rank_scan",
+                                                       "k_rank_scatter"};
 
 void profile_collect(Workspace& ws) {
   if (!ws.prof || !ws.prof_pending) return;
@@ -1386,13 +1395,27 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       fa.long_cap = ws.long_cap;
       fa.deferred = ws.deferred;
       fa.deferred_cap = ws.deferred_cap;
+      fa.stream = ws.stream;
+      fa.stream_cap = ws.stream_cap;
+      fa.fblocks = ws.fblocks;
+      fa.fblk_cap = ws.fblk_cap;
       launch_fused(T, fa, ntiles, use_hmm, st);
       g_launches.fetch_add(1);
       PROF(2);
+      BlockDpArgs ba;
+      ba.text = d_text;
+      ba.stream = ws.stream;
+      ba.fblocks = ws.fblocks;
+      ba.fblk_cap = ws.fblk_cap;
+      ba.counters = ws.counters;
+      ba.s_bits = ws.s_bits;
+      ba.e_bits = ws.e_bits;
+      launch_block_dp(T, ba, use_hmm, g_num_sms, st);
+      g_launches.fetch_add(1);
+      PROF(3);
       JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles);
       JB_LAUNCH(k_resolve_deferred, (unsigned)g_num_sms, 256, 0, st, ws.deferred, ws.counters, ws.deferred_cap, ws.tile_ctx, ws.s_bits,
                 ws.e_bits);
-      PROF(3);
       JB_LAUNCH(k_long_extent, (unsigned)g_num_sms * 4, 256, 0, st, T, d_text, n, ws.ds_bits, ws.long_seeds, ws.long_cap, ws.counters,
                 ws.ends, ws.tile_dirty);
       sa.mode = 1;

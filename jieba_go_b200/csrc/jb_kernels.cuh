@@ -30,6 +30,9 @@ enum Counter {
   C_FLAGS = 8,     // bit0: the batch must be redone by the general pipeline
   C_CUR_LDP = 9,   // work cursors of the long-block DP / walk
   C_CUR_LWALK = 10,
+  C_STREAM = 11,   // 8-byte units of the packed candidate stream in use
+  C_N_FBLK = 12,   // Han blocks packed by the fused kernel for k_block_dp
+  C_CUR_FBLK = 13,
   C_NUM = 16
 };
 
@@ -66,6 +69,10 @@ struct Workspace {
   uint32_t long_cap = 0;
   uint4* deferred = nullptr;
   uint32_t deferred_cap = 0;
+  unsigned long long* stream = nullptr;
+  uint32_t stream_cap = 0;
+  uint4* fblocks = nullptr;
+  uint32_t fblk_cap = 0;
   uint32_t* rank_cnt = nullptr;  // per rank tile: token count, then exclusive prefix
   uint32_t* counters = nullptr;  // Counter
   double* dbg_proba = nullptr;   // optional: selected route value per slot
