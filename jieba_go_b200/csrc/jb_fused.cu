@@ -29,14 +29,17 @@ struct FusedSmem {
   uint32_t CW[4];
   uint32_t HS[kFtSlots / 32 + 1], HE[kFtSlots / 32 + 1];
   uint32_t cmask[kFtSlots];
-  uint16_t woff[kFtSlots];
+  // per slot: [0] = wbuf index of its first candidates (stored back to back) | their number << 12 (0xFFFF = not packed);
+  // [1..3] = wbuf indexes of candidates found later by the work-list warp.  Ascending length throughout.
+  uint16_t xi[kFtSlots][4];
+  uint2 wl[kFtWorkList];              // prefix chains still alive after the two straight-line probes
   uint16_t blk[kFtMaxBlocks];      // owned blocks: first slot
   int16_t blk_end[kFtMaxBlocks];   //               last slot, or -1 when the block does not end inside the region
   double wbuf[kFtWCap];
   uint8_t wcls[kFtThreads / 32][40];
   uint16_t pofs[kFtSlots + 2];  // exclusive prefix of stream record sizes
   uint32_t wsum[kFtThreads / 32];
-  uint32_t nblk, wcnt, overflow, npacked, npacked2, sbase, bbase;
+  uint32_t nblk, wcnt, overflow, npacked, npacked2, sbase, bbase, wl_n;
   int first_ks, act_limit;
 };
 
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
     if (tid == 0) {
       S.nblk = 0;
       S.wcnt = 0;
+      S.wl_n = 0;
       S.overflow = 0;
       S.npacked = 0;
       S.first_ks = kFtSlots;
@@ -457,100 +461,129 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
   }
   __syncthreads();
 
-  // ---- F: DAG probe (buildDag T:462-497) for every Han slot of an owned, closed block.  Lanes are
-  // persistent: a lane whose prefix chain ends picks up the next slot of its warp's range at once, so
-  // chains of different length do not leave lanes idle. ----------------------------------------------
+  // ---- F: DAG probe (buildDag T:462-497).  Per Han slot of an owned, closed block: the first-rune
+  // table answers termFreq[string(iRune)] (T:468-472); then up to two more runes are probed in
+  // straight-line code (88 % of all prefix chains end within them); a chain that is still alive goes
+  // on a short work list that one warp finishes.  This is the reference's
+  // `for j := range textRunes[i:]` with its break on the first missing prefix (T:473-482). -------
+  // work-list entry: x = slot | L<<11 | maxlen<<27, y = parent id
   {
     const int first_ks = S.first_ks, act_limit = S.act_limit;
-    const int wend = (warp + 1) * (kFtSlots / (kFtThreads / 32));
-    int next = warp * (kFtSlots / (kFtThreads / 32));
-    bool active = false;
-    int kk = 0;
-    uint32_t L = 0, parent = 0, child = 0, mask = 0, cnt = 0, maxlen = 0, r0 = 0;
-    double wv[4];
-    bool over4 = false;
-    for (;;) {
-      const unsigned idle = __ballot_sync(FULL, !active);
-      bool fin = false;
-      if (idle && next < wend) {
-        const int cand = next + __popc(idle & ((1u << lane) - 1u));
-        next += __popc(idle);
-        if (!active && cand < wend && cand >= first_ks && cand <= act_limit) {
-          const uint32_t cur = S.ri[cand + 1];
-          if (RI_CLS(cur) == 1) {
-            kk = cand;
-            r0 = RI_CP(cur);
-            const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));  // termFreq[string(iRune)] (T:468-472)
-            wv[0] = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
-            mask = 1;
-            cnt = 1;
-            over4 = false;
-            child = f.w;
-            parent = JB_PARENT_FIRST(r0);
-            L = 1;
-            maxlen = (f.z >> 8) & 0xFF;
-            if ((f.z & JB_FIRST_GATE) || maxlen <= 1) fin = true;
-            else active = true;
-          }
+    for (int base = 0; base < kFtSlots; base += kFtThreads) {
+      const int kk = base + tid;
+      const uint32_t cur = S.ri[kk + 1];
+      const bool act = kk >= first_ks && kk <= act_limit && RI_CLS(cur) == 1;
+      uint32_t mask = 0, cnt = 0, L = 1, parent = 0, maxlen = 0;
+      double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+      bool alive = false;
+      if (act) {
+        const uint32_t r0 = RI_CP(cur);
+        const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));
+        w0 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
+        mask = 1;
+        cnt = 1;
+        maxlen = min((f.z >> 8) & 0xFFu, 31u);
+        if (!(f.z & JB_FIRST_GATE) && maxlen > 1 && !((S.HE[kk >> 5] >> (kk & 31)) & 1)) {
+          const uint32_t r1 = RI_CP(S.ri[kk + 2]);
+          alive = (f.w >> jb_bloom_bit(r1)) & 1;
+          parent = JB_PARENT_FIRST(r0);
         }
       }
-      if (active) {  // one step of `for j := range textRunes[i:]`, break on the first missing prefix (T:473-482)
-        const int last = kk + (int)L - 1;
-        bool stop = ((S.HE[last >> 5] >> (last & 31)) & 1) || L >= maxlen;
-        if (!stop) {
+#pragma unroll
+      for (int step = 0; step < 2; step++) {
+        if (alive) {
           const uint32_t rl = RI_CP(S.ri[kk + 1 + L]);
-          const bool may = (L == 1) ? ((child >> jb_bloom_bit(rl)) & 1) : ((child >> jb_bloom11(rl)) & 1);
-          if (!may) {
-            stop = true;
-          } else {
-            double pw;
-            uint32_t prb;
-            const int ps = jb_probe_edge(T.entries, T.hash_mask, parent, rl, &pw, &prb);
-            if (ps < 0) {
-              stop = true;
-            } else {
-              L++;
-              if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481)
-                mask |= 1u << (L - 1);
-                if (cnt < 4) wv[cnt] = pw;
-                else over4 = true;
-                cnt++;
-              }
+          double pw;
+          uint32_t prb;
+          const int ps = jb_probe_edge(T.entries, T.hash_mask, parent, rl, &pw, &prb);
+          alive = false;
+          if (ps >= 0) {  // !found -> break (T:476-478)
+            L++;
+            if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481)
+              mask |= 1u << (L - 1);
+              if (cnt == 1) w1 = pw;
+              else w2 = pw;
+              cnt++;
+            }
+            const int last = kk + (int)L - 1;
+            if (L < maxlen && !((S.HE[last >> 5] >> (last & 31)) & 1)) {
               parent = (uint32_t)ps;
-              child = prb >> 21;
+              alive = ((prb >> 21) >> jb_bloom11(RI_CP(S.ri[kk + 1 + L]))) & 1;
             }
           }
-        }
-        if (stop) {
-          active = false;
-          fin = true;
         }
       }
-      if (fin) {
-        const uint32_t off = atomicAdd(&S.wcnt, cnt);
+      // weight slots for what was found so far; chains still alive go on the work list
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const uint32_t total = __shfl_sync(FULL, incl, 31);
+      const uint32_t lm = __ballot_sync(FULL, alive);
+      uint32_t wb = 0, lb = 0;
+      if (lane == 0) {
+        if (total) wb = atomicAdd(&S.wcnt, total);
+        if (lm) lb = atomicAdd(&S.wl_n, (uint32_t)__popc(lm));
+      }
+      wb = __shfl_sync(FULL, wb, 0);
+      lb = __shfl_sync(FULL, lb, 0);
+      if (act) {
+        const uint32_t wi = wb + incl - cnt;
         S.cmask[kk] = mask;
-        S.woff[kk] = (uint16_t)off;
-        if (off + cnt <= (uint32_t)kFtWCap) {
-          if (!over4) {
-            for (uint32_t j = 0; j < cnt; j++) S.wbuf[off + j] = wv[j];
-          } else {  // rare: more than 4 candidates -- walk the chain again and store as we go
-            S.wbuf[off] = wv[0];
-            uint32_t pp = JB_PARENT_FIRST(r0), o = 1, LL = 1;
-            while (o < cnt) {
-              double pw;
-              uint32_t prb;
-              const int ps = jb_probe_edge(T.entries, T.hash_mask, pp, RI_CP(S.ri[kk + 1 + LL]), &pw, &prb);
-              if (ps < 0) break;
-              LL++;
-              if (jb_w_positive(pw)) S.wbuf[off + o++] = pw;
-              pp = (uint32_t)ps;
-            }
-          }
+        if (wi + cnt <= (uint32_t)kFtWCap) {
+          S.xi[kk][0] = (uint16_t)(wi | (cnt << 12));
+          S.wbuf[wi] = w0;
+          if (cnt > 1) S.wbuf[wi + 1] = w1;
+          if (cnt > 2) S.wbuf[wi + 2] = w2;
         } else {
+          S.xi[kk][0] = 0;
           S.overflow = 1;
         }
       }
-      if (next >= wend && !__any_sync(FULL, active)) break;
+      if (alive) {
+        const uint32_t li = lb + __popc(lm & ((1u << lane) - 1u));
+        if (li < (uint32_t)kFtWorkList) S.wl[li] = make_uint2((uint32_t)kk | (L << 11) | (maxlen << 27), parent);
+        else S.overflow = 1;
+      }
+    }
+    __syncthreads();
+    // leftovers (about one chain in ten): one thread each, spread over all warps (they are chains of
+    // dependent L2 probes: many warps with a lane or two each hide that latency, one warp would not)
+    {
+      const uint32_t nl = min(S.wl_n, (uint32_t)kFtWorkList);
+      const uint32_t nwarps = kFtThreads / 32;
+      for (uint32_t i = (uint32_t)lane * nwarps + warp; i < nl; i += kFtThreads) {
+        const uint2 e = S.wl[i];
+        const int kk = (int)(e.x & 0x7FFu);
+        uint32_t L = (e.x >> 11) & 31u, parent = e.y;
+        const uint32_t maxlen = e.x >> 27;
+        for (;;) {
+          const uint32_t rl = RI_CP(S.ri[kk + 1 + L]);
+          double pw;
+          uint32_t prb;
+          const int ps = jb_probe_edge(T.entries, T.hash_mask, parent, rl, &pw, &prb);
+          if (ps < 0) break;
+          L++;
+          if (jb_w_positive(pw)) {
+            const uint32_t m = S.cmask[kk];
+            const uint32_t x = __popc(m) - (S.xi[kk][0] >> 12);  // ordinal among the late candidates
+            const uint32_t wi = atomicAdd(&S.wcnt, 1u);
+            S.cmask[kk] = m | (1u << (L - 1));
+            if (wi < (uint32_t)kFtWCap && x < 3u) {
+              S.wbuf[wi] = pw;
+              S.xi[kk][1 + x] = (uint16_t)wi;
+            } else {
+              S.overflow = 1;
+            }
+          }
+          const int last = kk + (int)L - 1;
+          if (L >= maxlen || ((S.HE[last >> 5] >> (last & 31)) & 1)) break;
+          if (!(((prb >> 21) >> jb_bloom11(RI_CP(S.ri[kk + 1 + L]))) & 1)) break;
+          parent = (uint32_t)ps;
+        }
+      }
     }
   }
   __syncthreads();
@@ -572,7 +605,7 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
       else atomicOr(&A.counters[C_FLAGS], 1u);
       S.blk_end[b] = -1;
       if (ke >= 0 && !tile_overflow)
-        for (int k = ks; k <= ke; k++) S.woff[k] = 0xFFFFu;  // not packed
+        for (int k = ks; k <= ke; k++) S.xi[k][0] = 0xFFFFu;  // not packed
     } else {
       atomicAdd(&S.npacked, 1u);
     }
@@ -586,7 +619,7 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
     for (int j = 0; j < kFtSlots / kFtThreads; j++) {
       const int kk = tid * (kFtSlots / kFtThreads) + j;
       uint32_t v = 0;
-      if (kk >= first_ks && kk <= act_limit && RI_CLS(S.ri[kk + 1]) == 1 && S.woff[kk] != 0xFFFFu) v = 1u + __popc(S.cmask[kk]);
+      if (kk >= first_ks && kk <= act_limit && RI_CLS(S.ri[kk + 1]) == 1 && S.xi[kk][0] != 0xFFFFu) v = 1u + __popc(S.cmask[kk]);
       sz[j] = v;
       sum += v;
     }
@@ -633,8 +666,9 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
         const uint32_t off = total - S.pofs[kk + 1];
         const uint32_t m = S.cmask[kk];
         st[off] = (unsigned long long)m | ((unsigned long long)RI_CP(S.ri[kk + 1]) << 32);
-        const uint32_t wo = S.woff[kk];
-        for (uint32_t c = 0; c + 1 < sz[j]; c++) st[off + 1 + c] = (unsigned long long)__double_as_longlong(S.wbuf[wo + c]);
+        const uint32_t x0 = S.xi[kk][0], wi0 = x0 & 0xFFFu, n0 = x0 >> 12;
+        for (uint32_t c = 0; c + 1 < sz[j]; c++)
+          st[off + 1 + c] = (unsigned long long)__double_as_longlong(S.wbuf[c < n0 ? wi0 + c : S.xi[kk][1 + c - n0]]);
       }
       for (uint32_t b = tid; b < nblk; b += kFtThreads) {
         const int ke = S.blk_end[b];

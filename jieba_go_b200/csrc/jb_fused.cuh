@@ -28,7 +28,8 @@ constexpr int kFtSlots = (kFtTileBytes + kFtHaloBytes) / 3;                    /
 constexpr int kFtWords = (kFtTileBytes + kFtHaloBytes) / 32;                   // 120
 constexpr int kFtTileWords = kFtTileBytes / 32;                                // 96
 constexpr int kFtWCap = 2560;                                                  // candidate weights per tile in smem
-constexpr int kFtThreads = 256;
+constexpr int kFtThreads = 640;  // 20 warps: 2 slots per thread, 3 CTAs = 60 warps per SM (the probe chains are latency-bound)
+constexpr int kFtWorkList = 384;  // prefix chains longer than 3 runes per tile (more => the tile goes the general way)
 constexpr int kFtMaxBlocks = 768;
 constexpr int kFtMaxBlockLen = 256;  // longest Han block (runes) the block-DP kernel takes; longer ones go the general way  // owned Han blocks per tile (a block needs >= 4 bytes)
 

@@ -1256,7 +1256,7 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ok = ok && dalloc(ws.long_seeds, (uint64_t)ws.long_cap) && dalloc(ws.deferred, (uint64_t)ws.deferred_cap);
     ws.stream_cap = (uint32_t)std::min<uint64_t>(cap + cap / 2 + 65536, 0xFFFF0000ull);  // 8-byte units: 12 B per input byte
     ws.fblk_cap = (uint32_t)(cap / 4 + 4096);
-    ok = ok && dalloc(ws.stream, (uint64_t)ws.stream_cap) && dalloc(ws.fblocks, (uint64_t)ws.fblk_cap);
+    ok = ok && dalloc(ws.stream, (uint64_t)ws.stream_cap + 64) && dalloc(ws.fblocks, (uint64_t)ws.fblk_cap);
     ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8));
     if (!ws.counters) ok = ok && dalloc(ws.counters, (uint64_t)C_NUM);
     if (host_staging) ok = ok && dalloc(ws.text, cap + 64);
