@@ -249,25 +249,24 @@ def main():
         h_off = doc_off.cpu().numpy().astype(np.uint64)
         h_np = h_text.numpy()
         e_steps = max(2, min(args.steps, 3))
-        tk.cut_batch(h_np, h_off, hmm)  # warm-up (workspace allocation)
+        tk.cut_batch_view(h_np, h_off, hmm).close()  # warm-up (workspace + pinned result buffers)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            r = tk.cut_batch(h_np, h_off, hmm)
+            # the call a user makes: host text in, host (start,end) arrays out (zero-copy views of the
+            # library's pinned result, as the Go shim would slice them); the D2H read is inside
+            with tk.cut_batch_view(h_np, h_off, hmm) as r:
+                e_ntok = r.n_tokens
+                e_last = int(r.end[-1]) if e_ntok else 0
         torch.cuda.synchronize(dev)
         e_dt = (time.perf_counter() - t0) / e_steps
-        assert len(r[0]) == n_tok
+        assert e_ntok == n_tok
         e2e = (e_dt, nbytes + 8 * (ndocs + 1), 8 * n_tok + 8 * (ndocs + 1))
         del h_text
 
     # ---- reductions over ranks (max time, total bytes) ---------------------------------------------
-    t_all = torch.tensor([t_ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
-    b_all = torch.tensor([float(nbytes), float(n_tok)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-        dist.all_reduce(b_all, op=dist.ReduceOp.SUM)
-    t_ms_max, e_dt_max = t_all.tolist()
-    tot_bytes, tot_tok = b_all.tolist()
+    from jieba_go_b200.dist import reduce_max_sum
+    (t_ms_max, e_dt_max), (tot_bytes, tot_tok) = reduce_max_sum([t_ms, e2e[0] if e2e else 0.0], [float(nbytes), float(n_tok)], device=dev)
 
     if rank == 0:
         peak, peak_src = peaks()

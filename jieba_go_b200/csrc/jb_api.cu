@@ -58,7 +58,56 @@ struct jb_result {
   uint32_t* end = nullptr;
   uint64_t* doc_tok = nullptr;
   uint64_t cap = 0;
+  size_t start_bytes = 0, end_bytes = 0, doc_bytes = 0;
 };
+
+// Process-wide pool of pinned host buffers for results: cudaMallocHost of hundreds of MB costs more
+// than the whole pipeline, and callers free one result before asking for the next.
+namespace {
+struct PinBuf {
+  void* p;
+  size_t bytes;
+};
+std::mutex g_pin_mu;
+std::vector<PinBuf> g_pin_pool;
+size_t g_pin_pooled = 0;
+const size_t kPinPoolMax = 6ull << 30;
+
+void* pin_alloc(size_t bytes, size_t* got) {
+  {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pin_pool.size(); i++)
+      if (g_pin_pool[i].bytes >= bytes && g_pin_pool[i].bytes <= bytes * 4 + (1 << 20) &&
+          (best < 0 || g_pin_pool[i].bytes < g_pin_pool[best].bytes))
+        best = i;
+    if (best >= 0) {
+      PinBuf b = g_pin_pool[best];
+      g_pin_pool.erase(g_pin_pool.begin() + best);
+      g_pin_pooled -= b.bytes;
+      *got = b.bytes;
+      return b.p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+  *got = bytes ? bytes : 8;
+  return p;
+}
+
+void pin_free(void* p, size_t bytes) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    if (g_pin_pooled + bytes <= kPinPoolMax && g_pin_pool.size() < 32) {
+      g_pin_pool.push_back(PinBuf{p, bytes});
+      g_pin_pooled += bytes;
+      return;
+    }
+  }
+  cudaFreeHost(p);
+}
+}  // namespace
 
 template <typename T>
 static int upload(jb_tokenizer* tk, const std::vector<T>& v, const T** out) {
@@ -293,9 +342,9 @@ const uint32_t* jb_result_end(const jb_result* r) { return r->end; }
 const uint64_t* jb_result_doc_tok_off(const jb_result* r) { return r->doc_tok; }
 void jb_result_free(jb_result* r) {
   if (!r) return;
-  if (r->start) cudaFreeHost(r->start);
-  if (r->end) cudaFreeHost(r->end);
-  if (r->doc_tok) cudaFreeHost(r->doc_tok);
+  pin_free(r->start, r->start_bytes);
+  pin_free(r->end, r->end_bytes);
+  pin_free(r->doc_tok, r->doc_bytes);
   delete r;
 }
 
@@ -303,18 +352,25 @@ static int result_grow(jb_result* r, uint64_t need) {
   if (need <= r->cap) return JB_OK;
   uint64_t ncap = r->cap ? r->cap : 1024;
   while (ncap < need) ncap = ncap + ncap / 2 + 1024;
-  uint32_t *ns = nullptr, *ne = nullptr;
-  CUDA_TRY(cudaMallocHost(&ns, ncap * 4));
-  CUDA_TRY(cudaMallocHost(&ne, ncap * 4));
+  size_t sb = 0, eb = 0;
+  uint32_t* ns = (uint32_t*)pin_alloc(ncap * 4, &sb);
+  uint32_t* ne = (uint32_t*)pin_alloc(ncap * 4, &eb);
+  if (!ns || !ne) {
+    pin_free(ns, sb);
+    pin_free(ne, eb);
+    return fail(JB_ENOMEM, "pinned host allocation failed");
+  }
   if (r->n_tokens) {
     memcpy(ns, r->start, r->n_tokens * 4);
     memcpy(ne, r->end, r->n_tokens * 4);
   }
-  if (r->start) cudaFreeHost(r->start);
-  if (r->end) cudaFreeHost(r->end);
+  pin_free(r->start, r->start_bytes);
+  pin_free(r->end, r->end_bytes);
   r->start = ns;
   r->end = ne;
-  r->cap = ncap;
+  r->start_bytes = sb;
+  r->end_bytes = eb;
+  r->cap = (sb < eb ? sb : eb) / 4;
   return JB_OK;
 }
 
@@ -354,7 +410,8 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     *out = res;
     return (int)JB_OK;
   };
-  if (cudaMallocHost(&res->doc_tok, (ndocs + 1) * 8) != cudaSuccess) return done(fail(JB_ENOMEM, "cudaMallocHost failed"));
+  res->doc_tok = (uint64_t*)pin_alloc((ndocs + 1) * 8, &res->doc_bytes);
+  if (!res->doc_tok) return done(fail(JB_ENOMEM, "pinned host allocation failed"));
   res->doc_tok[0] = 0;
   cudaStream_t st = slot->stream;
   uint64_t d0 = 0;

@@ -106,6 +106,21 @@ class Tokenizer:
         return self._h
 
     # ---- Cut ------------------------------------------------------------------------------
+    def cut_batch_view(self, text, doc_off, use_hmm: bool):
+        """Like cut_batch, but returns a CutResult whose arrays are zero-copy views of the library's
+        pinned result buffers (what the Go shim slices in place); call .close() when done."""
+        if isinstance(text, (bytes, bytearray)):
+            tarr = np.frombuffer(text, dtype=np.uint8)
+        else:
+            tarr = np.ascontiguousarray(text, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        nd = len(doc_off) - 1
+        r = C.c_void_p()
+        with self._lock:
+            check(self._L.jb_cut_batch(self._h, tarr.ctypes.data if tarr.size else None, doc_off.ctypes.data, nd, int(bool(use_hmm)),
+                                       C.byref(r)), "jb_cut_batch")
+        return CutResult(self._L, r, nd)
+
     def cut_batch(self, text, doc_off, use_hmm: bool):
         """Batched Cut over HOST memory.  text: bytes / uint8 ndarray; doc_off: uint64[ndocs+1].
         -> (start uint32[], end uint32[], doc_tok_off uint64[ndocs+1]); offsets are doc-relative."""
@@ -219,6 +234,41 @@ class Tokenizer:
         if n < 0:
             check(n, "jb_debug_route")
         return be[:n].copy(), bp[:n].copy()
+
+
+class CutResult:
+    """Zero-copy view of a jb_result (library-owned pinned memory) -- valid until close()."""
+
+    def __init__(self, L, handle, ndocs):
+        self._L = L
+        self._r = handle
+        n = L.jb_result_num_tokens(handle)
+        self.n_tokens = n
+        if n:
+            self.start = np.ctypeslib.as_array(L.jb_result_start(handle), shape=(n,))
+            self.end = np.ctypeslib.as_array(L.jb_result_end(handle), shape=(n,))
+        else:
+            self.start = np.zeros(0, np.uint32)
+            self.end = np.zeros(0, np.uint32)
+        self.doc_tok_off = np.ctypeslib.as_array(L.jb_result_doc_tok_off(handle), shape=(ndocs + 1,))
+
+    def close(self):
+        if self._r:
+            self.start = self.end = self.doc_tok_off = None
+            self._L.jb_result_free(self._r)
+            self._r = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _emit_dict_arrays(emit):
