@@ -39,7 +39,7 @@ struct FusedSmem {
   uint8_t wcls[kFtThreads / 32][40];
   uint16_t pofs[kFtSlots + 2];  // exclusive prefix of stream record sizes
   uint32_t wsum[kFtThreads / 32];
-  uint32_t nblk, wcnt, overflow, npacked, npacked2, sbase, bbase, wl_n;
+  uint32_t nblk, wcnt, overflow, npacked, npacked2, sbase, bbase, wl_n, ovf_total, ovf_cur;
   int first_ks, act_limit;
 };
 
@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
       S.wl_n = 0;
       S.overflow = 0;
       S.npacked = 0;
+      S.ovf_total = 0;
       S.first_ks = kFtSlots;
       S.act_limit = -1;
     }
@@ -589,10 +590,12 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
   __syncthreads();
 
   // ---- G: hand the owned blocks to k_block_dp: pack every block's candidates into one stream -------
-  // Stream unit = 8 bytes.  Per position: header (low 32 bits candidate-length mask, bits 32..47 the
-  // rune) followed by one float64 weight per candidate in ascending length.  The tile's positions are
-  // stored in REVERSE slot order, so a block's records are contiguous and start with its last rune --
-  // the order the right-to-left route DP consumes them.
+  // Stream unit = 8 bytes; one 32-byte RECORD (= one L2 sector) per position: header (bits 0..31
+  // candidate-length mask, 32..47 the rune, 48..63 index of its overflow weights) + the first three
+  // float64 weights in ascending length; the rare 4th+ weights go to an overflow area behind the tile's
+  // records.  Records are fixed-size, so k_block_dp can prefetch them ahead of the dependent DP chain.
+  // The tile's positions are stored in REVERSE slot order: a block's records are contiguous and start
+  // with its last rune -- the order the right-to-left route DP consumes them.
   const uint32_t nblk = min(S.nblk, (uint32_t)kFtMaxBlocks);
   const bool tile_overflow = S.overflow != 0;
   for (uint32_t b = tid; b < nblk; b += kFtThreads) {
@@ -612,16 +615,19 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
   }
   __syncthreads();
   {
-    // exclusive scan of record sizes over the slots (5 consecutive slots per thread)
+    // exclusive scan of "packed position" flags over the slots (consecutive slots per thread)
     const int first_ks = S.first_ks, act_limit = tile_overflow ? -1 : S.act_limit;
-    uint32_t sz[kFtSlots / kFtThreads], sum = 0;
+    uint32_t sz[kFtSlots / kFtThreads], sum = 0, ovs = 0;
 #pragma unroll
     for (int j = 0; j < kFtSlots / kFtThreads; j++) {
       const int kk = tid * (kFtSlots / kFtThreads) + j;
       uint32_t v = 0;
-      if (kk >= first_ks && kk <= act_limit && RI_CLS(S.ri[kk + 1]) == 1 && S.xi[kk][0] != 0xFFFFu) v = 1u + __popc(S.cmask[kk]);
+      if (kk >= first_ks && kk <= act_limit && RI_CLS(S.ri[kk + 1]) == 1 && S.xi[kk][0] != 0xFFFFu) {
+        v = (uint32_t)__popc(S.cmask[kk]);  // candidates of this position (>= 1)
+        if (v > 3) ovs += v - 3;
+      }
       sz[j] = v;
-      sum += v;
+      sum += v ? 1u : 0u;
     }
     uint32_t incl = sum;
 #pragma unroll
@@ -630,18 +636,21 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
       if (lane >= o) incl += v;
     }
     if (lane == 31) S.wsum[warp] = incl;
+    ovs = __reduce_add_sync(FULL, ovs);
+    if (lane == 0 && ovs) atomicAdd(&S.ovf_total, ovs);
     __syncthreads();
     uint32_t pre = incl - sum;
     for (int w = 0; w < warp; w++) pre += S.wsum[w];
 #pragma unroll
     for (int j = 0; j < kFtSlots / kFtThreads; j++) {
       S.pofs[tid * (kFtSlots / kFtThreads) + j] = (uint16_t)pre;
-      pre += sz[j];
+      pre += sz[j] ? 1u : 0u;
     }
     if (tid == kFtThreads - 1) {
       S.pofs[kFtSlots] = (uint16_t)pre;
-      // reserve stream space and block descriptors for this tile
-      const uint32_t total = pre, np = S.npacked;
+      // reserve stream space (4 units per position + the overflow weights, rounded to whole records so that
+      // every record stays 32-byte aligned) and block descriptors for this tile
+      const uint32_t total = (4u * pre + S.ovf_total + 3u) & ~3u, np = S.npacked;
       uint32_t sbase = 0, bbase = 0;
       if (np) {
         sbase = atomicAdd(&A.counters[C_STREAM], total);
@@ -654,28 +663,39 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
       S.sbase = sbase;
       S.bbase = bbase;
       S.npacked2 = 0;
+      S.ovf_cur = 0;
     }
     __syncthreads();
     if (S.npacked) {
-      const uint32_t total = S.pofs[kFtSlots], sbase = S.sbase;
+      const uint32_t npos_t = S.pofs[kFtSlots], sbase = S.sbase;
       unsigned long long* __restrict__ st = A.stream + sbase;
 #pragma unroll
       for (int j = 0; j < kFtSlots / kFtThreads; j++) {
         const int kk = tid * (kFtSlots / kFtThreads) + j;
-        if (!sz[j]) continue;
-        const uint32_t off = total - S.pofs[kk + 1];
-        const uint32_t m = S.cmask[kk];
-        st[off] = (unsigned long long)m | ((unsigned long long)RI_CP(S.ri[kk + 1]) << 32);
+        const uint32_t cnt = sz[j];
+        if (!cnt) continue;
+        const uint32_t r = npos_t - S.pofs[kk + 1];  // record index: the tile's positions in reverse slot order
+        uint32_t ovi = 0;
+        if (cnt > 3) ovi = atomicAdd(&S.ovf_cur, cnt - 3);
         const uint32_t x0 = S.xi[kk][0], wi0 = x0 & 0xFFFu, n0 = x0 >> 12;
-        for (uint32_t c = 0; c + 1 < sz[j]; c++)
-          st[off + 1 + c] = (unsigned long long)__double_as_longlong(S.wbuf[c < n0 ? wi0 + c : S.xi[kk][1 + c - n0]]);
+        unsigned long long u[4];
+        u[0] = (unsigned long long)S.cmask[kk] | ((unsigned long long)RI_CP(S.ri[kk + 1]) << 32) | ((unsigned long long)(ovi & 0xFFFFu) << 48);
+#pragma unroll
+        for (uint32_t c = 0; c < 3; c++)
+          u[1 + c] = c < cnt ? (unsigned long long)__double_as_longlong(S.wbuf[c < n0 ? wi0 + c : S.xi[kk][1 + c - n0]]) : 0ull;
+        ulonglong2* rp = reinterpret_cast<ulonglong2*>(st + 4u * r);
+        rp[0] = make_ulonglong2(u[0], u[1]);
+        rp[1] = make_ulonglong2(u[2], u[3]);
+        for (uint32_t c = 3; c < cnt; c++)
+          st[4u * npos_t + ovi + (c - 3)] = (unsigned long long)__double_as_longlong(S.wbuf[c < n0 ? wi0 + c : S.xi[kk][1 + c - n0]]);
       }
       for (uint32_t b = tid; b < nblk; b += kFtThreads) {
         const int ke = S.blk_end[b];
         if (ke < 0) continue;
         const int ks = S.blk[b];
         const uint32_t bi = S.bbase + atomicAdd(&S.npacked2, 1u);
-        A.fblocks[bi] = make_uint4(sbase + total - S.pofs[ke + 1], t0 + 3 * ks - 2 + RI_PHI(S.ri[ks + 1]), (uint32_t)(ke - ks + 1), 0u);
+        A.fblocks[bi] = make_uint4(sbase + 4u * (npos_t - S.pofs[ke + 1]), t0 + 3 * ks - 2 + RI_PHI(S.ri[ks + 1]), (uint32_t)(ke - ks + 1),
+                                   sbase + 4u * npos_t);
       }
     }
   }
@@ -755,22 +775,34 @@ __global__ void __launch_bounds__(kBdThreads) k_block_dp(const JbTables T, const
     // NOTE: a warp takes 32 blocks at a time and each lane runs its block to completion; lanes of a
     // warp therefore finish together only as well as their block lengths match (sentence-sized blocks).
     const uint4 desc = A.fblocks[idx];
-    const unsigned long long* __restrict__ st = A.stream + desc.x;
+    const ulonglong2* __restrict__ rp = reinterpret_cast<const ulonglong2*>(A.stream + desc.x);
+    const unsigned long long* __restrict__ ovf = A.stream + desc.w;
     const uint32_t P0 = desc.y;
     const int npos = (int)desc.z;
-    // ---- route DP, right to left ----
-    uint32_t p = 0;
-    for (int k = npos - 1; k >= 0; --k) {
-      const unsigned long long hdr = st[p++];
-      uint32_t m = (uint32_t)hdr;
+    // ---- route DP, right to left: record i belongs to rune npos-1-i; records are prefetched two ahead ----
+    ulonglong2 a0 = __ldcg(rp), b0 = __ldcg(rp + 1), a1 = a0, b1 = b0;
+    if (npos > 1) {
+      a1 = __ldcg(rp + 2);
+      b1 = __ldcg(rp + 3);
+    }
+    for (int i = 0; i < npos; i++) {
+      const int k = npos - 1 - i;
+      ulonglong2 a2 = a1, b2 = b1;
+      if (i + 2 < npos) {
+        a2 = __ldcg(rp + 2 * (i + 2));
+        b2 = __ldcg(rp + 2 * (i + 2) + 1);
+      }
+      uint32_t m = (uint32_t)a0.x;
+      const uint32_t ovi = (uint32_t)(a0.x >> 48);
       double prev = JB_MINF, best_v = 0.0, v = 0.0;
-      uint32_t best_d = 0, d = 0;
+      uint32_t best_d = 0, d = 0, j = 0;
       while (m) {
         d = __ffs(m);
         m &= m - 1;
-        const double w = __longlong_as_double((long long)st[p++]);
+        const unsigned long long wu = j == 0 ? a0.y : (j == 1 ? b0.x : (j == 2 ? b0.y : ovf[ovi + j - 3]));
+        j++;
         const double nxt = (k + (int)d >= npos) ? 0.0 : ring[((k + d) & (RING - 1)) * kBdThreads + tid];  // {j,0.0} at the end (T:522)
-        v = w + nxt;  // pieceFreq + nextBestPiece.proba (T:529)
+        v = __longlong_as_double((long long)wu) + nxt;  // pieceFreq + nextBestPiece.proba (T:529)
         if (v >= prev) {  // maxIndexProba: compare with the PREVIOUS candidate (T:569)
           best_d = d;
           best_v = v;
@@ -783,9 +815,13 @@ __global__ void __launch_bounds__(kBdThreads) k_block_dp(const JbTables T, const
       }
       ring[(k & (RING - 1)) * kBdThreads + tid] = best_v;
       path[k * kBdThreads + tid] = (uint8_t)best_d;
+      a0 = a1;
+      b0 = b1;
+      a1 = a2;
+      b1 = b2;
     }
     // ---- forward walk + HMM ----
-    uint8_t* bp = reinterpret_cast<uint8_t*>(A.stream + desc.x);  // the block's stream is dead now: Viterbi back-pointers
+    uint8_t* bp = reinterpret_cast<uint8_t*>(A.stream + desc.x);  // the block's records are dead now: Viterbi back-pointers
     int k = 0;
     uint32_t run_n = 0;
     int run_s = 0;
