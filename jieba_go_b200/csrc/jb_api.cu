@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -43,6 +44,8 @@ struct jb_tokenizer {
   int device = 0;
   JbTables T;
   std::vector<void*> dev_allocs;
+  void* table_base = nullptr;
+  size_t table_bytes = 0;
   uint64_t max_batch = 256ull << 20;
   double w_per_slot = 3.0;
   int force_general = 0;  // 1: skip the fused fast path (tests / debugging)
@@ -109,12 +112,17 @@ void pin_free(void* p, size_t bytes) {
 }
 }  // namespace
 
+// All tables live in ONE device allocation (256-byte aligned sub-ranges), so a single L2 access-policy
+// window can keep them resident while gigabytes of one-touch text and records stream through the cache.
 template <typename T>
-static int upload(jb_tokenizer* tk, const std::vector<T>& v, const T** out) {
-  void* p = nullptr;
-  size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
-  CUDA_TRY(cudaMalloc(&p, bytes));
-  tk->dev_allocs.push_back(p);
+static size_t arena_reserve(size_t& off, const std::vector<T>& v) {
+  size_t at = off;
+  off += (((v.size() ? v.size() : 1) * sizeof(T)) + 255) & ~(size_t)255;
+  return at;
+}
+template <typename T>
+static int arena_put(jb_tokenizer* tk, size_t at, const std::vector<T>& v, const T** out) {
+  char* p = (char*)tk->table_base + at;
   if (v.size()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   *out = (const T*)p;
   return JB_OK;
@@ -247,12 +255,27 @@ int jb_tokenizer_create(const jb_dict_desc* dict, const jb_hmm_desc* hmm, const 
   if (tk->max_batch > (1ull << 31) - (1ull << 20)) tk->max_batch = (1ull << 31) - (1ull << 20);
   JbTables& T = tk->T;
   memset(&T, 0, sizeof T);
-  rc = upload(tk, img.first, &T.first);
-  if (rc == JB_OK) rc = upload(tk, img.entries, &T.entries);
-  if (rc == JB_OK) rc = upload(tk, img.emit, &T.emit);
-  if (rc == JB_OK) rc = upload(tk, img.emit_supp_rune, &T.emit_supp_rune);
-  if (rc == JB_OK) rc = upload(tk, img.emit_supp, &T.emit_supp);
-  if (rc == JB_OK) rc = upload(tk, img.han_bits, &T.han_bits);
+  size_t off = 0;
+  const size_t o_first = arena_reserve(off, img.first), o_ent = arena_reserve(off, img.entries), o_han = arena_reserve(off, img.han_bits),
+               o_emit = arena_reserve(off, img.emit), o_er = arena_reserve(off, img.emit_supp_rune), o_es = arena_reserve(off, img.emit_supp);
+  if (cudaMalloc(&tk->table_base, off) != cudaSuccess) {
+    delete tk;
+    return fail(JB_ENOMEM, "device allocation of the dictionary tables failed");
+  }
+  tk->dev_allocs.push_back(tk->table_base);
+  tk->table_bytes = off;
+  rc = arena_put(tk, o_first, img.first, &T.first);
+  if (rc == JB_OK) rc = arena_put(tk, o_ent, img.entries, &T.entries);
+  if (rc == JB_OK) rc = arena_put(tk, o_han, img.han_bits, &T.han_bits);
+  if (rc == JB_OK) rc = arena_put(tk, o_emit, img.emit, &T.emit);
+  if (rc == JB_OK) rc = arena_put(tk, o_er, img.emit_supp_rune, &T.emit_supp_rune);
+  if (rc == JB_OK) rc = arena_put(tk, o_es, img.emit_supp, &T.emit_supp);
+  {
+    // set aside L2 for persisting accesses (best effort; the window itself is set per stream at launch time)
+    int maxp = 0;
+    cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxp, off + (8u << 20)));
+  }
   if (rc != JB_OK) {
     jb_tokenizer_destroy(tk);
     return rc;
@@ -426,6 +449,8 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
       rc = workspace_reserve(slot->ws, nb, nd, wps, true);
       if (rc != JB_OK) return done(fail(rc, "device workspace allocation failed"));
       Workspace& ws = slot->ws;
+      ws.l2_base = tk->table_base;
+      ws.l2_bytes = tk->table_bytes;
       if (nb) CUDA_TRY(cudaMemcpyAsync(ws.text, text + doc_off[d0], nb, cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, doc_off + d0, (nd + 1) * 8, cudaMemcpyHostToDevice, st));
       rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nb, ws.doc_off64, nd, use_hmm != 0, nullptr, nullptr, 0, ws.out_doc_tok,
@@ -484,6 +509,8 @@ int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, cons
   std::lock_guard<std::mutex> g(tk->dev_mu);
   int rc = workspace_reserve(tk->dev_ws.ws, nbytes, ndocs, tk->w_per_slot, false);
   if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
+  tk->dev_ws.ws.l2_base = tk->table_base;
+  tk->dev_ws.ws.l2_bytes = tk->table_bytes;
   rc = run_pipeline(tk->T, tk->dev_ws.ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, d_start, d_end, cap_tokens,
                     d_doc_tok_off, 0, d_n_tokens, (cudaStream_t)cuda_stream, tk->force_general != 0);
   if (rc != JB_OK) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));

@@ -39,7 +39,8 @@ struct FusedSmem {
   uint8_t wcls[kFtThreads / 32][40];
   uint16_t pofs[kFtSlots + 2];  // exclusive prefix of stream record sizes
   uint32_t wsum[kFtThreads / 32];
-  uint32_t nblk, wcnt, overflow, npacked, npacked2, sbase, bbase, wl_n, ovf_total, ovf_cur;
+  uint32_t nblk, wcnt, overflow, npacked, npacked2, sbase, bbase, wl_n, ovf_total, ovf_cur, n_o3;
+  uint16_t o3[kFtTileBytes / 3 + 8];  // slots of the tile that hold a 3-byte non-Han, non-space rune (gated tokens)
   int first_ks, act_limit;
 };
 
@@ -180,6 +181,55 @@ __device__ __forceinline__ int f_find_start(const uint32_t* HS, int kk) {
   }
 }
 
+// exact per-byte rules for the 32-byte word g of the tile (one warp, one byte per lane)
+template <int NT>
+__device__ __forceinline__ void f_pb_word(FusedSmem& S, const FCtx& cx, const JbTables& T, const FusedArgs& A, uint32_t t0, uint32_t n,
+                                          int g, int lane, int warp) {
+    const int q = 32 * g + lane, i = q + kFtLeft;
+    const uint8_t c = f_pb_cls(S, cx, T, i);
+    S.wcls[warp][4 + lane] = c;
+    if (lane < 4) S.wcls[warp][lane] = f_pb_cls(S, cx, T, i - 4);
+    __syncwarp();
+    const uint32_t P = t0 + q;
+    const uint32_t cl = c >> 3, len = c & 7;
+    const bool start = c != 0 && P < n;
+    const bool han = cl == PCL_HAN;
+    uint32_t pc = PCL_OTHER;
+    for (int k = 1; k <= 4; k++) {
+      uint8_t c2 = S.wcls[warp][4 + lane - k];
+      if (c2) {
+        pc = c2 >> 3;
+        break;
+      }
+    }
+    __syncwarp();
+    if (start && han && len == 4) atomicOr(&A.counters[C_FLAGS], 1u);  // 4-byte Han: general pipeline redoes the batch
+    const bool dsq = start && (P == 0 || cx.ds_at(i));
+    const bool bnd = start && (dsq || (han != (pc == PCL_HAN)));
+    const bool aln = start && cl == PCL_ALNUM;
+    bool nsa = false, nea = false, gs = false;
+    if (start && !han && q < kFtTileBytes) {
+      if (cl == PCL_ALNUM) {  // alnum run = one token (T:298-299)
+        nsa = dsq || !f_is_alnum(S.sb[i - 1]);
+        nea = P + 1 >= n || cx.ds_at(i + 1) || !f_is_alnum(S.sb[i + 1]);
+      } else if (cl != PCL_SPACE) {  // any other rune is its own token, spaces are skipped (T:301-306)
+        gs = true;
+        f_set(S.GE, q + (int)len - 1);
+      }
+    }
+    uint32_t wb = __ballot_sync(FULL, bnd), wa = __ballot_sync(FULL, aln), w1 = __ballot_sync(FULL, nsa), w2 = __ballot_sync(FULL, nea),
+             w3 = __ballot_sync(FULL, gs);
+    if (lane == 0) {
+      if (wb) atomicOr(&S.BND[g], wb);
+      if (wa) atomicOr(&S.ALN[g], wa);
+      if (g < kFtTileWords) {
+        if (w1) atomicOr(&S.S[g], w1);
+        if (w2) atomicOr(&S.E[g], w2);
+        if (w3) atomicOr(&S.GS[g], w3);
+      }
+    }
+}
+
 template <bool HMM>
 __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const FusedArgs A) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -197,7 +247,7 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
       int64_t P = (int64_t)t0 - kFtLeft + c * 16;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (aligned && P >= 0 && P + 16 <= (int64_t)n) {
-        v = __ldg(reinterpret_cast<const uint4*>(A.text + P));
+        v = __ldcs(reinterpret_cast<const uint4*>(A.text + P));  // read once: evict first
       } else if (P + 16 > 0 && P < (int64_t)n) {
         uint8_t* vb = reinterpret_cast<uint8_t*>(&v);
         for (int j = 0; j < 16; j++) {
@@ -230,6 +280,7 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
       S.overflow = 0;
       S.npacked = 0;
       S.ovf_total = 0;
+      S.n_o3 = 0;
       S.first_ks = kFtSlots;
       S.act_limit = -1;
     }
@@ -311,70 +362,37 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
     const bool bnd = ccl && (ds || (han && seam_prev) || (!seam_prev && ((pcl == 1) != han)));
     if (bnd && q >= 0 && q < kFtWords * 32) f_set(S.BND, q);
     uint32_t hs = __ballot_sync(FULL, bstart), he = __ballot_sync(FULL, bend);
+    const bool o3 = ccl == 2 && q >= 0 && q < kFtTileBytes;
+    const uint32_t om = __ballot_sync(FULL, o3);
+    uint32_t ob = 0;
     if (lane == 0) {
       S.HS[kk >> 5] = hs;
       S.HE[kk >> 5] = he;
+      if (om) ob = atomicAdd(&S.n_o3, (uint32_t)__popc(om));
     }
+    ob = __shfl_sync(FULL, ob, 0);
+    if (o3) S.o3[ob + __popc(om & ((1u << lane) - 1u))] = (uint16_t)kk;
   }
   __syncthreads();
 
   // ---- C: exact per-byte rules on the words that need them (ASCII, 2/4-byte runes, ill-formed) ----
-  for (int g = warp; g < kFtWords; g += kFtThreads / 32) {
-    if (!((S.CW[g >> 5] >> (g & 31)) & 1)) continue;  // warp-uniform
-    const int q = 32 * g + lane, i = q + kFtLeft;
-    const uint8_t c = f_pb_cls(S, cx, T, i);
-    S.wcls[warp][4 + lane] = c;
-    if (lane < 4) S.wcls[warp][lane] = f_pb_cls(S, cx, T, i - 4);
-    __syncwarp();
-    const uint32_t P = t0 + q;
-    const uint32_t cl = c >> 3, len = c & 7;
-    const bool start = c != 0 && P < n;
-    const bool han = cl == PCL_HAN;
-    uint32_t pc = PCL_OTHER;
-    for (int k = 1; k <= 4; k++) {
-      uint8_t c2 = S.wcls[warp][4 + lane - k];
-      if (c2) {
-        pc = c2 >> 3;
-        break;
-      }
-    }
-    __syncwarp();
-    if (start && han && len == 4) atomicOr(&A.counters[C_FLAGS], 1u);  // 4-byte Han: general pipeline redoes the batch
-    const bool dsq = start && (P == 0 || cx.ds_at(i));
-    const bool bnd = start && (dsq || (han != (pc == PCL_HAN)));
-    const bool aln = start && cl == PCL_ALNUM;
-    bool nsa = false, nea = false, gs = false;
-    if (start && !han && q < kFtTileBytes) {
-      if (cl == PCL_ALNUM) {  // alnum run = one token (T:298-299)
-        nsa = dsq || !f_is_alnum(S.sb[i - 1]);
-        nea = P + 1 >= n || cx.ds_at(i + 1) || !f_is_alnum(S.sb[i + 1]);
-      } else if (cl != PCL_SPACE) {  // any other rune is its own token, spaces are skipped (T:301-306)
-        gs = true;
-        f_set(S.GE, q + (int)len - 1);
-      }
-    }
-    uint32_t wb = __ballot_sync(FULL, bnd), wa = __ballot_sync(FULL, aln), w1 = __ballot_sync(FULL, nsa), w2 = __ballot_sync(FULL, nea),
-             w3 = __ballot_sync(FULL, gs);
-    if (lane == 0) {
-      if (wb) atomicOr(&S.BND[g], wb);
-      if (wa) atomicOr(&S.ALN[g], wa);
-      if (g < kFtTileWords) {
-        if (w1) atomicOr(&S.S[g], w1);
-        if (w2) atomicOr(&S.E[g], w2);
-        if (w3) atomicOr(&S.GS[g], w3);
-      }
+  // complex words only: the n-th set bit of CW goes to warp n mod (number of warps)
+  for (int cw = 0, seen = 0; cw < 4; cw++) {
+    uint32_t bits = S.CW[cw];
+    while (bits) {
+      const int g = cw * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      if ((seen++ % (kFtThreads / 32)) != warp || g >= kFtWords) continue;
+      f_pb_word<kFtThreads>(S, cx, T, A, t0, n, g, lane, warp);
     }
   }
   __syncthreads();
-
   // ---- D: gated single-rune tokens (cutNonZh drops a block without [a-zA-Z0-9], T:290-293) ----
   // (1) 3-byte non-Han runes in clean words, straight from the slot table
-  for (int base = 0; base < kFtSlots; base += kFtThreads) {
-    const int kk = base + tid;
+  for (uint32_t oi = tid; oi < S.n_o3; oi += kFtThreads) {
+    const int kk = S.o3[oi];
     const uint32_t cur = S.ri[kk + 1];
-    if (RI_CLS(cur) != 2) continue;
     const int q = 3 * kk - 2 + (int)RI_PHI(cur);
-    if (q < 0 || q >= kFtTileBytes) continue;
     if ((S.CW[(q >> 5) >> 5] >> ((q >> 5) & 31)) & 1) continue;  // that word went through C
     uint32_t r = f_block_alnum(S.BND, S.ALN, q);
     if (r == 1) {
@@ -640,7 +658,15 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
     if (lane == 0 && ovs) atomicAdd(&S.ovf_total, ovs);
     __syncthreads();
     uint32_t pre = incl - sum;
-    for (int w = 0; w < warp; w++) pre += S.wsum[w];
+    {  // exclusive prefix of the warps' sums: one shuffle scan per warp
+      uint32_t ws = lane < kFtThreads / 32 ? S.wsum[lane] : 0u, wi = ws;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(FULL, wi, o);
+        if (lane >= o) wi += v;
+      }
+      pre += __shfl_sync(FULL, wi - ws, warp);
+    }
 #pragma unroll
     for (int j = 0; j < kFtSlots / kFtThreads; j++) {
       S.pofs[tid * (kFtSlots / kFtThreads) + j] = (uint16_t)pre;
@@ -683,11 +709,12 @@ __global__ void __launch_bounds__(kFtThreads) k_fused(const JbTables T, const Fu
 #pragma unroll
         for (uint32_t c = 0; c < 3; c++)
           u[1 + c] = c < cnt ? (unsigned long long)__double_as_longlong(S.wbuf[c < n0 ? wi0 + c : S.xi[kk][1 + c - n0]]) : 0ull;
+        // one-touch data: streaming stores, so that the record stream does not evict the hash table from L2
         ulonglong2* rp = reinterpret_cast<ulonglong2*>(st + 4u * r);
-        rp[0] = make_ulonglong2(u[0], u[1]);
-        rp[1] = make_ulonglong2(u[2], u[3]);
+        __stcs(rp, make_ulonglong2(u[0], u[1]));
+        __stcs(rp + 1, make_ulonglong2(u[2], u[3]));
         for (uint32_t c = 3; c < cnt; c++)
-          st[4u * npos_t + ovi + (c - 3)] = (unsigned long long)__double_as_longlong(S.wbuf[c < n0 ? wi0 + c : S.xi[kk][1 + c - n0]]);
+          __stcs(st + 4u * npos_t + ovi + (c - 3), (unsigned long long)__double_as_longlong(S.wbuf[c < n0 ? wi0 + c : S.xi[kk][1 + c - n0]]));
       }
       for (uint32_t b = tid; b < nblk; b += kFtThreads) {
         const int ke = S.blk_end[b];
@@ -780,17 +807,17 @@ __global__ void __launch_bounds__(kBdThreads) k_block_dp(const JbTables T, const
     const uint32_t P0 = desc.y;
     const int npos = (int)desc.z;
     // ---- route DP, right to left: record i belongs to rune npos-1-i; records are prefetched two ahead ----
-    ulonglong2 a0 = __ldcg(rp), b0 = __ldcg(rp + 1), a1 = a0, b1 = b0;
+    ulonglong2 a0 = __ldcs(rp), b0 = __ldcs(rp + 1), a1 = a0, b1 = b0;
     if (npos > 1) {
-      a1 = __ldcg(rp + 2);
-      b1 = __ldcg(rp + 3);
+      a1 = __ldcs(rp + 2);
+      b1 = __ldcs(rp + 3);
     }
     for (int i = 0; i < npos; i++) {
       const int k = npos - 1 - i;
       ulonglong2 a2 = a1, b2 = b1;
       if (i + 2 < npos) {
-        a2 = __ldcg(rp + 2 * (i + 2));
-        b2 = __ldcg(rp + 2 * (i + 2) + 1);
+        a2 = __ldcs(rp + 2 * (i + 2));
+        b2 = __ldcs(rp + 2 * (i + 2) + 1);
       }
       uint32_t m = (uint32_t)a0.x;
       const uint32_t ovi = (uint32_t)(a0.x >> 48);

@@ -15,6 +15,7 @@
 #include "jb_fused.cuh"
 
 #include <stdio.h>
+#include <string.h>
 
 #include <algorithm>
 #include <atomic>
@@ -1332,6 +1333,25 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       if (!ws.ev[i]) cudaEventCreate(&ws.ev[i]);
   }
   PROF(0);
+  if (ws.l2_base && ws.l2_bytes) {
+    // keep the dictionary tables resident in L2: everything else that flows through the cache is one-touch
+    static int max_win = -1;
+    if (max_win < 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    }
+    if (max_win > 0) {
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof av);
+      av.accessPolicyWindow.base_ptr = ws.l2_base;
+      av.accessPolicyWindow.num_bytes = std::min<size_t>(ws.l2_bytes, (size_t)max_win);
+      av.accessPolicyWindow.hitRatio = 1.0f;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
+  }
   cudaMemsetAsync(ws.counters, 0, C_NUM * sizeof(uint32_t), st);
   cudaMemsetAsync(ws.ds_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.s_bits, 0, ((uint64_t)nwords + 4) * 4, st);

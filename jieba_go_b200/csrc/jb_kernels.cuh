@@ -46,6 +46,9 @@ struct Workspace {
   cudaEvent_t ev[kNumProfKernels + 1] = {};
   double prof_ms[kNumProfKernels] = {};
   uint64_t prof_steps = 0;
+  // dictionary tables (one allocation): L2 access-policy window set around the pipeline
+  void* l2_base = nullptr;
+  size_t l2_bytes = 0;
   // capacity
   uint64_t cap_bytes = 0;
   uint32_t w_per_tile = 0;  // candidate weights reserved per tile
