@@ -50,39 +50,54 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons DURING the timed region (NVML)."""
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, every 5 ms)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index = index
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
         self._halt = threading.Event()
-
-    def run(self):
+        self._nv = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
+            self._nv = nv
+            self._h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+            self._names = {
                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             }
-            while not self._halt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.05)
         except Exception as e:  # pragma: no cover
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
+    def _sample(self):
+        nv = self._nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for bit, name in self._names.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def run(self):
+        if self._nv is None:
+            return
+        try:
+            while not self._halt.is_set():
+                self._sample()
+                time.sleep(0.005)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add("nvml_error:%s" % type(e).__name__)
+
     def stop(self):
+        if self._nv is not None and self.is_alive():
+            try:
+                self._sample()  # at least one sample taken while the GPU is still busy/just finished
+            except Exception:
+                pass
         self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
