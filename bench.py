@@ -203,7 +203,7 @@ def main():
 
     sd = synth.make_dictionary(n_words=args.dict_words, seed=synth.SEED_BASE)
     emit = synth.make_emit(sd)
-    tk = Tokenizer.from_dict_text(sd.dict_txt(), 1, emit, device=local_rank, max_batch_bytes=(1 << 31) - (2 << 20))
+    tk = Tokenizer.from_dict_text(sd.dict_txt(), 1, emit, device=local_rank)  # host batches: default 256 MiB sub-batches, pipelined
     L = _capi.lib()
     # each rank cuts its own shard (documents are independent; no collective on the data path)
     text, doc_off = synth.make_corpus(sd, cfg["kind"], args.bytes, synth.SEED_BASE + args.config + 1000 * rank, device=dev)
@@ -264,7 +264,8 @@ def main():
         h_off = doc_off.cpu().numpy().astype(np.uint64)
         h_np = h_text.numpy()
         e_steps = max(2, min(args.steps, 3))
-        tk.cut_batch_view(h_np, h_off, hmm).close()  # warm-up (workspace + pinned result buffers)
+        for _ in range(2):  # warm-up (workspaces of both pipeline slots + pinned result buffers)
+            tk.cut_batch_view(h_np, h_off, hmm).close()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):

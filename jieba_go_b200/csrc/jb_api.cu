@@ -38,6 +38,8 @@ struct jb_emit_buf {
 struct WsSlot {
   Workspace ws;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;
+  uint64_t* h_cnt = nullptr;  // pinned: token count + status of the batch in flight
 };
 
 struct jb_tokenizer {
@@ -338,6 +340,8 @@ int jb_tokenizer_create_from_gob(const char* gob_path, int64_t size, const char*
 static void free_slot(WsSlot* s) {
   workspace_free(s->ws);
   if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->ev) cudaEventDestroy(s->ev);
+  if (s->h_cnt) cudaFreeHost(s->h_cnt);
 }
 
 void jb_tokenizer_destroy(jb_tokenizer* tk) {
@@ -397,14 +401,7 @@ static int result_grow(jb_result* r, uint64_t need) {
   return JB_OK;
 }
 
-int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm, jb_result** out) {
-  if (!tk || !out || !doc_off || (ndocs && doc_off[ndocs] > doc_off[0] && !text)) return fail(JB_EINVAL, "null argument");
-  for (uint64_t d = 0; d < ndocs; d++) {
-    if (doc_off[d + 1] < doc_off[d]) return fail(JB_EINVAL, "doc_off must be non-decreasing");
-    if (doc_off[d + 1] - doc_off[d] > tk->max_batch)
-      return fail(JB_ELIMIT, "a document exceeds the device batch size (raise jb_options.max_batch_bytes; hard limit 2 GiB)");
-  }
-  CUDA_TRY(cudaSetDevice(tk->device));
+static WsSlot* take_slot(jb_tokenizer* tk) {
   WsSlot* slot = nullptr;
   {
     std::lock_guard<std::mutex> g(tk->mu);
@@ -415,17 +412,50 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
   }
   if (!slot) {
     slot = new WsSlot();
-    if (cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMallocHost(&slot->h_cnt, 16) != cudaSuccess) {
       delete slot;
-      return fail(JB_ECUDA, "cudaStreamCreate failed");
+      return nullptr;
     }
   }
+  return slot;
+}
+
+// Batched Cut over host memory.  Sub-batches of whole documents (<= max_batch bytes) flow through a
+// two-deep pipeline on two streams / workspaces: the H2D copy of batch i+1 and the D2H copy of batch i-1
+// overlap the kernels of batch i (separate copy engines).
+int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm, jb_result** out) {
+  if (!tk || !out || !doc_off || (ndocs && doc_off[ndocs] > doc_off[0] && !text)) return fail(JB_EINVAL, "null argument");
+  for (uint64_t d = 0; d < ndocs; d++) {
+    if (doc_off[d + 1] < doc_off[d]) return fail(JB_EINVAL, "doc_off must be non-decreasing");
+    if (doc_off[d + 1] - doc_off[d] > tk->max_batch)
+      return fail(JB_ELIMIT, "a document exceeds the device batch size (raise jb_options.max_batch_bytes; hard limit 2 GiB)");
+  }
+  CUDA_TRY(cudaSetDevice(tk->device));
+  // plan: greedy batches of whole documents
+  struct Chunk {
+    uint64_t d0, d1, nb, base;
+    uint64_t nt;
+  };
+  std::vector<Chunk> chunks;
+  for (uint64_t d0 = 0; d0 < ndocs;) {
+    uint64_t d1 = d0 + 1;
+    while (d1 < ndocs && doc_off[d1 + 1] - doc_off[d0] <= tk->max_batch) d1++;
+    chunks.push_back(Chunk{d0, d1, doc_off[d1] - doc_off[d0], 0, 0});
+    d0 = d1;
+  }
+  WsSlot* slots[2] = {take_slot(tk), chunks.size() > 1 ? take_slot(tk) : nullptr};
   jb_result* res = new jb_result();
   res->ndocs = ndocs;
-  int rc = JB_OK;
   auto done = [&](int code) {
-    std::lock_guard<std::mutex> g(tk->mu);
-    tk->free_ws.push_back(slot);
+    for (WsSlot* sl : slots)
+      if (sl) cudaStreamSynchronize(sl->stream);
+    {
+      std::lock_guard<std::mutex> g(tk->mu);
+      for (WsSlot* sl : slots)
+        if (sl) tk->free_ws.push_back(sl);
+    }
     if (code != JB_OK) {
       jb_result_free(res);
       return code;
@@ -433,65 +463,120 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     *out = res;
     return (int)JB_OK;
   };
+  if (!slots[0] || (chunks.size() > 1 && !slots[1])) return done(fail(JB_ECUDA, "stream / event creation failed"));
   res->doc_tok = (uint64_t*)pin_alloc((ndocs + 1) * 8, &res->doc_bytes);
   if (!res->doc_tok) return done(fail(JB_ENOMEM, "pinned host allocation failed"));
   res->doc_tok[0] = 0;
-  cudaStream_t st = slot->stream;
-  uint64_t d0 = 0;
   double wps = tk->w_per_slot;
-  while (d0 < ndocs || (ndocs == 0 && d0 == 0)) {
-    if (ndocs == 0) break;
-    // greedy batch of whole documents
-    uint64_t d1 = d0 + 1;
-    while (d1 < ndocs && doc_off[d1 + 1] - doc_off[d0] <= tk->max_batch) d1++;
-    const uint64_t nb = doc_off[d1] - doc_off[d0], nd = d1 - d0;
+  const uint64_t total_bytes = ndocs ? doc_off[ndocs] - doc_off[0] : 0;
+  int rc = result_grow(res, total_bytes / 6 + 1024);  // typical: one token per ~7 bytes; grows if needed
+  if (rc != JB_OK) return done(rc);
+
+  // stage A: copy in, run the whole pipeline (scatter into the slot's device buffers), copy the count out
+  auto enqueue = [&](size_t ci) -> int {
+    Chunk& c = chunks[ci];
+    WsSlot* sl = slots[ci & 1];
+    cudaStream_t st = sl->stream;
+    int r = workspace_reserve(sl->ws, c.nb, c.d1 - c.d0, wps, true);
+    if (r != JB_OK) return fail(r, "device workspace allocation failed");
+    Workspace& ws = sl->ws;
+    ws.l2_base = tk->table_base;
+    ws.l2_bytes = tk->table_bytes;
+    const uint64_t want = c.nb / 4 + 4096;
+    if (ws.out_cap < want) {
+      if (ws.out_start) cudaFree(ws.out_start);
+      if (ws.out_end) cudaFree(ws.out_end);
+      ws.out_start = ws.out_end = nullptr;
+      ws.out_cap = 0;
+      if (cudaMalloc(&ws.out_start, want * 4) != cudaSuccess || cudaMalloc(&ws.out_end, want * 4) != cudaSuccess)
+        return fail(JB_ENOMEM, "device output allocation failed");
+      ws.out_cap = want;
+    }
+    if (c.nb) CUDA_TRY(cudaMemcpyAsync(ws.text, text + doc_off[c.d0], c.nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, doc_off + c.d0, (c.d1 - c.d0 + 1) * 8, cudaMemcpyHostToDevice, st));
+    r = run_pipeline(tk->T, ws, ws.text, (uint32_t)c.nb, ws.doc_off64, c.d1 - c.d0, use_hmm != 0, ws.out_start, ws.out_end, ws.out_cap,
+                     ws.out_doc_tok, 0, ws.out_ntok, st, tk->force_general != 0);
+    if (r != JB_OK) return fail(r, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    CUDA_TRY(cudaMemcpyAsync(sl->h_cnt, ws.out_ntok, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(sl->ev, st));
+    return JB_OK;
+  };
+
+  uint64_t base = 0;
+  if (!chunks.empty()) {
+    rc = enqueue(0);
+    if (rc != JB_OK) return done(rc);
+  }
+  for (size_t ci = 0; ci < chunks.size(); ci++) {
+    if (ci + 1 < chunks.size()) {
+      rc = enqueue(ci + 1);
+      if (rc != JB_OK) return done(rc);
+    }
+    Chunk& c = chunks[ci];
+    WsSlot* sl = slots[ci & 1];
+    cudaStream_t st = sl->stream;
+    Workspace& ws = sl->ws;
     for (;;) {
-      rc = workspace_reserve(slot->ws, nb, nd, wps, true);
-      if (rc != JB_OK) return done(fail(rc, "device workspace allocation failed"));
-      Workspace& ws = slot->ws;
-      ws.l2_base = tk->table_base;
-      ws.l2_bytes = tk->table_bytes;
-      if (nb) CUDA_TRY(cudaMemcpyAsync(ws.text, text + doc_off[d0], nb, cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, doc_off + d0, (nd + 1) * 8, cudaMemcpyHostToDevice, st));
-      rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nb, ws.doc_off64, nd, use_hmm != 0, nullptr, nullptr, 0, ws.out_doc_tok,
-                        res->n_tokens, ws.out_ntok, st, tk->force_general != 0);
-      if (rc != JB_OK) return done(fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError())));
-      uint64_t cnt[2];
-      CUDA_TRY(cudaMemcpyAsync(cnt, ws.out_ntok, 16, cudaMemcpyDeviceToHost, st));
-      cudaError_t se = cudaStreamSynchronize(st);
+      cudaError_t se = cudaEventSynchronize(sl->ev);
       if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("pipeline failed: ") + cudaGetErrorString(se)));
-      if (cnt[1] & 1) {  // candidate buffer overflow: enlarge and redo this batch
+      if (sl->h_cnt[1] & 1) {  // candidate buffer overflow in the general path: enlarge and redo this batch
         wps = wps * 2 > 30 ? 30 : wps * 2;
+        rc = enqueue(ci);
+        if (rc != JB_OK) return done(rc);
         continue;
       }
-      const uint64_t nt = cnt[0];
-      if (nt > ws.out_cap) {
-        uint64_t ncap = nt + nt / 8 + 1024;
-        if (ws.out_start) cudaFree(ws.out_start);
-        if (ws.out_end) cudaFree(ws.out_end);
-        ws.out_start = ws.out_end = nullptr;
-        ws.out_cap = 0;
-        if (cudaMalloc(&ws.out_start, ncap * 4) != cudaSuccess || cudaMalloc(&ws.out_end, ncap * 4) != cudaSuccess)
-          return done(fail(JB_ENOMEM, "device output allocation failed"));
-        ws.out_cap = ncap;
-      }
-      rc = run_scatter(ws, (uint32_t)nb, nd, ws.out_start, ws.out_end, ws.out_cap, ws.out_doc_tok, res->n_tokens, st);
-      if (rc != JB_OK) return done(fail(rc, "scatter launch failed"));
-      rc = result_grow(res, res->n_tokens + nt);
-      if (rc != JB_OK) return done(rc);
-      if (nt) {
-        CUDA_TRY(cudaMemcpyAsync(res->start + res->n_tokens, ws.out_start, nt * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(res->end + res->n_tokens, ws.out_end, nt * 4, cudaMemcpyDeviceToHost, st));
-      }
-      CUDA_TRY(cudaMemcpyAsync(res->doc_tok + d0, ws.out_doc_tok, (nd + 1) * 8, cudaMemcpyDeviceToHost, st));
-      se = cudaStreamSynchronize(st);
-      if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("pipeline failed: ") + cudaGetErrorString(se)));
-      res->n_tokens += nt;
       break;
     }
-    d0 = d1;
+    const uint64_t nt = sl->h_cnt[0];
+    c.nt = nt;
+    c.base = base;
+    if (nt > ws.out_cap) {  // more tokens than the output guess: enlarge and scatter again (the bitmaps are still there)
+      uint64_t ncap = nt + nt / 8 + 1024;
+      cudaFree(ws.out_start);
+      cudaFree(ws.out_end);
+      ws.out_start = ws.out_end = nullptr;
+      ws.out_cap = 0;
+      if (cudaMalloc(&ws.out_start, ncap * 4) != cudaSuccess || cudaMalloc(&ws.out_end, ncap * 4) != cudaSuccess)
+        return done(fail(JB_ENOMEM, "device output allocation failed"));
+      ws.out_cap = ncap;
+      rc = run_scatter(ws, (uint32_t)c.nb, c.d1 - c.d0, ws.out_start, ws.out_end, ws.out_cap, ws.out_doc_tok, 0, st);
+      if (rc != JB_OK) return done(fail(rc, "scatter launch failed"));
+    }
+    if (base + nt > res->cap) {  // the pinned result must move: no copy may be in flight into the old one
+      for (WsSlot* s2 : slots)
+        if (s2 && s2 != sl) cudaStreamSynchronize(s2->stream);
+      cudaStreamSynchronize(st);
+      res->n_tokens = base;
+      rc = result_grow(res, base + nt + (total_bytes - (doc_off[c.d1] - doc_off[0])) / 6);
+      if (rc != JB_OK) return done(rc);
+    }
+    if (nt) {
+      CUDA_TRY(cudaMemcpyAsync(res->start + base, ws.out_start, nt * 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(res->end + base, ws.out_end, nt * 4, cudaMemcpyDeviceToHost, st));
+    }
+    // (the batch's last entry belongs to the next batch's first document: copy d1-d0 entries, not one more)
+    CUDA_TRY(cudaMemcpyAsync(res->doc_tok + c.d0, ws.out_doc_tok, (c.d1 - c.d0) * 8, cudaMemcpyDeviceToHost, st));
+    base += nt;
+    res->n_tokens = base;
+    // the slot is reused by batch ci+2: its copies must be done before that batch overwrites the buffers
+    if (ci + 2 < chunks.size()) {
+      cudaError_t se = cudaStreamSynchronize(st);
+      if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("copy failed: ") + cudaGetErrorString(se)));
+      // (doc_tok of this batch is final on the host now: make it absolute)
+      for (uint64_t d = c.d0; d < c.d1; d++) res->doc_tok[d] += c.base;
+      c.base = 0;
+    }
   }
-  res->doc_tok[ndocs] = res->n_tokens;
+  for (WsSlot* sl : slots)
+    if (sl) {
+      cudaError_t se = cudaStreamSynchronize(sl->stream);
+      if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("pipeline failed: ") + cudaGetErrorString(se)));
+    }
+  for (Chunk& c : chunks)
+    if (c.base)
+      for (uint64_t d = c.d0; d < c.d1; d++) res->doc_tok[d] += c.base;
+  res->n_tokens = base;
+  res->doc_tok[ndocs] = base;
   return done(JB_OK);
 }
 

@@ -2,7 +2,7 @@
 import csv, re, subprocess, sys, os, collections, tempfile
 rep = sys.argv[1]; fn = sys.argv[2] if len(sys.argv) > 2 else 'k_fusedILb0'; srcfile = sys.argv[3] if len(sys.argv) > 3 else 'jb_fused.cu'
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-root = os.path.dirname(os.path.abspath(__file__))
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(f"cd {tmp} && cuobjdump -xelf all {root}/jieba_go_b200/libjieba_b200.so >/dev/null 2>&1", shell=True)
 cub = [f for f in os.listdir(tmp) if f.startswith(srcfile.replace('.cu', '') + '.sm')][0]
