@@ -13,6 +13,7 @@
 //   k_rank_*        bitmap rank + scatter: token offsets in document order (the appends of Cut)
 #include "jb_kernels.cuh"
 #include "jb_fused.cuh"
+#include "jb_stream.cuh"
 
 #include <stdio.h>
 #include <string.h>
@@ -1229,7 +1230,7 @@ static bool dalloc(T*& p, uint64_t count) {
 
 void workspace_free(Workspace& ws) {
   void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.rec, ws.gend, ws.wbuf, ws.ends,
-                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.tile_dirty, ws.long_seeds, ws.deferred, ws.stream, ws.fblocks, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
+                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.tile_dirty, ws.long_seeds, ws.deferred, ws.stream, ws.fblocks, ws.hs_bits, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1258,6 +1259,8 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ws.stream_cap = (uint32_t)std::min<uint64_t>(cap + cap / 2 + 65536, 0xFFFF0000ull);  // 8-byte units: 12 B per input byte
     ws.fblk_cap = (uint32_t)(cap / 4 + 4096);
     ok = ok && dalloc(ws.stream, (uint64_t)ws.stream_cap + 64) && dalloc(ws.fblocks, (uint64_t)ws.fblk_cap);
+    ok = ok && dalloc(ws.hs_bits, nwords) && dalloc(ws.path, cap / 12 + 64) && dalloc(ws.bp, cap / 3 + 64);
+    ws.blocks_cap = (uint32_t)std::min<uint64_t>(ntiles * kTileSlots + 8, 0xFFFFFFF0ull);
     ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8));
     if (!ws.counters) ok = ok && dalloc(ws.counters, (uint64_t)C_NUM);
     if (host_staging) ok = ok && dalloc(ws.text, cap + 64);
@@ -1283,9 +1286,9 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
 }
 
 const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset",
-                                                       "k_fused",
-                                                       "k_block_dp",
-                                                       "k_tile_scan+k_resolve_deferred+long-block kernels",
+                                                       "k_scan",
+                                                       "k_route",
+                                                       "k_emit+k_tile_scan+k_resolve_deferred",
                                                        "general pipeline (flagged batches)",
                                                        "k_rank_count",
                                                        "k_rank_scan",
@@ -1312,7 +1315,7 @@ static bool g_attr_done = false;
 
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t n, const uint64_t* d_doc_off, uint64_t ndocs,
                  bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens, uint64_t* d_doc_tok_off, uint64_t tok_base,
-                 uint64_t* d_n_tokens, cudaStream_t st, bool force_general) {
+                 uint64_t* d_n_tokens, cudaStream_t st, bool force_general, int path_mode) {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1401,7 +1404,53 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       if (use_hmm) JB_LAUNCH(k_walk<true>, pgrid, kWalkThreads, 0, st, T, wa);
       else JB_LAUNCH(k_walk<false>, pgrid, kWalkThreads, 0, st, T, wa);
     };
-    if (!force_general) {
+    if (!force_general && path_mode == 0) {
+      // ---- fast path: k_scan -> k_route -> k_emit (jb_stream.cu) ----------------------------------
+      const uint32_t nt1 = scan_tiles(n);
+      cudaMemsetAsync(ws.path, 0, ((uint64_t)n / 12 + 16) * 4, st);
+      ScanArgs sc;
+      sc.text = d_text;
+      sc.n = n;
+      sc.ds_bits = ws.ds_bits;
+      sc.s_bits = ws.s_bits;
+      sc.e_bits = ws.e_bits;
+      sc.hs_bits = ws.hs_bits;
+      sc.tile_sum = ws.tile_sum;
+      sc.counters = ws.counters;
+      sc.deferred = ws.deferred;
+      sc.deferred_cap = ws.deferred_cap;
+      sc.blocks = ws.ends;
+      sc.blocks_cap = ws.blocks_cap;
+      launch_scan(T, sc, st);
+      g_launches.fetch_add(1);
+      PROF(2);
+      RouteArgs ra;
+      ra.text = d_text;
+      ra.hs_bits = ws.hs_bits;
+      ra.blocks = ws.ends;
+      ra.blocks_cap = ws.blocks_cap;
+      ra.counters = ws.counters;
+      ra.path = ws.path;
+      launch_route(T, ra, g_num_sms, st);
+      g_launches.fetch_add(1);
+      PROF(3);
+      EmitArgs ea;
+      ea.text = d_text;
+      ea.blocks = ws.ends;
+      ea.blocks_cap = ws.blocks_cap;
+      ea.counters = ws.counters;
+      ea.path = ws.path;
+      ea.bp = ws.bp;
+      ea.s_bits = ws.s_bits;
+      ea.e_bits = ws.e_bits;
+      launch_emit(T, ea, use_hmm, g_num_sms, st);
+      g_launches.fetch_add(1);
+      JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, nt1);
+      JB_LAUNCH(k_resolve_deferred, (unsigned)g_num_sms, 256, 0, st, ws.deferred, ws.counters, ws.deferred_cap, ws.tile_ctx, ws.s_bits,
+                ws.e_bits);
+      PROF(4);
+      JB_LAUNCH(k_fallback_reset, (unsigned)g_num_sms * 4, 256, 0, st, ws.counters, ws.s_bits, ws.e_bits, nwords + 4);
+    } else if (!force_general) {
       // ---- fast path: one fused kernel; leftovers (long blocks, deferred tokens) to small kernels ----
       FusedArgs fa;
       fa.text = d_text;

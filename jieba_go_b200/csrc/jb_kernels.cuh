@@ -33,6 +33,7 @@ enum Counter {
   C_STREAM = 11,   // 8-byte units of the packed candidate stream in use
   C_N_FBLK = 12,   // Han blocks packed by the fused kernel for k_block_dp
   C_CUR_FBLK = 13,
+  C_CUR_EMIT = 14, // work cursor of k_emit
   C_NUM = 16
 };
 
@@ -76,6 +77,10 @@ struct Workspace {
   uint32_t stream_cap = 0;
   uint4* fblocks = nullptr;
   uint32_t fblk_cap = 0;
+  uint32_t* hs_bits = nullptr;   // Han-block start bitmap (k_scan -> k_route)
+  uint32_t* path = nullptr;      // chosen word length - 1 per rune (k_route -> k_emit)
+  uint8_t* bp = nullptr;         // Viterbi back-pointers per rune (k_emit)
+  uint32_t blocks_cap = 0;       // entries of `ends` usable as the stream path's block list
   uint32_t* rank_cnt = nullptr;  // per rank tile: token count, then exclusive prefix
   uint32_t* counters = nullptr;  // Counter
   double* dbg_proba = nullptr;   // optional: selected route value per slot
@@ -95,11 +100,12 @@ void workspace_free(Workspace& ws);
 //   Token (start,end) are written doc-relative into d_start/d_end (up to cap_tokens),
 //   d_doc_tok_off[ndocs+1] gets tok_base + rank, d_n_tokens[0] the batch's token count and
 //   d_n_tokens[1] the status word.
-//   force_general: skip the fused fast path and run the general kernels on everything.
+//   force_general: skip the fast path and run the general kernels on everything.
+//   path_mode: 0 = streaming fast path (jb_stream.cu), 1 = the older fused tile kernel (jb_fused.cu).
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_doc_off,
                  uint64_t ndocs, bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
                  uint64_t* d_doc_tok_off, uint64_t tok_base, uint64_t* d_n_tokens, cudaStream_t stream,
-                 bool force_general = false);
+                 bool force_general = false, int path_mode = 0);
 
 // Second phase when d_start/d_end were NULL in run_pipeline (count first, then scatter).
 int run_scatter(Workspace& ws, uint32_t nbytes, uint64_t ndocs, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,

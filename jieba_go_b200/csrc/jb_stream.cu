@@ -1,0 +1,749 @@
+// Streaming fast path -- see jb_stream.cuh for the contract and DESIGN.md for the measurements.
+// Reference functions restated here: Cut/splitText T:151-210, cutNonZh T:289-310, buildDag T:462-497,
+// calcDagProba T:502-548, maxIndexProba T:565-578, findDagPath T:552-562, cutZh T:221-255,
+// viterbi T:668-730, stateTransitionRoute T:736-756, cutHMM T:273-285  (T = /root/reference/tokenizer.go).
+#include "jb_stream.cuh"
+
+#include "../../include/jieba_b200.h"
+
+namespace jb {
+
+#define FULL 0xFFFFFFFFu
+
+// ==========================================================================================
+// k_scan
+// ==========================================================================================
+enum : uint32_t { SC_HAN = 1, SC_ALNUM = 2, SC_SPACE = 3, SC_OTHER = 4, SC_INVALID = 5 };
+#define SCLS(c, len) (uint8_t)(((c) << 3) | (len))
+
+struct ScanSmem {
+  uint8_t sb[kScRegion];
+  uint32_t dsw[kScThreads + 2];  // dsw[j] <-> global word t0/32 - 2 + j; lane wj's own word is dsw[wj + 1]
+  uint32_t HANL[kScThreads];     // Han rune starts
+  uint32_t ALN[kScThreads];      // ASCII [a-zA-Z0-9] bytes
+  uint32_t BND[kScThreads];      // first byte of every block (Han or not), end of text
+  uint32_t OTE[kScThreads + 1];  // last byte of every non-Han, non-alnum, non-space rune
+  uint32_t S[kScThreads + 1], E[kScThreads + 1];
+  uint32_t wsum[kScThreads / 32];
+  uint32_t ends_base;
+};
+
+__device__ __forceinline__ bool s_is_alnum(uint32_t c) { return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u); }
+// unicode.IsSpace (T:302)
+__device__ __forceinline__ bool s_is_space(uint32_t cp) {
+  if (cp <= 0xFF) return (cp - 9u < 5u) || cp == 0x20 || cp == 0x85 || cp == 0xA0;
+  return cp == 0x1680 || (cp - 0x2000u <= 0xAu) || cp == 0x2028 || cp == 0x2029 || cp == 0x202F || cp == 0x205F || cp == 0x3000;
+}
+__device__ __forceinline__ bool s_is_han(uint32_t cp, const JbTables& T) {
+  if (cp - 0x4E00u < 0x51A6u) return true;  // U+4E00..U+9FA5: Han in every Unicode version the tables cover
+  if (cp < 0x10000) return (__ldg(T.han_bits + (cp >> 5)) >> (cp & 31)) & 1;
+  for (uint32_t i = 0; i < T.n_supp; i++)
+    if (cp >= T.supp_lo[i] && cp <= T.supp_hi[i]) return true;
+  return false;
+}
+
+struct ScCtx {
+  const ScanSmem* s;
+  uint32_t t0, n;
+  // is region index i a document start, or at/after the end of the text?
+  __device__ __forceinline__ bool ds_at(int i) const {
+    int64_t P = (int64_t)t0 - kScLeft + i;
+    if (P >= (int64_t)n) return true;
+    if (P < 0) return false;
+    return (s->dsw[(i + 16) >> 5] >> ((i + 16) & 31)) & 1;
+  }
+};
+// validated length (2..4) of the UTF-8 sequence whose lead byte is at region index i, 0 if ill-formed
+// (Go's decoding rules: RFC 3629 ranges; a document boundary inside the sequence cuts it)
+__device__ __forceinline__ int s_seqlen(const ScanSmem& S, const ScCtx& cx, int i) {
+  uint32_t b = S.sb[i];
+  int len = 0;
+  if (b >= 0xC2 && b <= 0xDF) len = 2;
+  else if (b >= 0xE0 && b <= 0xEF) len = 3;
+  else if (b >= 0xF0 && b <= 0xF4) len = 4;
+  if (!len || i + len > kScRegion) return 0;
+  uint32_t b1 = S.sb[i + 1], lo = 0x80, hi = 0xBF;
+  if (b == 0xE0) lo = 0xA0;
+  if (b == 0xED) hi = 0x9F;
+  if (b == 0xF0) lo = 0x90;
+  if (b == 0xF4) hi = 0x8F;
+  if (b1 < lo || b1 > hi || cx.ds_at(i + 1)) return 0;
+  if (len >= 3 && ((S.sb[i + 2] & 0xC0) != 0x80 || cx.ds_at(i + 2))) return 0;
+  if (len == 4 && ((S.sb[i + 3] & 0xC0) != 0x80 || cx.ds_at(i + 3))) return 0;
+  return len;
+}
+// exact class of the byte at region index i: 0 = interior of a rune, else class << 3 | rune length
+__device__ uint8_t s_byte_class(const ScanSmem& S, const ScCtx& cx, const JbTables& T, int i) {
+  uint32_t b = S.sb[i];
+  if (b < 0x80) return s_is_alnum(b) ? SCLS(SC_ALNUM, 1) : (s_is_space(b) ? SCLS(SC_SPACE, 1) : SCLS(SC_OTHER, 1));
+  if ((b & 0xC0) == 0x80) {
+    for (int k = 1; k <= 3 && i - k >= 0; k++)
+      if ((S.sb[i - k] & 0xC0) != 0x80) return s_seqlen(S, cx, i - k) > k ? 0 : SCLS(SC_INVALID, 1);
+    return SCLS(SC_INVALID, 1);
+  }
+  int len = s_seqlen(S, cx, i);
+  if (!len) return SCLS(SC_INVALID, 1);
+  const uint8_t* p = &S.sb[i];
+  uint32_t cp;
+  if (len == 2) cp = ((p[0] & 0x1Fu) << 6) | (p[1] & 0x3Fu);
+  else if (len == 3) cp = ((p[0] & 0x0Fu) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3Fu);
+  else cp = ((p[0] & 0x07u) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3Fu);
+  return s_is_han(cp, T) ? SCLS(SC_HAN, len) : (s_is_space(cp) ? SCLS(SC_SPACE, len) : SCLS(SC_OTHER, len));
+}
+
+// 4 predicate bits (bit 7 of each byte of x) -> a nibble
+__device__ __forceinline__ uint32_t s_mm4(uint32_t x) { return (((x >> 7) * 0x00204081u) >> 21) & 0xFu; }
+
+struct ScWord {
+  uint32_t c, l3, as, bad;  // nibbles: continuation bytes, E0..EF leads, ASCII; bad != 0: something else (or E0 / ED)
+};
+__device__ __forceinline__ ScWord s_word(uint32_t w) {
+  const uint32_t M = 0x80808080u;
+  const uint32_t t1 = w << 1, t2 = w << 2, t3 = w << 3;
+  const uint32_t cont = w & ~t1 & M;
+  const uint32_t l3 = w & t1 & t2 & ~t3 & M;
+  uint32_t bad = w & t1 & (~t2 | t3) & M;  // 110xxxxx / 1111xxxx leads
+  // E0 and ED leads restrict their second byte (and never start a Han rune): exact rules for those words.
+  // (zero-byte test on the low nibbles; a false positive only sends a clean word the exact way)
+  const uint32_t nib = w & 0x0F0F0F0Fu, nd = nib ^ 0x0D0D0D0Du;
+  bad |= (((nib - 0x01010101u) & ~nib) | ((nd - 0x01010101u) & ~nd)) & l3;
+  ScWord r;
+  r.c = s_mm4(cont);
+  r.l3 = s_mm4(l3);
+  r.as = s_mm4(~w & M);
+  r.bad = bad;
+  return r;
+}
+
+// Does the non-Han block around bit b of word wj hold an ASCII alnum (cutNonZh T:290-293)?  Own words are
+// 1..nown.  returns 1 yes, 0 no, else (2 | need_fwd<<2 | need_bwd<<3) when the block leaves the tile.
+__device__ uint32_t s_block_alnum(const uint32_t* BND, const uint32_t* ALN, int w, int b, int nown) {
+  uint32_t lowmask = (b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u);
+  bool found = false;
+  uint32_t m = BND[w] & lowmask;
+  if (m) {
+    int bb = 31 - __clz(m);
+    if (ALN[w] & lowmask & ~((1u << bb) - 1u)) return 1;
+    found = true;
+  } else {
+    if (ALN[w] & lowmask) return 1;
+    for (int ww = w - 1; ww >= 1; --ww) {
+      m = BND[ww];
+      if (m) {
+        int bb = 31 - __clz(m);
+        if (ALN[ww] & ~((1u << bb) - 1u)) return 1;
+        found = true;
+        break;
+      } else if (ALN[ww])
+        return 1;
+    }
+  }
+  uint32_t need = found ? 0u : 4u;
+  uint32_t highmask = ~lowmask;
+  found = false;
+  m = BND[w] & highmask;
+  if (m) {
+    int bb = __ffs(m) - 1;
+    if (ALN[w] & highmask & ((1u << bb) - 1u)) return 1;
+    found = true;
+  } else {
+    if (ALN[w] & highmask) return 1;
+    for (int ww = w + 1; ww <= nown; ++ww) {
+      m = BND[ww];
+      if (m) {
+        int bb = __ffs(m) - 1;
+        if (ALN[ww] & ((1u << bb) - 1u)) return 1;
+        found = true;
+        break;
+      } else if (ALN[ww])
+        return 1;
+    }
+  }
+  if (!found) need |= 8u;
+  return need ? (2u | need) : 0u;
+}
+
+__global__ void __launch_bounds__(kScThreads, 4) k_scan(const JbTables T, const ScanArgs A) {
+  __shared__ __align__(16) ScanSmem S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wj = tid;  // word index inside the staged region: 0 = halo before, 1..254 own, 255 = halo after
+  const uint32_t tile = blockIdx.x;
+  const uint32_t t0 = tile * (uint32_t)kScTileBytes;
+  const uint32_t n = A.n;
+  ScCtx cx{&S, t0, n};
+
+  // ---- stage the bytes (+ halo) and the document-start words -----------------------------------
+  {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(A.text) & 15) == 0);
+    for (int c = tid; c < kScRegion / 16; c += kScThreads) {
+      const int64_t P = (int64_t)t0 - kScLeft + c * 16;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (aligned && P >= 0 && P + 16 <= (int64_t)n) {
+        v = __ldg(reinterpret_cast<const uint4*>(A.text + P));
+      } else if (P + 16 > 0 && P < (int64_t)n) {
+        uint8_t* vb = reinterpret_cast<uint8_t*>(&v);
+        for (int j = 0; j < 16; j++) {
+          int64_t q = P + j;
+          vb[j] = (q >= 0 && q < (int64_t)n) ? __ldg(A.text + q) : 0;
+        }
+      }
+      *reinterpret_cast<uint4*>(&S.sb[c * 16]) = v;
+    }
+    const uint32_t nwords = (n + 31) / 32;
+    for (int j = tid; j < kScThreads + 2; j += kScThreads) {
+      int64_t gw = (int64_t)(t0 / 32) - 2 + j;
+      S.dsw[j] = (gw >= 0 && gw < (int64_t)nwords) ? __ldg(A.ds_bits + gw) : 0;
+    }
+    S.OTE[tid] = 0;
+    S.S[tid] = 0;
+    S.E[tid] = 0;
+    if (tid == 0) {
+      S.OTE[kScThreads] = 0;
+      S.S[kScThreads] = 0;
+      S.E[kScThreads] = 0;
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 1: per 32-byte word, bitmasks of rune starts / Han / alnum / other-token runes ----
+  const int64_t Pw = (int64_t)t0 - 32 + 32 * (int64_t)wj;  // text position of this lane's word
+  const int base = 16 + 32 * wj;                           // its region index
+  const bool live = Pw >= 0 && Pw < (int64_t)n;
+  const uint32_t D = S.dsw[wj + 1];
+  uint32_t RS = 0, HANL = 0, ALN = 0, OTH = 0;
+  if (live) {
+    const uint32_t VM = (Pw + 32 <= (int64_t)n) ? FULL : ((1u << (uint32_t)(n - Pw)) - 1u);
+    const uint4 qa = *reinterpret_cast<const uint4*>(&S.sb[base]), qb = *reinterpret_cast<const uint4*>(&S.sb[base + 16]);
+    const uint32_t wp = *reinterpret_cast<const uint32_t*>(&S.sb[base - 4]), wn = *reinterpret_cast<const uint32_t*>(&S.sb[base + 32]);
+    const uint32_t ww[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+    uint32_t C = 0, L3 = 0, AS = 0, bad = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const ScWord r = s_word(ww[j]);
+      C |= r.c << (4 * j);
+      L3 |= r.l3 << (4 * j);
+      AS |= r.as << (4 * j);
+      bad |= r.bad;
+    }
+    const ScWord rp = s_word(wp), rn = s_word(wn);
+    const uint32_t Cp = rp.c << 28, L3p = rp.l3 << 28, Cn = rn.c, Dn = S.dsw[wj + 2], Dp = S.dsw[wj];
+    bad |= rp.bad | rn.bad;
+    // every E? lead from byte -3 on is followed by two continuation bytes; every continuation byte is covered
+    bad |= L3 & ~(__funnelshift_r(C, Cn, 1) & __funnelshift_r(C, Cn, 2));
+    bad |= L3p & ~(__funnelshift_r(Cp, C, 1) & __funnelshift_r(Cp, C, 2)) & 0xE0000000u;
+    bad |= C & ~(__funnelshift_l(L3p, L3, 1) | __funnelshift_l(L3p, L3, 2));
+    // no document boundary inside a rune
+    bad |= (D & C) | (Dn & Cn & 3u) | (Dp & Cp & 0x80000000u);
+    if (Pw + 36 > (int64_t)n) bad = 1;
+    if (!bad) {
+      // ---- clean word: ASCII and well-formed 3-byte runes only ----
+      RS = AS | L3;
+      uint32_t SPC = 0;
+      uint32_t m = L3;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const int off = base + b;
+        const uint32_t* wq = reinterpret_cast<const uint32_t*>(&S.sb[off & ~3]);
+        const uint32_t x = __funnelshift_r(wq[0], wq[1], (off & 3) * 8);
+        const uint32_t cp = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
+        if (s_is_han(cp, T)) HANL |= 1u << b;
+        else if (s_is_space(cp)) SPC |= 1u << b;
+      }
+      m = AS;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t c = S.sb[base + b];
+        if (s_is_alnum(c)) ALN |= 1u << b;
+        else if (s_is_space(c)) SPC |= 1u << b;
+      }
+      OTH = RS & ~HANL & ~ALN & ~SPC;  // each its own token if the block holds an alnum (T:301-306)
+      const uint32_t o3 = OTH & L3;
+      const uint32_t ote = (OTH & AS) | (o3 << 2);
+      if (ote) atomicOr(&S.OTE[wj], ote);
+      if (o3 >> 30) atomicOr(&S.OTE[wj + 1], o3 >> 30);
+    } else {
+      // ---- anything else (2/4-byte runes, ill-formed bytes, runes cut by a document boundary, the
+      // end of the text): Go's decoding rules byte by byte ----
+      for (int b = 0; b < 32; b++) {
+        if (!((VM >> b) & 1)) break;
+        const uint8_t c = s_byte_class(S, cx, T, base + b);
+        if (!c) continue;
+        const uint32_t cl = c >> 3, len = c & 7;
+        RS |= 1u << b;
+        if (cl == SC_HAN) {
+          HANL |= 1u << b;
+          if (len == 4) atomicOr(&A.counters[C_FLAGS], 1u);  // 4-byte Han: the general pipeline redoes the batch
+        } else if (cl == SC_ALNUM) {
+          ALN |= 1u << b;
+        } else if (cl != SC_SPACE) {
+          OTH |= 1u << b;
+          const int eb = b + (int)len - 1;
+          atomicOr(&S.OTE[wj + (eb >> 5)], 1u << (eb & 31));
+        }
+      }
+    }
+  }
+  S.HANL[wj] = HANL;
+  S.ALN[wj] = ALN;
+  __syncthreads();
+
+  // ---- stage 2: block boundaries, Han block starts / ends, alnum-run tokens ----------------------
+  const bool own = wj >= 1 && wj <= kScOwnWords && Pw <= (int64_t)n;
+  uint32_t HE = 0;
+  if (own) {
+    const uint32_t Dn = S.dsw[wj + 2];
+    const uint32_t prevHan = __funnelshift_l(S.HANL[wj - 1], HANL, 3);              // rune right before is Han (3 bytes)
+    const uint32_t nextHan = __funnelshift_r(HANL & ~D, S.HANL[wj + 1] & ~Dn, 3);   // Han rune follows in the same document
+    uint32_t BND = RS & (D | (HANL ^ prevHan));
+    if ((int64_t)n < Pw + 32) BND |= 1u << (uint32_t)(n - Pw);  // end of the text
+    const uint32_t HS = HANL & (D | ~prevHan);
+    HE = HANL & ~nextHan;
+    const uint32_t prevAl = __funnelshift_l(S.ALN[wj - 1], ALN, 1);
+    const uint32_t nextAl = __funnelshift_r(ALN & ~D, S.ALN[wj + 1] & ~Dn, 1);
+    S.BND[wj] = BND;
+    S.S[wj] = ALN & (D | ~prevAl);  // an alnum run is one token (T:298-299)
+    S.E[wj] = ALN & ~nextAl;
+    if (Pw < (int64_t)n) A.hs_bits[(uint32_t)(Pw >> 5)] = HS;
+  } else {
+    S.BND[wj] = 0;
+  }
+  // Han block ends -> list, in text order within the tile
+  {
+    const uint32_t cnt = __popc(HE);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) S.wsum[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t tot = 0;
+#pragma unroll
+      for (int j = 0; j < kScThreads / 32; j++) {
+        uint32_t v = S.wsum[j];
+        S.wsum[j] = tot;
+        tot += v;
+      }
+      uint32_t b0 = 0;
+      if (tot) {
+        b0 = atomicAdd(&A.counters[C_N_FBLK], tot);
+        if (b0 + tot > A.blocks_cap) atomicOr(&A.counters[C_FLAGS], 1u);
+      }
+      S.ends_base = b0;
+    }
+    __syncthreads();
+    uint32_t o = S.ends_base + S.wsum[warp] + incl - cnt;
+    uint32_t m = HE;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (o < A.blocks_cap) A.blocks[o] = make_uint2((uint32_t)Pw + b, 0u);
+      o++;
+    }
+  }
+
+  // ---- stage 3: gated single-rune tokens (cutNonZh drops a block without [a-zA-Z0-9], T:290-293) ----
+  if (own) {
+    uint32_t m = OTH;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      // its last byte: first OTE bit at or after it
+      int we = wj;
+      uint32_t em = S.OTE[we] & ~((1u << b) - 1u);
+      if (!em) em = S.OTE[++we];
+      const int eb = __ffs(em) - 1;
+      const uint32_t r = s_block_alnum(S.BND, S.ALN, wj, b, kScOwnWords);
+      if (r == 1) {
+        atomicOr(&S.S[wj], 1u << b);
+        atomicOr(&S.E[we], 1u << eb);
+      } else if (r & 2) {
+        const uint32_t idx = atomicAdd(&A.counters[C_N_DEFER], 1u);
+        if (idx < A.deferred_cap)
+          A.deferred[idx] = make_uint4((uint32_t)Pw + b, (uint32_t)((we - wj) * 32 + eb - b + 1), (r >> 2) & 3u, tile);
+        else atomicOr(&A.counters[C_FLAGS], 1u);
+      }
+    }
+  }
+  // tile summary for k_tile_scan: has a boundary / alnum before the first / alnum after the last
+  if (warp == 0) {
+    int firstw = kScThreads, lastw = -1;
+    for (int j = 1 + lane; j <= kScOwnWords; j += 32)
+      if (S.BND[j]) {
+        firstw = min(firstw, j);
+        lastw = max(lastw, j);
+      }
+    firstw = __reduce_min_sync(FULL, firstw);
+    lastw = __reduce_max_sync(FULL, lastw);
+    bool pre = false, post = false;
+    if (lastw < 0) {
+      for (int j = 1 + lane; j <= kScOwnWords; j += 32) pre |= S.ALN[j] != 0;
+      post = pre;
+    } else {
+      const uint32_t fb = __ffs(S.BND[firstw]) - 1, lb = 31 - __clz(S.BND[lastw]);
+      for (int j = 1 + lane; j <= kScOwnWords; j += 32) {
+        const uint32_t a = S.ALN[j];
+        if (j < firstw) pre |= a != 0;
+        if (j == firstw) pre |= (a & ((1u << fb) - 1u)) != 0;
+        if (j > lastw) post |= a != 0;
+        if (j == lastw) post |= (a & ~((1u << lb) - 1u)) != 0;
+      }
+    }
+    pre = __any_sync(FULL, pre);
+    post = __any_sync(FULL, post);
+    if (lane == 0) A.tile_sum[tile] = (uint8_t)((lastw >= 0 ? 1 : 0) | (pre ? 2 : 0) | (post ? 4 : 0));
+  }
+  __syncthreads();
+  // ---- publish the non-Han token bits (a rune may end in the next tile's first word) --------------
+  if (wj >= 1 && wj <= kScOwnWords + 1) {
+    const int64_t gw = (int64_t)(t0 / 32) - 1 + wj;
+    const uint32_t sbits = S.S[wj], ebits = S.E[wj];
+    if (sbits) atomicOr(&A.s_bits[gw], sbits);
+    if (ebits) atomicOr(&A.e_bits[gw], ebits);
+  }
+}
+
+int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st) {
+  k_scan<<<scan_tiles(A.n), kScThreads, 0, st>>>(T, A);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ==========================================================================================
+// k_route: buildDag + calcDagProba + maxIndexProba, one lane per Han block, right to left.
+//
+// Lane state machine, one step per loop iteration:
+//   POS     decode the rune, first-rune table -> candidate (i,i+1) (T:468-472), selector init
+//   PROBE   one trie-edge probe of the rune-prefix hash = one turn of `for j := range textRunes[i:]`
+//           (T:473-482); a hit with freq > 0 is the next candidate: pieceFreq + next.proba (T:519-529)
+//           folded straight into maxIndexProba's running (prev, best) pair (T:565-578)
+//   COMMIT  the position's selected (length, value); block start reached -> hand the block to k_emit
+// A lane that finishes its block takes the next one from the warp's queue, so all 32 lanes stay busy
+// whatever the block lengths.  Per-lane shared memory: the last RING route values and runes.
+// ==========================================================================================
+constexpr int kRtThreads = 128;
+constexpr int kRtQueue = 64;
+enum : int { ST_IDLE = 0, ST_POS = 1, ST_PROBE = 2, ST_COMMIT = 3 };
+
+template <int RING, int PB>
+__global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const RouteArgs A) {
+  __shared__ double ring[RING][kRtThreads];
+  __shared__ uint32_t rr[RING][kRtThreads];
+  constexpr uint32_t M = RING - 1;
+  constexpr uint32_t PPW = 32 / PB;  // path entries per word
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t nblocks = min(A.counters[C_N_FBLK], A.blocks_cap);
+  if (A.counters[C_FLAGS] & 1u) return;  // the general pipeline redoes this batch
+  const uint8_t* __restrict__ text = A.text;
+  uint32_t qh = 0, qt = 0;
+  bool exhausted = false;
+  int st = ST_IDLE;
+  uint32_t bi = 0, p = 0, kq = 0, e3 = 0;  // block index, lead byte of the current rune, runes to its right, end / 3
+  uint32_t L = 0, parent = 0, maxlen = 0;
+  uint32_t best_d = 0, last_d = 0;
+  double best_v = 0.0, last_v = 0.0, prev_v = 0.0;
+  uint32_t tw_lo = 0, tw_hi = 0;
+  uintptr_t ta = 1;  // address of the aligned 8-byte text window held in (tw_lo, tw_hi)
+  uint32_t hsw = 0, hst = 0xFFFFFFFFu;
+  uint32_t acc = 0, accw = 0xFFFFFFFFu;
+  for (;;) {
+    // ---- refill idle lanes from the warp's queue of block indexes ----
+    const uint32_t nm = __ballot_sync(FULL, st == ST_IDLE);
+    if (nm) {
+      if (qh == qt && !exhausted) {
+        uint32_t b0 = 0;
+        if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_FBLK], (uint32_t)kRtQueue);
+        b0 = __shfl_sync(FULL, b0, 0);
+        if (b0 >= nblocks) exhausted = true;
+        else {
+          qh = b0;
+          qt = min(b0 + (uint32_t)kRtQueue, nblocks);
+        }
+      }
+      if (st == ST_IDLE) {
+        const uint32_t mine = qh + __popc(nm & lt_mask);
+        if (mine < qt) {
+          bi = mine;
+          p = A.blocks[bi].x;
+          e3 = p / 3u;
+          kq = 0;
+          st = ST_POS;
+        }
+      }
+      qh = min(qt, qh + (uint32_t)__popc(nm));
+      if (exhausted && __all_sync(FULL, st == ST_IDLE)) break;
+    }
+    // ---- PROBE ----
+    if (st == ST_PROBE) {
+      const uint32_t nk = (kq - L) & M;  // ring cell of the rune right after the current prefix
+      const uint32_t rl = rr[nk][tid];
+      uint32_t slot = jb_hash_edge(parent, rl) & T.hash_mask;
+      uint4 e;
+      bool found;
+      for (;;) {
+        e = __ldg(reinterpret_cast<const uint4*>(T.entries + slot));
+        if (e.z == JB_PARENT_EMPTY) {
+          found = false;
+          break;
+        }
+        if (e.z == parent && JB_RB_RUNE(e.w) == rl) {
+          found = true;
+          break;
+        }
+        slot = (slot + 1) & T.hash_mask;
+      }
+      bool alive = false;
+      if (found) {  // !found -> break (T:476-478)
+        L++;
+        const double pw = __longlong_as_double(((long long)e.y << 32) | (long long)e.x);
+        if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481)
+          const double nxt = (L > kq) ? 0.0 : ring[(kq - L) & M][tid];  // {j, 0.0} at the end of the block (T:522)
+          const double v = pw + nxt;                                    // pieceFreq + nextBestPiece.proba (T:529)
+          if (v >= prev_v) {  // maxIndexProba compares with the PREVIOUS candidate (T:569)
+            best_d = L;
+            best_v = v;
+          }
+          prev_v = v;
+          last_d = L;
+          last_v = v;
+        }
+        if (L < maxlen) {
+          alive = ((e.w >> 21) >> jb_bloom11(rr[(kq - L) & M][tid])) & 1;
+          parent = slot;
+        }
+      }
+      if (!alive) st = ST_COMMIT;
+    }
+    // ---- COMMIT ----
+    if (st == ST_COMMIT) {
+      if (best_d == 0) {  // best.index == -1 -> return prev (T:574-576)
+        best_d = last_d;
+        best_v = last_v;
+      }
+      ring[kq & M][tid] = best_v;
+      const uint32_t idx = e3 - kq, pwd = idx / PPW;
+      if (pwd != accw) {
+        if (acc) atomicOr(&A.path[accw], acc);
+        acc = 0;
+        accw = pwd;
+      }
+      acc |= (best_d - 1u) << ((idx % PPW) * PB);
+      if ((p >> 5) != hst) {
+        hst = p >> 5;
+        hsw = __ldg(A.hs_bits + hst);
+      }
+      if ((hsw >> (p & 31)) & 1) {  // first rune of the block
+        if (acc) atomicOr(&A.path[accw], acc);
+        acc = 0;
+        accw = 0xFFFFFFFFu;
+        A.blocks[bi] = make_uint2(p, kq + 1u);
+        st = ST_IDLE;
+      } else {
+        p -= 3u;
+        kq++;
+        st = ST_POS;
+      }
+    }
+    // ---- POS ----
+    if (st == ST_POS) {
+      const uintptr_t ap = reinterpret_cast<uintptr_t>(text) + p, a = ap & ~(uintptr_t)3;
+      if (a != ta) {
+        if (a + 4 == ta) {
+          tw_hi = tw_lo;
+          tw_lo = __ldg(reinterpret_cast<const uint32_t*>(a));
+        } else {
+          tw_lo = __ldg(reinterpret_cast<const uint32_t*>(a));
+          tw_hi = __ldg(reinterpret_cast<const uint32_t*>(a + 4));
+        }
+        ta = a;
+      }
+      const uint32_t x = __funnelshift_r(tw_lo, tw_hi, (uint32_t)(ap & 3) * 8u);
+      const uint32_t r0 = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
+      rr[kq & M][tid] = r0;
+      const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));
+      const double w0 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
+      const double nxt = kq ? ring[(kq - 1u) & M][tid] : 0.0;
+      const double v = w0 + nxt;
+      last_d = 1;
+      last_v = v;
+      prev_v = v;
+      best_v = v;
+      best_d = (v >= JB_MINF) ? 1u : 0u;  // first comparison is against minFloat (T:566,569)
+      maxlen = min(min((f.z >> 8) & 0xFFu, 31u), kq + 1u);
+      bool alive = false;
+      if (!(f.z & JB_FIRST_GATE) && maxlen > 1) alive = (f.w >> jb_bloom_bit(rr[(kq - 1u) & M][tid])) & 1;
+      parent = JB_PARENT_FIRST(r0);
+      L = 1;
+      st = alive ? ST_PROBE : ST_COMMIT;
+    }
+  }
+}
+
+int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st) {
+  const bool r16 = T.max_delta <= 16;
+  const unsigned grid = (unsigned)num_sms * 8u;
+  if (r16) k_route<16, 4><<<grid, kRtThreads, 0, st>>>(T, A);
+  else k_route<32, 8><<<grid, kRtThreads, 0, st>>>(T, A);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ==========================================================================================
+// k_emit: findDagPath + cutZh/viterbi/cutHMM, one lane per Han block -> token start / end bits
+// ==========================================================================================
+constexpr int kEmThreads = 128;
+constexpr int kEmQueue = 32;
+
+struct BitAcc2 {  // token bits of one lane, flushed one 32-byte word at a time (positions only grow)
+  uint32_t* bits;
+  uint32_t w, m;
+  __device__ __forceinline__ void init(uint32_t* b) {
+    bits = b;
+    w = 0xFFFFFFFFu;
+    m = 0;
+  }
+  __device__ __forceinline__ void set(uint32_t p) {
+    const uint32_t pw = p >> 5;
+    if (pw != w) {
+      if (m) atomicOr(&bits[w], m);
+      w = pw;
+      m = 0;
+    }
+    m |= 1u << (p & 31);
+  }
+  __device__ __forceinline__ void flush() {
+    if (m) atomicOr(&bits[w], m);
+    m = 0;
+    w = 0xFFFFFFFFu;
+  }
+};
+
+template <bool HMM, int PB>
+__global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const EmitArgs A) {
+  constexpr uint32_t PPW = 32 / PB, PMASK = (1u << PB) - 1u;
+  const int lane = threadIdx.x & 31;
+  if (A.counters[C_FLAGS] & 1u) return;
+  const uint32_t nblocks = min(A.counters[C_N_FBLK], A.blocks_cap);
+  BitAcc2 sa, ea;
+  sa.init(A.s_bits);
+  ea.init(A.e_bits);
+  for (;;) {
+    uint32_t b0 = 0;
+    if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_EMIT], (uint32_t)kEmQueue);
+    b0 = __shfl_sync(FULL, b0, 0);
+    if (b0 >= nblocks) break;
+    const uint32_t idx = b0 + lane;
+    if (idx >= nblocks) continue;
+    const uint2 desc = A.blocks[idx];
+    const uint32_t P0 = desc.x, i0 = P0 / 3u;
+    const int npos = (int)desc.y;
+    uint32_t pw = 0, pt = 0xFFFFFFFFu;
+    int k = 0;
+    uint32_t run_n = 0;
+    int run_s = 0;
+    double V[4];
+    while (k < npos) {
+      const uint32_t pi = i0 + (uint32_t)k;
+      if (pi / PPW != pt) {
+        pt = pi / PPW;
+        pw = A.path[pt];
+      }
+      const uint32_t d = ((pw >> ((pi % PPW) * PB)) & PMASK) + 1u;
+      const bool single = HMM && d == 1;
+      if (single) {  // collect singletons (T:233-234): one Viterbi step per rune (T:688-719)
+        const uint8_t* tp = A.text + P0 + 3u * (uint32_t)k;
+        const uint32_t cp = ((tp[0] & 0xFu) << 12) | ((tp[1] & 0x3Fu) << 6) | (tp[2] & 0x3Fu);
+        const double2* ep = reinterpret_cast<const double2*>(T.emit + (size_t)cp * 4);
+        const double2 e0 = __ldg(ep), e1 = __ldg(ep + 1);
+        const double em[4] = {e0.x, e0.y, e1.x, e1.y};
+        if (run_n == 0) {
+          run_s = k;
+#pragma unroll
+          for (int s = 0; s < 4; s++) V[s] = T.start[s] + em[s];
+        } else {
+          double W[4];
+          uint32_t code = 0;
+#pragma unroll
+          for (int s = 0; s < 4; s++) {  // stateTransitionRoute (T:736-756): strict > from minFloat, list order
+            const int pa = (s == 0 || s == 3) ? 2 : 0, pb = (s == 0 || s == 3) ? 3 : 1;
+            const double r0 = V[pa] + T.trans[s][0], r1 = V[pb] + T.trans[s][1];
+            double best = JB_MINF;
+            uint32_t from = 0;
+            if (r0 > best) {
+              best = r0;
+              from = 1;
+            }
+            if (r1 > best) {
+              best = r1;
+              from = 2;
+            }
+            W[s] = best + em[s];
+            code |= from << (2 * s);
+          }
+#pragma unroll
+          for (int s = 0; s < 4; s++) V[s] = W[s];
+          A.bp[pi] = (uint8_t)code;
+        }
+        run_n++;
+      }
+      if (!single || k + 1 >= npos) {
+        if (HMM && run_n) {  // flush the run: viterbi's tail (T:723-729) + cutHMM (T:273-285)
+          if (run_n == 1) {
+            sa.set(P0 + 3u * run_s);
+            ea.set(P0 + 3u * run_s + 2);
+          } else {
+            int st2 = V[2] > V[3] ? 2 : 3;
+            int kb = run_s + (int)run_n - 1;
+            uint32_t plen = 0;
+            for (;;) {  // back-trace; stops early where route.from == "" (T:715-716)
+              const uint8_t code = A.bp[i0 + (uint32_t)kb];
+              A.bp[i0 + (uint32_t)kb] = (uint8_t)(st2 >= 2 ? 0x80 : 0);  // the state of this path entry is E or S
+              plen++;
+              if (kb == run_s) break;
+              const int c = (code >> (2 * st2)) & 3;
+              if (c == 0) break;
+              st2 = (st2 == 0 || st2 == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
+              kb--;
+            }
+            // path[j] applies to rune j (T:277-283): a short path drops the run's tail
+            const int shift = (int)(run_n - plen);
+            bool prev_es = true;
+            for (uint32_t j2 = 0; j2 < plen; j2++) {
+              const bool es = A.bp[i0 + (uint32_t)(run_s + shift + (int)j2)] & 0x80;
+              const uint32_t qq = P0 + 3u * (uint32_t)(run_s + (int)j2);
+              if (prev_es) sa.set(qq);
+              if (es) ea.set(qq + 2);
+              prev_es = es;
+            }
+          }
+          run_n = 0;
+        }
+        if (!single) {
+          sa.set(P0 + 3u * (uint32_t)k);
+          ea.set(P0 + 3u * (uint32_t)(k + (int)d) - 1);
+        }
+      }
+      k += (int)d;
+    }
+    sa.flush();
+    ea.flush();
+  }
+}
+
+int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st) {
+  const bool r16 = T.max_delta <= 16;
+  const unsigned grid = (unsigned)num_sms * 8u;
+  if (r16) {
+    if (hmm) k_emit<true, 4><<<grid, kEmThreads, 0, st>>>(T, A);
+    else k_emit<false, 4><<<grid, kEmThreads, 0, st>>>(T, A);
+  } else {
+    if (hmm) k_emit<true, 8><<<grid, kEmThreads, 0, st>>>(T, A);
+    else k_emit<false, 8><<<grid, kEmThreads, 0, st>>>(T, A);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace jb

@@ -1,0 +1,65 @@
+// Streaming fast path of the Cut pipeline: three kernels, no per-position state in HBM.
+//
+//   k_scan   (S, N)        one lane per 32-byte word of text: UTF-8 / \p{Han} classification as BITMASKS
+//                          (SWAR byte predicates -> one bit per byte), block boundaries, cutNonZh tokens,
+//                          the Han-block start bitmap and the list of Han-block ends.
+//   k_route  (D, G, P, X)  one lane per Han block, lanes refilled as they finish: walks the block right to
+//                          left and, per rune, does buildDag's prefix probes and calcDagProba's selector
+//                          update in one state machine -- candidates never leave registers; only the
+//                          chosen word length per rune (4 bits) goes to HBM.
+//   k_emit   (W, H, V, O)  one lane per Han block: findDagPath walk, Viterbi over single-rune runs, token bits.
+//
+// Handed to the general kernels (jb_kernels.cu): a batch that contains a well-formed 4-byte Han rune or
+// overflows a list (C_FLAGS bit0).  Blocks of any length stay on this path.
+#pragma once
+#include "jb_kernels.cuh"
+
+namespace jb {
+
+constexpr int kScThreads = 256;               // lane 0 / 255 classify one halo word on either side
+constexpr int kScOwnWords = kScThreads - 2;   // 254 words = 8128 bytes per tile
+constexpr int kScTileBytes = kScOwnWords * 32;
+constexpr int kScLeft = 48;                   // staged bytes before the tile: 16 pad + the 32-byte halo word
+constexpr int kScRegion = kScLeft + kScTileBytes + 48;
+
+struct ScanArgs {
+  const uint8_t* text;
+  uint32_t n;
+  const uint32_t* ds_bits;
+  uint32_t* s_bits;
+  uint32_t* e_bits;
+  uint32_t* hs_bits;      // bit at the lead byte of the first rune of every Han block (plain stores, every word)
+  uint8_t* tile_sum;
+  uint32_t* counters;
+  uint4* deferred;        // (byte pos, len, flags: 1 need fwd 2 need bwd, tile)
+  uint32_t deferred_cap;
+  uint2* blocks;          // .x = lead byte of the LAST rune of a Han block (k_route rewrites the entry)
+  uint32_t blocks_cap;
+};
+
+struct RouteArgs {
+  const uint8_t* text;
+  const uint32_t* hs_bits;
+  uint2* blocks;          // in: .x = last rune; out: (lead byte of the first rune, runes)
+  uint32_t blocks_cap;
+  uint32_t* counters;
+  uint32_t* path;         // chosen word length - 1 per rune, index = lead byte / 3
+};
+
+struct EmitArgs {
+  const uint8_t* text;
+  const uint2* blocks;
+  uint32_t blocks_cap;
+  uint32_t* counters;
+  const uint32_t* path;
+  uint8_t* bp;            // Viterbi back-pointers / state flags per rune, index = lead byte / 3
+  uint32_t* s_bits;
+  uint32_t* e_bits;
+};
+
+int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st);
+int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st);
+int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st);
+inline uint32_t scan_tiles(uint32_t n) { return (n + kScTileBytes - 1) / kScTileBytes; }
+
+}  // namespace jb

@@ -79,8 +79,8 @@ class Tokenizer:
         old, self._h = self._h, h
         if old:
             L.jb_tokenizer_destroy(old)
-        if getattr(self, "_general_only", False):
-            L.jb_set_general_only(self._h, 1)
+        if getattr(self, "_path_mode", 0):
+            L.jb_set_general_only(self._h, self._path_mode)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -96,10 +96,11 @@ class Tokenizer:
         except Exception:
             pass
 
-    def set_general_only(self, on: bool):
-        """Bypass the fused fast path (the general kernels then cut every block); for tests."""
-        self._general_only = bool(on)
-        check(self._L.jb_set_general_only(self._h, int(bool(on))), "jb_set_general_only")
+    def set_general_only(self, on):
+        """Device path selector, for tests: 0/False = streaming fast path (default), 1/True = the general
+        kernels cut every block, 2 = the older fused tile kernel."""
+        self._path_mode = int(on)
+        check(self._L.jb_set_general_only(self._h, self._path_mode), "jb_set_general_only")
 
     @property
     def handle(self):

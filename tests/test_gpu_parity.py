@@ -12,18 +12,18 @@ from helpers import c_oracle_tokenizer, emit_arrays, fuzz_docs, pack_docs
 pytestmark = pytest.mark.gpu
 
 
-PATHS = ["fused", "general"]  # default fast path (fused tile kernel + leftovers) / general kernels only
+PATHS = ["stream", "fused", "general"]  # default streaming fast path / older fused tile kernel / general kernels only
 
 
-def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="fused", **kw):
+def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="stream", **kw):
     from jieba_go_b200.tokenizer import Tokenizer
     if isinstance(sd_or_lines, (list, tuple)):
         data = "\n".join(sd_or_lines).encode() + b"\n"
     else:
         data = sd_or_lines.dict_txt()
     tk = Tokenizer.from_dict_text(data, mode, emit, **kw)
-    if path == "general":
-        tk.set_general_only(True)
+    if path != "stream":
+        tk.set_general_only({"general": 1, "fused": 2}[path])
     return tk
 
 
