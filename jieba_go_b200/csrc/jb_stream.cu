@@ -478,46 +478,51 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
       if (exhausted && __all_sync(FULL, st == ST_IDLE)) break;
     }
     // ---- PROBE ----
-    if (st == ST_PROBE) {
-      const uint32_t nk = (kq - L) & M;  // ring cell of the rune right after the current prefix
-      const uint32_t rl = rr[nk][tid];
-      uint32_t slot = jb_hash_edge(parent, rl) & T.hash_mask;
-      uint4 e;
-      bool found;
-      for (;;) {
+    // (the three sections are separated by __syncwarp(): without it the compiler threads the exits of this
+    // section straight into the next ones and the lanes run them a few at a time)
+    {
+      const bool probing = st == ST_PROBE;
+      uint32_t rl = 0, slot = 0;
+      uint4 e = make_uint4(0, 0, JB_PARENT_EMPTY, 0);
+      if (probing) {
+        rl = rr[(kq - L) & M][tid];  // the rune right after the current prefix
+        slot = jb_hash_edge(parent, rl) & T.hash_mask;
         e = __ldg(reinterpret_cast<const uint4*>(T.entries + slot));
-        if (e.z == JB_PARENT_EMPTY) {
-          found = false;
-          break;
-        }
-        if (e.z == parent && JB_RB_RUNE(e.w) == rl) {
-          found = true;
-          break;
-        }
-        slot = (slot + 1) & T.hash_mask;
       }
-      bool alive = false;
-      if (found) {  // !found -> break (T:476-478)
-        L++;
-        const double pw = __longlong_as_double(((long long)e.y << 32) | (long long)e.x);
-        if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481)
-          const double nxt = (L > kq) ? 0.0 : ring[(kq - L) & M][tid];  // {j, 0.0} at the end of the block (T:522)
-          const double v = pw + nxt;                                    // pieceFreq + nextBestPiece.proba (T:529)
-          if (v >= prev_v) {  // maxIndexProba compares with the PREVIOUS candidate (T:569)
-            best_d = L;
-            best_v = v;
+      // linear probing: the whole warp takes another turn while any lane sits on a foreign entry
+      for (;;) {
+        const bool miss = probing && e.z != JB_PARENT_EMPTY && !(e.z == parent && JB_RB_RUNE(e.w) == rl);
+        if (!__any_sync(FULL, miss)) break;
+        if (miss) {
+          slot = (slot + 1) & T.hash_mask;
+          e = __ldg(reinterpret_cast<const uint4*>(T.entries + slot));
+        }
+      }
+      if (probing) {
+        bool alive = false;
+        if (e.z != JB_PARENT_EMPTY) {  // !found -> break (T:476-478)
+          L++;
+          const double pw = __longlong_as_double(((long long)e.y << 32) | (long long)e.x);
+          if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481)
+            const double nxt = (L > kq) ? 0.0 : ring[(kq - L) & M][tid];  // {j, 0.0} at the end of the block (T:522)
+            const double v = pw + nxt;                                    // pieceFreq + nextBestPiece.proba (T:529)
+            if (v >= prev_v) {  // maxIndexProba compares with the PREVIOUS candidate (T:569)
+              best_d = L;
+              best_v = v;
+            }
+            prev_v = v;
+            last_d = L;
+            last_v = v;
           }
-          prev_v = v;
-          last_d = L;
-          last_v = v;
+          if (L < maxlen) {
+            alive = ((e.w >> 21) >> jb_bloom11(rr[(kq - L) & M][tid])) & 1;
+            parent = slot;
+          }
         }
-        if (L < maxlen) {
-          alive = ((e.w >> 21) >> jb_bloom11(rr[(kq - L) & M][tid])) & 1;
-          parent = slot;
-        }
+        if (!alive) st = ST_COMMIT;
       }
-      if (!alive) st = ST_COMMIT;
     }
+    __syncwarp();
     // ---- COMMIT ----
     if (st == ST_COMMIT) {
       if (best_d == 0) {  // best.index == -1 -> return prev (T:574-576)
@@ -548,6 +553,7 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
         st = ST_POS;
       }
     }
+    __syncwarp();
     // ---- POS ----
     if (st == ST_POS) {
       const uintptr_t ap = reinterpret_cast<uintptr_t>(text) + p, a = ap & ~(uintptr_t)3;
