@@ -415,18 +415,25 @@ int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st) {
 // ==========================================================================================
 // k_route: buildDag + calcDagProba + maxIndexProba, one lane per Han block, right to left.
 //
-// Lane state machine, one step per loop iteration:
-//   POS     decode the rune, first-rune table -> candidate (i,i+1) (T:468-472), selector init
-//   PROBE   one trie-edge probe of the rune-prefix hash = one turn of `for j := range textRunes[i:]`
-//           (T:473-482); a hit with freq > 0 is the next candidate: pieceFreq + next.proba (T:519-529)
-//           folded straight into maxIndexProba's running (prev, best) pair (T:565-578)
-//   COMMIT  the position's selected (length, value); block start reached -> hand the block to k_emit
-// A lane that finishes its block takes the next one from the warp's queue, so all 32 lanes stay busy
-// whatever the block lengths.  Per-lane shared memory: the last RING route values and runes.
+// Lane state machine, one step per loop iteration (sections separated by __syncwarp(), otherwise the
+// compiler threads the exits of one section into the next and the lanes run them a few at a time):
+//   POS     consumes the two loads that were issued when the lane ADVANCED to this rune -- the first-rune
+//           table entry (T:468-472) and the hash entry of the 2-rune prefix (its address needs only the two
+//           runes, so it is fetched speculatively, before the gate / Bloom test says whether buildDag
+//           would look at it) -- and turns them into the first candidates of maxIndexProba's running
+//           (prev, best) pair: pieceFreq + next.proba (T:519-529), compared with the previous one (T:569).
+//   PROBE   one more trie-edge probe = one turn of `for j := range textRunes[i:]` (T:473-482), or one
+//           more step of linear probing when the slot held a foreign entry.
+//   COMMIT  the position's selected (length, value) -> route ring + 4-bit path entry; first rune of the
+//           block reached (start bitmap) -> hand the block to k_emit; else advance: decode the next rune
+//           from the register window, issue its two table loads and the next text word.
+// No load is consumed in the iteration that issues it, and a lane that finishes its block takes the next
+// one from the warp's queue, so all 32 lanes stay busy whatever the block lengths.
+// Per-lane shared memory: the last RING route values and runes.
 // ==========================================================================================
 constexpr int kRtThreads = 128;
-constexpr int kRtQueue = 64;
-enum : int { ST_IDLE = 0, ST_POS = 1, ST_PROBE = 2, ST_COMMIT = 3 };
+constexpr int kRtQueue = 32;
+enum : int { ST_IDLE = 0, ST_POS = 1, ST_PROBE = 2 };
 
 template <int RING, int PB>
 __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const RouteArgs A) {
@@ -438,18 +445,44 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t nblocks = min(A.counters[C_N_FBLK], A.blocks_cap);
   if (A.counters[C_FLAGS] & 1u) return;  // the general pipeline redoes this batch
-  const uint8_t* __restrict__ text = A.text;
+  const uintptr_t tbase = reinterpret_cast<uintptr_t>(A.text);
+  const uint4* __restrict__ first = reinterpret_cast<const uint4*>(T.first);
+  const uint4* __restrict__ entries = reinterpret_cast<const uint4*>(T.entries);
+  const uint32_t hmask = T.hash_mask;
   uint32_t qh = 0, qt = 0;
   bool exhausted = false;
   int st = ST_IDLE;
   uint32_t bi = 0, p = 0, kq = 0, e3 = 0;  // block index, lead byte of the current rune, runes to its right, end / 3
-  uint32_t L = 0, parent = 0, maxlen = 0;
+  uint32_t r0 = 0;                         // the current rune
+  uint4 f = make_uint4(0, 0, 0, 0);        // its first-rune table entry (in flight until POS)
+  uint4 e = make_uint4(0, 0, 0, 0);        // the hash entry in flight: 2-rune prefix (POS) or the chain's next probe (PROBE)
+  uint32_t slot = 0;                       // where e was loaded from
+  uint32_t L = 0, parent = 0, rl = 0, maxlen = 0;
   uint32_t best_d = 0, last_d = 0;
   double best_v = 0.0, last_v = 0.0, prev_v = 0.0;
   uint32_t tw_lo = 0, tw_hi = 0;
   uintptr_t ta = 1;  // address of the aligned 8-byte text window held in (tw_lo, tw_hi)
   uint32_t hsw = 0, hst = 0xFFFFFFFFu;
   uint32_t acc = 0, accw = 0xFFFFFFFFu;
+
+  // the lane now stands on the rune at p (inside the text window): decode it, issue its table loads and the
+  // text word the next rune to the left needs
+  auto setup_pos = [&]() {
+    const uintptr_t ap = tbase + p;
+    const uint32_t x = __funnelshift_r(tw_lo, tw_hi, (uint32_t)(ap & 3) * 8u);
+    r0 = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
+    rr[kq & M][tid] = r0;
+    f = __ldg(first + r0);
+    if (p >= 3u) {
+      const uintptr_t a = (ap - 3) & ~(uintptr_t)3;
+      if (a != ta) {
+        tw_hi = tw_lo;
+        tw_lo = __ldg(reinterpret_cast<const uint32_t*>(a));
+        ta = a;
+      }
+    }
+  };
+
   for (;;) {
     // ---- refill idle lanes from the warp's queue of block indexes ----
     const uint32_t nm = __ballot_sync(FULL, st == ST_IDLE);
@@ -471,60 +504,73 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
           p = A.blocks[bi].x;
           e3 = p / 3u;
           kq = 0;
+          const uintptr_t a = (tbase + p) & ~(uintptr_t)3;
+          tw_lo = __ldg(reinterpret_cast<const uint32_t*>(a));
+          tw_hi = __ldg(reinterpret_cast<const uint32_t*>(a + 4));
+          ta = a;
+          setup_pos();
           st = ST_POS;
         }
       }
       qh = min(qt, qh + (uint32_t)__popc(nm));
       if (exhausted && __all_sync(FULL, st == ST_IDLE)) break;
     }
-    // ---- PROBE ----
-    // (the three sections are separated by __syncwarp(): without it the compiler threads the exits of this
-    // section straight into the next ones and the lanes run them a few at a time)
-    {
-      const bool probing = st == ST_PROBE;
-      uint32_t rl = 0, slot = 0;
-      uint4 e = make_uint4(0, 0, JB_PARENT_EMPTY, 0);
-      if (probing) {
-        rl = rr[(kq - L) & M][tid];  // the rune right after the current prefix
-        slot = jb_hash_edge(parent, rl) & T.hash_mask;
-        e = __ldg(reinterpret_cast<const uint4*>(T.entries + slot));
-      }
-      // linear probing: the whole warp takes another turn while any lane sits on a foreign entry
-      for (;;) {
-        const bool miss = probing && e.z != JB_PARENT_EMPTY && !(e.z == parent && JB_RB_RUNE(e.w) == rl);
-        if (!__any_sync(FULL, miss)) break;
-        if (miss) {
-          slot = (slot + 1) & T.hash_mask;
-          e = __ldg(reinterpret_cast<const uint4*>(T.entries + slot));
-        }
-      }
-      if (probing) {
-        bool alive = false;
-        if (e.z != JB_PARENT_EMPTY) {  // !found -> break (T:476-478)
-          L++;
-          const double pw = __longlong_as_double(((long long)e.y << 32) | (long long)e.x);
-          if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481)
-            const double nxt = (L > kq) ? 0.0 : ring[(kq - L) & M][tid];  // {j, 0.0} at the end of the block (T:522)
-            const double v = pw + nxt;                                    // pieceFreq + nextBestPiece.proba (T:529)
-            if (v >= prev_v) {  // maxIndexProba compares with the PREVIOUS candidate (T:569)
-              best_d = L;
-              best_v = v;
-            }
-            prev_v = v;
-            last_d = L;
-            last_v = v;
+    // ---- 1. a lane that advanced: its first-rune entry has arrived -> candidate (i,i+1), gate (T:468-472) ----
+    bool probing = st == ST_PROBE, done = false;
+    if (st == ST_POS) {
+      const double w0 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
+      const double nxt = kq ? ring[(kq - 1u) & M][tid] : 0.0;
+      const double v = w0 + nxt;
+      last_d = 1;
+      last_v = v;
+      prev_v = v;
+      best_v = v;
+      best_d = (v >= JB_MINF) ? 1u : 0u;  // first comparison is against minFloat (T:566,569)
+      maxlen = min(min((f.z >> 8) & 0xFFu, 31u), kq + 1u);
+      // the 2-rune prefix's entry was fetched speculatively; buildDag looks at it only past the gate (the
+      // Bloom filter of second runes only spares work: a miss means the entry cannot match)
+      probing = !(f.z & JB_FIRST_GATE) && maxlen > 1 && ((f.w >> jb_bloom_bit(rl)) & 1);
+      done = !probing;
+      st = ST_PROBE;
+    }
+    __syncwarp();
+    // ---- 2. one turn of `for j := range textRunes[i:]` (T:473-482) on the hash entry that has arrived ----
+    bool issue = false, foreign = false;
+    if (probing) {
+      if (e.z == JB_PARENT_EMPTY) {  // !found -> break (T:476-478)
+        done = true;
+      } else if (e.z == parent && JB_RB_RUNE(e.w) == rl) {
+        L++;
+        const double pw = __longlong_as_double(((long long)e.y << 32) | (long long)e.x);
+        if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481); maxIndexProba's loop body (T:568-572)
+          const double nxt = (L > kq) ? 0.0 : ring[(kq - L) & M][tid];  // {j, 0.0} at the end of the block (T:522)
+          const double v = pw + nxt;                                    // pieceFreq + nextBestPiece.proba (T:529)
+          if (v >= prev_v) {
+            best_d = L;
+            best_v = v;
           }
-          if (L < maxlen) {
-            alive = ((e.w >> 21) >> jb_bloom11(rr[(kq - L) & M][tid])) & 1;
+          prev_v = v;
+          last_d = L;
+          last_v = v;
+        }
+        done = true;
+        if (L < maxlen) {
+          const uint32_t rn = rr[(kq - L) & M][tid];
+          if (((e.w >> 21) >> jb_bloom11(rn)) & 1) {  // some key extends this prefix by rn
             parent = slot;
+            rl = rn;
+            issue = true;
+            done = false;
           }
         }
-        if (!alive) st = ST_COMMIT;
+      } else {  // foreign entry: linear probing
+        foreign = true;
+        issue = true;
       }
     }
     __syncwarp();
-    // ---- COMMIT ----
-    if (st == ST_COMMIT) {
+    // ---- 3. commit the position; advance to the rune on the left ----
+    if (done) {
       if (best_d == 0) {  // best.index == -1 -> return prev (T:574-576)
         best_d = last_d;
         best_v = last_v;
@@ -550,41 +596,19 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
       } else {
         p -= 3u;
         kq++;
+        rl = r0;  // the rune right of the new position: second rune of its 2-rune prefix
+        setup_pos();
+        parent = JB_PARENT_FIRST(r0);
+        L = 1;
+        issue = true;
         st = ST_POS;
       }
     }
     __syncwarp();
-    // ---- POS ----
-    if (st == ST_POS) {
-      const uintptr_t ap = reinterpret_cast<uintptr_t>(text) + p, a = ap & ~(uintptr_t)3;
-      if (a != ta) {
-        if (a + 4 == ta) {
-          tw_hi = tw_lo;
-          tw_lo = __ldg(reinterpret_cast<const uint32_t*>(a));
-        } else {
-          tw_lo = __ldg(reinterpret_cast<const uint32_t*>(a));
-          tw_hi = __ldg(reinterpret_cast<const uint32_t*>(a + 4));
-        }
-        ta = a;
-      }
-      const uint32_t x = __funnelshift_r(tw_lo, tw_hi, (uint32_t)(ap & 3) * 8u);
-      const uint32_t r0 = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
-      rr[kq & M][tid] = r0;
-      const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));
-      const double w0 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
-      const double nxt = kq ? ring[(kq - 1u) & M][tid] : 0.0;
-      const double v = w0 + nxt;
-      last_d = 1;
-      last_v = v;
-      prev_v = v;
-      best_v = v;
-      best_d = (v >= JB_MINF) ? 1u : 0u;  // first comparison is against minFloat (T:566,569)
-      maxlen = min(min((f.z >> 8) & 0xFFu, 31u), kq + 1u);
-      bool alive = false;
-      if (!(f.z & JB_FIRST_GATE) && maxlen > 1) alive = (f.w >> jb_bloom_bit(rr[(kq - 1u) & M][tid])) & 1;
-      parent = JB_PARENT_FIRST(r0);
-      L = 1;
-      st = alive ? ST_PROBE : ST_COMMIT;
+    // ---- 4. issue the next hash probe (consumed in a later iteration) ----
+    if (issue) {
+      slot = foreign ? ((slot + 1) & hmask) : (jb_hash_edge(parent, rl) & hmask);
+      e = __ldg(entries + slot);
     }
   }
 }
