@@ -445,6 +445,9 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t nblocks = min(A.counters[C_N_FBLK], A.blocks_cap);
   if (A.counters[C_FLAGS] & 1u) return;  // the general pipeline redoes this batch
+  // few blocks (long ones): spread them over all warps instead of filling a few warps
+  const uint32_t nwarps = gridDim.x * (kRtThreads / 32);
+  const uint32_t chunk = min((uint32_t)kRtQueue, max(1u, (nblocks + nwarps - 1) / nwarps));
   const uintptr_t tbase = reinterpret_cast<uintptr_t>(A.text);
   const uint4* __restrict__ first = reinterpret_cast<const uint4*>(T.first);
   const uint4* __restrict__ entries = reinterpret_cast<const uint4*>(T.entries);
@@ -489,12 +492,12 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
     if (nm) {
       if (qh == qt && !exhausted) {
         uint32_t b0 = 0;
-        if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_FBLK], (uint32_t)kRtQueue);
+        if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_FBLK], chunk);
         b0 = __shfl_sync(FULL, b0, 0);
         if (b0 >= nblocks) exhausted = true;
         else {
           qh = b0;
-          qt = min(b0 + (uint32_t)kRtQueue, nblocks);
+          qt = min(b0 + chunk, nblocks);
         }
       }
       if (st == ST_IDLE) {
@@ -625,7 +628,6 @@ int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_
 // k_emit: findDagPath + cutZh/viterbi/cutHMM, one lane per Han block -> token start / end bits
 // ==========================================================================================
 constexpr int kEmThreads = 128;
-constexpr int kEmQueue = 32;
 
 struct BitAcc2 {  // token bits of one lane, flushed one 32-byte word at a time (positions only grow)
   uint32_t* bits;
@@ -654,29 +656,58 @@ struct BitAcc2 {  // token bits of one lane, flushed one 32-byte word at a time 
 template <bool HMM, int PB>
 __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const EmitArgs A) {
   constexpr uint32_t PPW = 32 / PB, PMASK = (1u << PB) - 1u;
+  constexpr uint32_t kRegRun = 16;  // back-pointers of runs up to this length stay in registers
   const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   if (A.counters[C_FLAGS] & 1u) return;
   const uint32_t nblocks = min(A.counters[C_N_FBLK], A.blocks_cap);
+  // few blocks (long ones): spread them over all warps instead of filling a few warps
+  const uint32_t nwarps = gridDim.x * (kEmThreads / 32);
+  const uint32_t chunk = min(32u, max(1u, (nblocks + nwarps - 1) / nwarps));
+  const uintptr_t tbase = reinterpret_cast<uintptr_t>(A.text);
   BitAcc2 sa, ea;
   sa.init(A.s_bits);
   ea.init(A.e_bits);
+  uint32_t qh = 0, qt = 0;
+  bool exhausted = false, active = false;
+  uint32_t P0 = 0, i0 = 0, npos = 0, k = 0;
+  uint32_t pw = 0, pt = 0xFFFFFFFFu;
+  uint32_t run_n = 0, run_s = 0;
+  double V[4] = {0.0, 0.0, 0.0, 0.0};
+  unsigned long long bplo = 0, bphi = 0;  // the last 16 back-pointer codes, newest in the low byte of bplo
   for (;;) {
-    uint32_t b0 = 0;
-    if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_EMIT], (uint32_t)kEmQueue);
-    b0 = __shfl_sync(FULL, b0, 0);
-    if (b0 >= nblocks) break;
-    const uint32_t idx = b0 + lane;
-    if (idx >= nblocks) continue;
-    const uint2 desc = A.blocks[idx];
-    const uint32_t P0 = desc.x, i0 = P0 / 3u;
-    const int npos = (int)desc.y;
-    uint32_t pw = 0, pt = 0xFFFFFFFFu;
-    int k = 0;
-    uint32_t run_n = 0;
-    int run_s = 0;
-    double V[4];
-    while (k < npos) {
-      const uint32_t pi = i0 + (uint32_t)k;
+    // ---- refill idle lanes from the warp's queue of block indexes ----
+    const uint32_t nm = __ballot_sync(FULL, !active);
+    if (nm) {
+      if (qh == qt && !exhausted) {
+        uint32_t b0 = 0;
+        if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_EMIT], chunk);
+        b0 = __shfl_sync(FULL, b0, 0);
+        if (b0 >= nblocks) exhausted = true;
+        else {
+          qh = b0;
+          qt = min(b0 + chunk, nblocks);
+        }
+      }
+      if (!active) {
+        const uint32_t mine = qh + __popc(nm & lt_mask);
+        if (mine < qt) {
+          const uint2 desc = A.blocks[mine];
+          P0 = desc.x;
+          npos = desc.y;
+          i0 = P0 / 3u;
+          k = 0;
+          run_n = 0;
+          pt = 0xFFFFFFFFu;
+          active = true;
+        }
+      }
+      qh = min(qt, qh + (uint32_t)__popc(nm));
+      if (exhausted && __all_sync(FULL, !active)) break;
+    }
+    // ---- one piece of findDagPath's walk (T:552-562) per iteration ----
+    if (active) {
+      const uint32_t pi = i0 + k;
       if (pi / PPW != pt) {
         pt = pi / PPW;
         pw = A.path[pt];
@@ -684,8 +715,10 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
       const uint32_t d = ((pw >> ((pi % PPW) * PB)) & PMASK) + 1u;
       const bool single = HMM && d == 1;
       if (single) {  // collect singletons (T:233-234): one Viterbi step per rune (T:688-719)
-        const uint8_t* tp = A.text + P0 + 3u * (uint32_t)k;
-        const uint32_t cp = ((tp[0] & 0xFu) << 12) | ((tp[1] & 0x3Fu) << 6) | (tp[2] & 0x3Fu);
+        const uintptr_t ap = tbase + P0 + 3u * k, a4 = ap & ~(uintptr_t)3;
+        const uint32_t x = __funnelshift_r(__ldg(reinterpret_cast<const uint32_t*>(a4)), __ldg(reinterpret_cast<const uint32_t*>(a4 + 4)),
+                                           (uint32_t)(ap & 3) * 8u);
+        const uint32_t cp = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
         const double2* ep = reinterpret_cast<const double2*>(T.emit + (size_t)cp * 4);
         const double2 e0 = __ldg(ep), e1 = __ldg(ep + 1);
         const double em[4] = {e0.x, e0.y, e1.x, e1.y};
@@ -715,51 +748,84 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           }
 #pragma unroll
           for (int s = 0; s < 4; s++) V[s] = W[s];
-          A.bp[pi] = (uint8_t)code;
+          bphi = (bphi << 8) | (bplo >> 56);
+          bplo = (bplo << 8) | code;
+          if (run_n >= kRegRun - 1) {  // long run: the codes also go to HBM
+            if (run_n == kRegRun - 1)
+              for (uint32_t t = 1; t < kRegRun - 1; t++) {  // codes of steps 1..14 so far (step t sits kRegRun-1-t bytes back)
+                const uint32_t back = kRegRun - 1 - t;
+                A.bp[i0 + run_s + t] = (uint8_t)(back < 8 ? (bplo >> (8 * back)) : (bphi >> (8 * (back - 8))));
+              }
+            A.bp[pi] = (uint8_t)code;
+          }
         }
         run_n++;
       }
-      if (!single || k + 1 >= npos) {
-        if (HMM && run_n) {  // flush the run: viterbi's tail (T:723-729) + cutHMM (T:273-285)
-          if (run_n == 1) {
-            sa.set(P0 + 3u * run_s);
-            ea.set(P0 + 3u * run_s + 2);
-          } else {
-            int st2 = V[2] > V[3] ? 2 : 3;
-            int kb = run_s + (int)run_n - 1;
-            uint32_t plen = 0;
-            for (;;) {  // back-trace; stops early where route.from == "" (T:715-716)
-              const uint8_t code = A.bp[i0 + (uint32_t)kb];
-              A.bp[i0 + (uint32_t)kb] = (uint8_t)(st2 >= 2 ? 0x80 : 0);  // the state of this path entry is E or S
-              plen++;
-              if (kb == run_s) break;
-              const int c = (code >> (2 * st2)) & 3;
-              if (c == 0) break;
-              st2 = (st2 == 0 || st2 == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
-              kb--;
-            }
-            // path[j] applies to rune j (T:277-283): a short path drops the run's tail
-            const int shift = (int)(run_n - plen);
-            bool prev_es = true;
-            for (uint32_t j2 = 0; j2 < plen; j2++) {
-              const bool es = A.bp[i0 + (uint32_t)(run_s + shift + (int)j2)] & 0x80;
-              const uint32_t qq = P0 + 3u * (uint32_t)(run_s + (int)j2);
-              if (prev_es) sa.set(qq);
-              if (es) ea.set(qq + 2);
-              prev_es = es;
-            }
+      if (HMM && run_n && (!single || k + 1 >= npos)) {  // flush the run: viterbi's tail (T:723-729) + cutHMM (T:273-285)
+        if (run_n == 1) {
+          sa.set(P0 + 3u * run_s);
+          ea.set(P0 + 3u * run_s + 2);
+        } else if (run_n <= kRegRun) {
+          int st2 = V[2] > V[3] ? 2 : 3;
+          uint32_t es = 0, plen = 0;
+          int j = (int)run_n - 1;
+          for (;;) {  // back-trace; stops early where route.from == "" (T:715-716)
+            es |= (st2 >= 2 ? 1u : 0u) << j;
+            plen++;
+            if (j == 0) break;
+            const uint32_t back = run_n - 1 - (uint32_t)j;
+            const uint32_t code = (uint32_t)(back < 8 ? (bplo >> (8 * back)) : (bphi >> (8 * (back - 8)))) & 0xFFu;
+            const int c = (code >> (2 * st2)) & 3;
+            if (c == 0) break;
+            st2 = (st2 == 0 || st2 == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
+            j--;
           }
-          run_n = 0;
+          // path[j] applies to rune j (T:277-283): a short path drops the run's tail
+          es >>= run_n - plen;
+          const uint32_t starts = (es << 1) | 1u;
+          for (uint32_t j2 = 0; j2 < plen; j2++) {
+            const uint32_t qq = P0 + 3u * (run_s + j2);
+            if ((starts >> j2) & 1) sa.set(qq);
+            if ((es >> j2) & 1) ea.set(qq + 2);
+          }
+        } else {
+          int st2 = V[2] > V[3] ? 2 : 3;
+          uint32_t kb = run_s + run_n - 1;
+          uint32_t plen = 0;
+          for (;;) {
+            const uint8_t code = A.bp[i0 + kb];
+            A.bp[i0 + kb] = (uint8_t)(st2 >= 2 ? 0x80 : 0);  // the state of this path entry is E or S
+            plen++;
+            if (kb == run_s) break;
+            const int c = (code >> (2 * st2)) & 3;
+            if (c == 0) break;
+            st2 = (st2 == 0 || st2 == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
+            kb--;
+          }
+          const uint32_t shift = run_n - plen;
+          bool prev_es = true;
+          for (uint32_t j2 = 0; j2 < plen; j2++) {
+            const bool es = A.bp[i0 + run_s + shift + j2] & 0x80;
+            const uint32_t qq = P0 + 3u * (run_s + j2);
+            if (prev_es) sa.set(qq);
+            if (es) ea.set(qq + 2);
+            prev_es = es;
+          }
         }
-        if (!single) {
-          sa.set(P0 + 3u * (uint32_t)k);
-          ea.set(P0 + 3u * (uint32_t)(k + (int)d) - 1);
-        }
+        run_n = 0;
       }
-      k += (int)d;
+      if (!single) {
+        sa.set(P0 + 3u * k);
+        ea.set(P0 + 3u * (k + d) - 1u);
+      }
+      k += d;
+      if (k >= npos) {
+        sa.flush();
+        ea.flush();
+        active = false;
+      }
     }
-    sa.flush();
-    ea.flush();
+    __syncwarp();
   }
 }
 
