@@ -50,7 +50,7 @@ struct jb_tokenizer {
   size_t table_bytes = 0;
   uint64_t max_batch = 256ull << 20;
   double w_per_slot = 3.0;
-  int force_general = 0;  // 1: skip the fused fast path (tests / debugging)
+  int force_general = 0;  // 1: skip the streaming fast path (tests / debugging)
   std::mutex mu;
   std::vector<WsSlot*> free_ws;
   WsSlot dev_ws;  // workspace of jb_cut_device (one caller at a time per tokenizer for the device API)
@@ -495,7 +495,7 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     if (c.nb) CUDA_TRY(cudaMemcpyAsync(ws.text, text + doc_off[c.d0], c.nb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, doc_off + c.d0, (c.d1 - c.d0 + 1) * 8, cudaMemcpyHostToDevice, st));
     r = run_pipeline(tk->T, ws, ws.text, (uint32_t)c.nb, ws.doc_off64, c.d1 - c.d0, use_hmm != 0, ws.out_start, ws.out_end, ws.out_cap,
-                     ws.out_doc_tok, 0, ws.out_ntok, st, tk->force_general == 1, tk->force_general == 2 ? 1 : 0);
+                     ws.out_doc_tok, 0, ws.out_ntok, st, tk->force_general != 0);
     if (r != JB_OK) return fail(r, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     CUDA_TRY(cudaMemcpyAsync(sl->h_cnt, ws.out_ntok, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(sl->ev, st));
@@ -597,14 +597,14 @@ int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, cons
   tk->dev_ws.ws.l2_base = tk->table_base;
   tk->dev_ws.ws.l2_bytes = tk->table_bytes;
   rc = run_pipeline(tk->T, tk->dev_ws.ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, d_start, d_end, cap_tokens,
-                    d_doc_tok_off, 0, d_n_tokens, (cudaStream_t)cuda_stream, tk->force_general == 1, tk->force_general == 2 ? 1 : 0);
+                    d_doc_tok_off, 0, d_n_tokens, (cudaStream_t)cuda_stream, tk->force_general != 0);
   if (rc != JB_OK) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   return JB_OK;
 }
 
 int jb_set_general_only(jb_tokenizer* tk, int on) {
   if (!tk) return JB_EINVAL;
-  tk->force_general = on;  // 0: streaming fast path, 1: general kernels only, 2: the older fused tile kernel
+  tk->force_general = on != 0;
   return JB_OK;
 }
 int jb_profile_enable(jb_tokenizer* tk, int on) {

@@ -12,7 +12,6 @@
 //                   viterbi, cutHMM) -> token start/end bits
 //   k_rank_*        bitmap rank + scatter: token offsets in document order (the appends of Cut)
 #include "jb_kernels.cuh"
-#include "jb_fused.cuh"
 #include "jb_stream.cuh"
 
 #include <stdio.h>
@@ -206,8 +205,8 @@ struct SplitArgs {
   uint32_t* counters;
   const uint8_t* tile_ctx;
   uint8_t* tile_sum;
-  const uint8_t* tile_dirty;
-  int mode;  // 0: whole general pipeline; 1: DAG records only, on tiles overlapped by a long block;
+  uint32_t ntiles;
+  int mode;  // 0: whole general pipeline;
              // 2: whole general pipeline, but only if the batch was flagged for it (C_FLAGS bit0)
 };
 
@@ -274,16 +273,10 @@ struct SplitSmem {
 };
 
 template <bool SUMMARY>
-__global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const SplitArgs A) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  SplitSmem& S = *reinterpret_cast<SplitSmem*>(smem_raw);
+__device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, const uint32_t tile) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = blockIdx.x;
   const uint32_t t0 = tile * (uint32_t)kTileBytes;
   const uint32_t n = A.n;
-  if (A.mode == 2 && !(A.counters[C_FLAGS] & 1u)) return;
-  if (A.mode == 1 && !A.tile_dirty[tile]) return;
-  const bool dag_only = A.mode == 1;
   classify_tile<kSplitThreads>(S.t, A.text, n, A.ds_bits, t0, T);
   TileCtx cx{&S.t, t0, n};
   const int NW = kTileBytes / 32;
@@ -365,7 +358,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
     return;
   }
   // ---- cutNonZh gating: other-rune tokens survive only if their block has an alnum ---------
-  const uint8_t ctx = dag_only ? 0 : A.tile_ctx[tile];
+  const uint8_t ctx = A.tile_ctx[tile];
   const bool fwd_in = ctx & 1, bwd_in = ctx & 2;
   for (int g = warp; g < NW; g += kSplitThreads / 32) {
     uint32_t so = S.NSO[g];
@@ -385,8 +378,8 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
   for (int j = tid; j < NW + 1; j += kSplitThreads) {
     uint32_t sbits = j < NW ? (S.NSA[j] | S.NSO[j]) : 0;
     uint32_t ebits = (j < NW ? S.NEA[j] : 0) | S.NEO[j];
-    if (sbits && !dag_only) atomicOr(&A.s_bits[w0 + j], sbits);
-    if (ebits && !dag_only) atomicOr(&A.e_bits[w0 + j], ebits);
+    if (sbits) atomicOr(&A.s_bits[w0 + j], sbits);
+    if (ebits) atomicOr(&A.e_bits[w0 + j], ebits);
   }
   // ---- Han slots: block start/end flags and the DAG probe (buildDag, tokenizer.go:462-497) ----
   const uint32_t slot0 = tile * (uint32_t)kTileSlots;
@@ -514,7 +507,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
         }
       }
       A.rec[k] = mask | (bstart ? JB_REC_START : 0u);
-      if (bend && !dag_only) {
+      if (bend) {
         uint32_t e = atomicAdd(&S.n_ends_local, 1u);
         uint32_t wend = min(excl + cnt, cap + 1024u);
         S.ends_local[e] = make_uint2(k, (uint32_t)(tile * (uint64_t)A.w_per_tile) + wend);
@@ -536,6 +529,19 @@ __global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const
   for (uint32_t j = tid; j < S.n_ends_local; j += kSplitThreads) A.ends[S.ends_base + j] = S.ends_local[j];
 }
 
+// Persistent over tiles: when the batch is not flagged for the general pipeline (mode 2) the launch costs
+// a few microseconds instead of one CTA per tile.
+template <bool SUMMARY>
+__global__ void __launch_bounds__(kSplitThreads) k_split(const JbTables T, const SplitArgs A) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SplitSmem& S = *reinterpret_cast<SplitSmem*>(smem_raw);
+  if (A.mode == 2 && !(A.counters[C_FLAGS] & 1u)) return;
+  for (uint32_t tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+    split_tile<SUMMARY>(T, A, S, tile);
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Segmented OR-scan over tile summaries.  Monoid element (has, pre, post):
 //   combine(a,b) = (a.has|b.has, a.has ? a.pre : a.pre|b.pre, b.has ? b.post : a.post|b.post)
@@ -549,7 +555,9 @@ __device__ __forceinline__ uint32_t seg_combine(uint32_t a, uint32_t b) {
   return has | pre | post;
 }
 // identity: has=0, pre=post=0 combined with x gives x when treated as "no alnum, no boundary"
-__global__ void __launch_bounds__(1024) k_tile_scan(const uint8_t* __restrict__ sum, uint8_t* __restrict__ ctx, uint32_t nt) {
+__global__ void __launch_bounds__(1024) k_tile_scan(const uint8_t* __restrict__ sum, uint8_t* __restrict__ ctx, uint32_t nt,
+                                                    const uint32_t* __restrict__ counters, int require_flag) {
+  if (require_flag && !(counters[C_FLAGS] & 1u)) return;
   __shared__ uint32_t part[1024];
   __shared__ uint32_t pfx[1024], sfx[1024];
   const int tid = threadIdx.x;
@@ -1102,59 +1110,6 @@ __global__ void k_resolve_deferred(const uint4* __restrict__ deferred, const uin
   }
 }
 
-// One warp per long block: walk forward over back-to-back 3-byte Han runes to find the block's last
-// rune, mark the split tiles it overlaps.  (A 4-byte Han rune flags the whole batch elsewhere.)
-__global__ void k_long_extent(const JbTables T, const uint8_t* __restrict__ text, uint32_t n, const uint32_t* __restrict__ ds_bits,
-                              const uint32_t* __restrict__ seeds, uint32_t cap, const uint32_t* __restrict__ counters,
-                              uint2* __restrict__ ends, uint8_t* __restrict__ dirty) {
-  const uint32_t nl = min(counters[C_N_LONG], cap);
-  const int lane = threadIdx.x & 31;
-  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t i = wid; i < nl; i += nw) {
-    const uint32_t P0 = seeds[i];
-    uint32_t cnt = 0;  // runes in the block
-    for (uint32_t it = 0;; it++) {
-      uint32_t P = P0 + 3u * (32u * it + lane);
-      bool ok = P + 2 < n;
-      if (ok) {
-        uint32_t L = text[P], c1 = text[P + 1], c2 = text[P + 2];
-        ok = (L & 0xF0) == 0xE0 && (c1 & 0xC0) == 0x80 && (c2 & 0xC0) == 0x80 && !(L == 0xE0 && c1 < 0xA0) && !(L == 0xED && c1 > 0x9F);
-        if (ok) {
-          uint32_t cp = ((L & 0xF) << 12) | ((c1 & 0x3F) << 6) | (c2 & 0x3F);
-          ok = (__ldg(T.han_bits + (cp >> 5)) >> (cp & 31)) & 1;
-        }
-        // a document boundary at or inside the rune ends the block (the block's own first byte may be one)
-        for (uint32_t j = (it == 0 && lane == 0) ? 1u : 0u; ok && j < 3; j++) {
-          uint32_t q = P + j;
-          if ((ds_bits[q >> 5] >> (q & 31)) & 1) ok = false;
-        }
-      }
-      uint32_t good = __ballot_sync(FULL, ok);
-      if (good != FULL) {
-        cnt = 32u * it + (uint32_t)(__ffs(~good) - 1);
-        break;
-      }
-    }
-    if (cnt == 0) cnt = 1;
-    const uint32_t Plast = P0 + 3u * (cnt - 1);
-    const uint32_t ks = d_slot(P0), ke = d_slot(Plast);
-    if (lane == 0) ends[i] = make_uint2(ke, 0u);
-    for (uint32_t t = ks / kTileSlots + lane; t <= ke / kTileSlots; t += 32) dirty[t] = 1;
-  }
-}
-
-// weight end offset of every long block's last rune (before the DP starts rewriting records)
-__global__ void k_long_wp(uint2* __restrict__ ends, const uint32_t* __restrict__ counters, uint32_t cap, const uint32_t* __restrict__ rec,
-                          const uint32_t* __restrict__ gend) {
-  const uint32_t nl = min(counters[C_N_LONG], cap);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += gridDim.x * blockDim.x) {
-    const uint32_t k = ends[i].x;
-    uint32_t wp = gend[k >> 5];
-    for (uint32_t j = k + 1; j <= (k | 31u); j++) wp -= __popc(rec[j] & JB_REC_MASK);
-    ends[i].y = wp;
-  }
-}
-
 // the batch was flagged for the general pipeline: forget what the fast path produced
 __global__ void k_fallback_reset(uint32_t* __restrict__ counters, uint32_t* __restrict__ s_bits, uint32_t* __restrict__ e_bits,
                                  uint32_t nwords) {
@@ -1230,7 +1185,7 @@ static bool dalloc(T*& p, uint64_t count) {
 
 void workspace_free(Workspace& ws) {
   void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.rec, ws.gend, ws.wbuf, ws.ends,
-                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.tile_dirty, ws.long_seeds, ws.deferred, ws.stream, ws.fblocks, ws.hs_bits, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
+                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.deferred, ws.hs_bits, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1252,13 +1207,9 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ok = ok && dalloc(ws.rec, ntiles * kTileSlots + 64) && dalloc(ws.gend, ntiles * (kTileSlots / 32) + 8);
     ok = ok && dalloc(ws.wbuf, ntiles * (uint64_t)wpt + 4096);
     ok = ok && dalloc(ws.ends, ntiles * kTileSlots + 8) && dalloc(ws.walks, ntiles * kTileSlots + 8);
-    ok = ok && dalloc(ws.tile_sum, ntiles + 8) && dalloc(ws.tile_ctx, ntiles + 8) && dalloc(ws.tile_dirty, ntiles + 8);
-    ws.long_cap = (uint32_t)(cap / 64 + 4096);
+    ok = ok && dalloc(ws.tile_sum, ntiles + 8) && dalloc(ws.tile_ctx, ntiles + 8);
     ws.deferred_cap = (uint32_t)(cap / 64 + 4096);
-    ok = ok && dalloc(ws.long_seeds, (uint64_t)ws.long_cap) && dalloc(ws.deferred, (uint64_t)ws.deferred_cap);
-    ws.stream_cap = (uint32_t)std::min<uint64_t>(cap + cap / 2 + 65536, 0xFFFF0000ull);  // 8-byte units: 12 B per input byte
-    ws.fblk_cap = (uint32_t)(cap / 4 + 4096);
-    ok = ok && dalloc(ws.stream, (uint64_t)ws.stream_cap + 64) && dalloc(ws.fblocks, (uint64_t)ws.fblk_cap);
+    ok = ok && dalloc(ws.deferred, (uint64_t)ws.deferred_cap);
     ok = ok && dalloc(ws.hs_bits, nwords) && dalloc(ws.path, cap / 12 + 64) && dalloc(ws.bp, cap / 3 + 64);
     ws.blocks_cap = (uint32_t)std::min<uint64_t>(ntiles * kTileSlots + 8, 0xFFFFFFF0ull);
     ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8));
@@ -1315,7 +1266,7 @@ static bool g_attr_done = false;
 
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t n, const uint64_t* d_doc_off, uint64_t ndocs,
                  bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens, uint64_t* d_doc_tok_off, uint64_t tok_base,
-                 uint64_t* d_n_tokens, cudaStream_t st, bool force_general, int path_mode) {
+                 uint64_t* d_n_tokens, cudaStream_t st, bool force_general) {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1359,11 +1310,11 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
   cudaMemsetAsync(ws.ds_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.s_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.e_bits, 0, ((uint64_t)nwords + 4) * 4, st);
-  if (n > 0 && !force_general) cudaMemsetAsync(ws.tile_dirty, 0, (uint64_t)ntiles + 2, st);
   JB_LAUNCH(k_docstart, (unsigned)((ndocs + 1 + 255) / 256), 256, 0, st, d_doc_off, ndocs, n, ws.doc_off32, ws.ds_bits);
   PROF(1);
   if (n > 0) {
     const unsigned pgrid = (unsigned)g_num_sms * 8;
+    const unsigned sgrid = std::min<unsigned>(ntiles, (unsigned)g_num_sms * 8);
     SplitArgs sa;
     sa.text = d_text;
     sa.n = n;
@@ -1376,9 +1327,9 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
     sa.w_per_tile = ws.w_per_tile;
     sa.ends = ws.ends;
     sa.counters = ws.counters;
+    sa.ntiles = ntiles;
     sa.tile_ctx = ws.tile_ctx;
     sa.tile_sum = ws.tile_sum;
-    sa.tile_dirty = ws.tile_dirty;
     DpArgs da;
     da.text = d_text;
     da.rec = ws.rec;
@@ -1404,7 +1355,7 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       if (use_hmm) JB_LAUNCH(k_walk<true>, pgrid, kWalkThreads, 0, st, T, wa);
       else JB_LAUNCH(k_walk<false>, pgrid, kWalkThreads, 0, st, T, wa);
     };
-    if (!force_general && path_mode == 0) {
+    if (!force_general) {
       // ---- fast path: k_scan -> k_route -> k_emit (jb_stream.cu) ----------------------------------
       const uint32_t nt1 = scan_tiles(n);
       cudaMemsetAsync(ws.path, 0, ((uint64_t)n / 12 + 16) * 4, st);
@@ -1445,61 +1396,10 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       ea.e_bits = ws.e_bits;
       launch_emit(T, ea, use_hmm, g_num_sms, st);
       g_launches.fetch_add(1);
-      JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, nt1);
+      JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, nt1, ws.counters, 0);
       JB_LAUNCH(k_resolve_deferred, (unsigned)g_num_sms, 256, 0, st, ws.deferred, ws.counters, ws.deferred_cap, ws.tile_ctx, ws.s_bits,
                 ws.e_bits);
       PROF(4);
-      JB_LAUNCH(k_fallback_reset, (unsigned)g_num_sms * 4, 256, 0, st, ws.counters, ws.s_bits, ws.e_bits, nwords + 4);
-    } else if (!force_general) {
-      // ---- fast path: one fused kernel; leftovers (long blocks, deferred tokens) to small kernels ----
-      FusedArgs fa;
-      fa.text = d_text;
-      fa.n = n;
-      fa.ds_bits = ws.ds_bits;
-      fa.s_bits = ws.s_bits;
-      fa.e_bits = ws.e_bits;
-      fa.tile_sum = ws.tile_sum;
-      fa.counters = ws.counters;
-      fa.long_seeds = ws.long_seeds;
-      fa.long_cap = ws.long_cap;
-      fa.deferred = ws.deferred;
-      fa.deferred_cap = ws.deferred_cap;
-      fa.stream = ws.stream;
-      fa.stream_cap = ws.stream_cap;
-      fa.fblocks = ws.fblocks;
-      fa.fblk_cap = ws.fblk_cap;
-      launch_fused(T, fa, ntiles, use_hmm, st);
-      g_launches.fetch_add(1);
-      PROF(2);
-      BlockDpArgs ba;
-      ba.text = d_text;
-      ba.stream = ws.stream;
-      ba.fblocks = ws.fblocks;
-      ba.fblk_cap = ws.fblk_cap;
-      ba.counters = ws.counters;
-      ba.s_bits = ws.s_bits;
-      ba.e_bits = ws.e_bits;
-      launch_block_dp(T, ba, use_hmm, g_num_sms, st);
-      g_launches.fetch_add(1);
-      PROF(3);
-      JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles);
-      JB_LAUNCH(k_resolve_deferred, (unsigned)g_num_sms, 256, 0, st, ws.deferred, ws.counters, ws.deferred_cap, ws.tile_ctx, ws.s_bits,
-                ws.e_bits);
-      JB_LAUNCH(k_long_extent, (unsigned)g_num_sms * 4, 256, 0, st, T, d_text, n, ws.ds_bits, ws.long_seeds, ws.long_cap, ws.counters,
-                ws.ends, ws.tile_dirty);
-      sa.mode = 1;
-      JB_LAUNCH(k_split<false>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
-      JB_LAUNCH(k_long_wp, (unsigned)g_num_sms, 256, 0, st, ws.ends, ws.counters, ws.long_cap, ws.rec, ws.gend);
-      da.count_idx = C_N_LONG;
-      da.cursor_idx = C_CUR_LDP;
-      da.require_flag = 0;
-      launch_dp();
-      wa.count_idx = C_N_LONG;
-      wa.cursor_idx = C_CUR_LWALK;
-      wa.require_flag = 0;
-      launch_walk();
-      PROF(4);
-      // ---- batch flagged (4-byte Han rune, list overflow): the general pipeline redoes it -----------
       JB_LAUNCH(k_fallback_reset, (unsigned)g_num_sms * 4, 256, 0, st, ws.counters, ws.s_bits, ws.e_bits, nwords + 4);
     } else {
       PROF(2);
@@ -1513,9 +1413,9 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
     wa.count_idx = C_N_ENDS;
     wa.cursor_idx = C_CUR_WALK;
     wa.require_flag = force_general ? 0 : 1;
-    JB_LAUNCH(k_split<true>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
-    JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles);
-    JB_LAUNCH(k_split<false>, ntiles, kSplitThreads, sizeof(SplitSmem), st, T, sa);
+    JB_LAUNCH(k_split<true>, sgrid, kSplitThreads, sizeof(SplitSmem), st, T, sa);
+    JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles, ws.counters, force_general ? 0 : 1);
+    JB_LAUNCH(k_split<false>, sgrid, kSplitThreads, sizeof(SplitSmem), st, T, sa);
     launch_dp();
     launch_walk();
     PROF(5);

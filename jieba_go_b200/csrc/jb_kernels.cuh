@@ -25,15 +25,11 @@ enum Counter {
   C_STATUS = 3,    // bit0: candidate-weight buffer overflow
   C_N_TOKENS = 4,
   C_W_NEEDED = 5,  // max weights needed by any tile (to size a retry)
-  C_N_LONG = 6,    // Han blocks the fused kernel handed to the general kernels
   C_N_DEFER = 7,   // gated non-Han tokens waiting for the tile-summary scan
   C_FLAGS = 8,     // bit0: the batch must be redone by the general pipeline
-  C_CUR_LDP = 9,   // work cursors of the long-block DP / walk
-  C_CUR_LWALK = 10,
-  C_STREAM = 11,   // 8-byte units of the packed candidate stream in use
-  C_N_FBLK = 12,   // Han blocks packed by the fused kernel for k_block_dp
-  C_CUR_FBLK = 13,
-  C_CUR_EMIT = 14, // work cursor of k_emit
+  C_N_BLK = 12,    // Han blocks listed by k_scan for k_route / k_emit
+  C_CUR_ROUTE = 13,  // work cursors of k_route / k_emit
+  C_CUR_EMIT = 14,
   C_NUM = 16
 };
 
@@ -68,15 +64,8 @@ struct Workspace {
   uint2* walks = nullptr;        // per Han block: (first rune slot, block end byte)
   uint8_t* tile_sum = nullptr;   // per split tile: has-boundary / alnum-before / alnum-after
   uint8_t* tile_ctx = nullptr;   // per split tile: bit0 fwd, bit1 bwd
-  uint8_t* tile_dirty = nullptr; // per split tile: overlapped by a long block (k_split<dag-only> runs there)
-  uint32_t* long_seeds = nullptr;
-  uint32_t long_cap = 0;
   uint4* deferred = nullptr;
   uint32_t deferred_cap = 0;
-  unsigned long long* stream = nullptr;
-  uint32_t stream_cap = 0;
-  uint4* fblocks = nullptr;
-  uint32_t fblk_cap = 0;
   uint32_t* hs_bits = nullptr;   // Han-block start bitmap (k_scan -> k_route)
   uint32_t* path = nullptr;      // chosen word length - 1 per rune (k_route -> k_emit)
   uint8_t* bp = nullptr;         // Viterbi back-pointers per rune (k_emit)
@@ -101,11 +90,10 @@ void workspace_free(Workspace& ws);
 //   d_doc_tok_off[ndocs+1] gets tok_base + rank, d_n_tokens[0] the batch's token count and
 //   d_n_tokens[1] the status word.
 //   force_general: skip the fast path and run the general kernels on everything.
-//   path_mode: 0 = streaming fast path (jb_stream.cu), 1 = the older fused tile kernel (jb_fused.cu).
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_doc_off,
                  uint64_t ndocs, bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
                  uint64_t* d_doc_tok_off, uint64_t tok_base, uint64_t* d_n_tokens, cudaStream_t stream,
-                 bool force_general = false, int path_mode = 0);
+                 bool force_general = false);
 
 // Second phase when d_start/d_end were NULL in run_pipeline (count first, then scatter).
 int run_scatter(Workspace& ws, uint32_t nbytes, uint64_t ndocs, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,

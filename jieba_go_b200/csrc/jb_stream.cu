@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kScThreads, 4) k_scan(const JbTables T, const 
       }
       uint32_t b0 = 0;
       if (tot) {
-        b0 = atomicAdd(&A.counters[C_N_FBLK], tot);
+        b0 = atomicAdd(&A.counters[C_N_BLK], tot);
         if (b0 + tot > A.blocks_cap) atomicOr(&A.counters[C_FLAGS], 1u);
       }
       S.ends_base = b0;
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
   constexpr uint32_t PPW = 32 / PB;  // path entries per word
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t nblocks = min(A.counters[C_N_FBLK], A.blocks_cap);
+  const uint32_t nblocks = min(A.counters[C_N_BLK], A.blocks_cap);
   if (A.counters[C_FLAGS] & 1u) return;  // the general pipeline redoes this batch
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kRtThreads / 32);
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
     if (nm) {
       if (qh == qt && !exhausted) {
         uint32_t b0 = 0;
-        if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_FBLK], chunk);
+        if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_ROUTE], chunk);
         b0 = __shfl_sync(FULL, b0, 0);
         if (b0 >= nblocks) exhausted = true;
         else {
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   if (A.counters[C_FLAGS] & 1u) return;
-  const uint32_t nblocks = min(A.counters[C_N_FBLK], A.blocks_cap);
+  const uint32_t nblocks = min(A.counters[C_N_BLK], A.blocks_cap);
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kEmThreads / 32);
   const uint32_t chunk = min(32u, max(1u, (nblocks + nwarps - 1) / nwarps));

@@ -97,8 +97,7 @@ class Tokenizer:
             pass
 
     def set_general_only(self, on):
-        """Device path selector, for tests: 0/False = streaming fast path (default), 1/True = the general
-        kernels cut every block, 2 = the older fused tile kernel."""
+        """Bypass the streaming fast path (the general kernels then cut every block); for tests."""
         self._path_mode = int(on)
         check(self._L.jb_set_general_only(self._h, self._path_mode), "jb_set_general_only")
 

@@ -7,12 +7,12 @@ import pytest
 from jieba_go_b200 import synth
 
 import kat_vectors as kv
-from helpers import c_oracle_tokenizer, emit_arrays, fuzz_docs, pack_docs
+from helpers import c_oracle_tokenizer, emit_arrays, fuzz_docs, pack_docs  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
 
-PATHS = ["stream", "fused", "general"]  # default streaming fast path / older fused tile kernel / general kernels only
+PATHS = ["stream", "general"]  # default streaming fast path (k_scan/k_route/k_emit) / general kernels only
 
 
 def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="stream", **kw):
@@ -22,8 +22,8 @@ def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="stream", **kw):
     else:
         data = sd_or_lines.dict_txt()
     tk = Tokenizer.from_dict_text(data, mode, emit, **kw)
-    if path != "stream":
-        tk.set_general_only({"general": 1, "fused": 2}[path])
+    if path == "general":
+        tk.set_general_only(True)
     return tk
 
 
@@ -153,6 +153,19 @@ def test_fuzz_docs(small_synth, mode, hmm, path):
     _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 2), text, off)
 
 
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("hmm", [False, True])
+def test_fuzz_docs_streaming_path(small_synth, mode, hmm):
+    """No 4-byte Han rune anywhere, so the batch really stays on k_scan/k_route/k_emit."""
+    sd, emit = small_synth
+    tk = _gpu_tokenizer(sd, emit, mode)
+    ora = c_oracle_tokenizer(sd, emit, mode)
+    rng = np.random.default_rng(300 + mode)
+    docs = fuzz_docs(sd, rng, n_docs=1500, max_len=150, supp_han=False) + [b"", b"", "甲".encode(), b"\xe4", b"x"]
+    text, off = pack_docs(docs)
+    _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 2), text, off)
+
+
 @pytest.mark.parametrize("kind", ["freq", "oov", "long"])
 @pytest.mark.parametrize("hmm", [False, True])
 def test_corpora(medium_pair, kind, hmm):
@@ -219,7 +232,7 @@ def test_device_api(medium_pair):
     assert np.array_equal(d_dto.cpu().numpy().astype(np.uint64), od)
 
 
-# ---- routes specific to the fused fast path -----------------------------------------------------
+# ---- routes specific to the streaming fast path -------------------------------------------------
 def _mixed_corpus(sd, rng, nbytes):
     """Dictionary words with every kind of interruption the fast path hands over or defers: long
     unpunctuated blocks, Japanese/Korean runs (gated tokens across tile edges), ASCII, 2- and 4-byte
@@ -249,7 +262,7 @@ def _mixed_corpus(sd, rng, nbytes):
 
 
 @pytest.mark.parametrize("hmm", [False, True])
-def test_fused_handover_routes(medium_pair, hmm):
+def test_fast_path_handover_routes(medium_pair, hmm):
     sd, emit, tk, ora = medium_pair
     rng = np.random.default_rng(77)
     docs = [_mixed_corpus(sd, rng, 150_000) for _ in range(6)]
@@ -259,3 +272,94 @@ def test_fused_handover_routes(medium_pair, hmm):
     docs2 = docs[:2] + ["甲\U00020000乙".encode() + docs[2]] + docs[3:]
     text, off = pack_docs(docs2)
     _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 8), text, off)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_long_single_rune_runs(small_synth, path):
+    """Viterbi over runs of out-of-vocabulary runes of every length around the 16-rune register window of
+    k_emit (shorter runs keep their back-pointers in registers, longer ones in HBM)."""
+    sd, emit = small_synth
+    tk = _gpu_tokenizer(sd, emit, 1, path=path)
+    ora = c_oracle_tokenizer(sd, emit, 1)
+    rng = np.random.default_rng(11)
+    known = set(w.decode() for w in sd.words if len(w) == 3)
+    pool = [chr(c) for c in range(0x4E00, 0x9FA6) if chr(c) not in known]
+    docs = []
+    for n in list(range(1, 41)) + [63, 64, 65, 100, 257, 1000, 5000]:
+        run = "".join(pool[int(i)] for i in rng.integers(0, len(pool), n))
+        docs.append(run.encode())
+        docs.append((sd.words[3].decode() + run + "，" + run[: n // 2] + sd.words[5].decode() + run).encode())
+    text, off = pack_docs(docs)
+    for hmm in (True, False):
+        _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 2), text, off)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_keys_longer_than_16_runes(path):
+    """A 20- and a 30-rune key: the route ring has 32 cells and path entries take 8 bits (k_route<32,8>)."""
+    sd = synth.make_dictionary(n_words=3000, seed=synth.SEED_BASE + 91, total_freq=1.0e6, max_len=8)
+    emit = synth.make_emit(sd, seed=synth.SEED_BASE + 92)
+    lines = [ln.decode() for ln in sd.lines()]
+    w20 = "".join(chr(0x4E00 + 7 * i) for i in range(20))
+    w30 = "".join(chr(0x5E00 + 11 * i) for i in range(30))
+    lines = lines + ["%s 900 n" % w20, "%s 70000 n" % w30]
+    tk = _gpu_tokenizer(lines, emit, 1, path=path)
+    from oracle import c_oracle as co
+    hm = co.Hmm()
+    hm.set_emit_arrays(*emit_arrays(emit))
+    ora = co.Tokenizer(co.Dict.from_lines(lines, 1), hm)
+    rng = np.random.default_rng(12)
+    docs = []
+    for _ in range(200):
+        parts = []
+        for _ in range(int(rng.integers(1, 40))):
+            r = rng.random()
+            if r < 0.1:
+                parts.append(w20[: int(rng.integers(1, 21))])
+            elif r < 0.2:
+                parts.append(w30[int(rng.integers(0, 5)): int(rng.integers(5, 31))])
+            elif r < 0.25:
+                parts.append("，")
+            else:
+                parts.append(sd.words[int(rng.integers(0, len(sd.words)))].decode())
+        docs.append("".join(parts).encode())
+    text, off = pack_docs(docs)
+    for hmm in (False, True):
+        _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 2), text, off)
+
+
+@pytest.mark.parametrize("hmm", [False, True])
+def test_scan_tile_edges(small_synth, hmm):
+    """k_scan works on 8128-byte tiles with a 32-byte halo word on either side: put every kind of content on
+    the edges (text lengths and document starts within a few bytes of k * 8128)."""
+    sd, emit = small_synth
+    tk = _gpu_tokenizer(sd, emit, 1)
+    ora = c_oracle_tokenizer(sd, emit, 1)
+    rng = np.random.default_rng(13)
+    words = [w for w in sd.words]
+    fillers = ["，", "a1", " ", "é", "€", "ステ", "\n", "9"]
+    docs = []
+    for tiles in (1, 2, 3):
+        for delta in range(-5, 6):
+            target = tiles * 8128 + delta
+            parts, size = [], 0
+            while size < target - 40:
+                p = words[int(rng.integers(0, len(words)))] if rng.random() < 0.9 else fillers[int(rng.integers(0, len(fillers)))].encode()
+                parts.append(p)
+                size += len(p)
+            tail = [b"a", "，".encode(), "乙".encode(), b" ", "é".encode()]
+            while size < target:
+                p = tail[int(rng.integers(0, len(tail)))]
+                if size + len(p) > target:
+                    p = b"x"
+                parts.append(p)
+                size += len(p)
+            docs.append(b"".join(parts))
+    # one document per batch (its end is the end of the text) ...
+    for d in docs:
+        t = np.frombuffer(d, dtype=np.uint8)
+        off = np.array([0, len(d)], dtype=np.uint64)
+        _assert_same(tk.cut_batch(t, off, hmm), ora.cut_batch(t, off, hmm, 1), t, off)
+    # ... and all of them in one batch (document starts near tile edges)
+    text, off = pack_docs(docs)
+    _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 2), text, off)
