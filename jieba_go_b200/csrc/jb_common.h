@@ -25,7 +25,8 @@ struct __attribute__((aligned(16))) JbFirst {
 #define JB_FIRST_GATE 1u
 
 // ---------------------------------------------------------------------------------------
-// Rune-prefix hash: open addressing, linear probing, 16-byte entries (two per 32-byte L2 sector).
+// Rune-prefix hash: open addressing, linear probing, 16-byte entries (two per 32-byte L2 sector),
+// home slot = jb_hash_next fold over the key's runes (below).
 // A key is stored as a TRIE EDGE: (id of the entry of the key minus its last rune, last rune).
 // Matching a probe is two integer compares and is exact -- no key bytes, no fingerprints -- and it
 // mirrors how buildDag reaches a key: only through all of its prefixes (tokenizer.go:473-482), so a key
@@ -55,7 +56,11 @@ JB_HD uint32_t jb_hash_fin(uint32_t h) {
   h ^= h >> 15;
   return h;
 }
-JB_HD uint32_t jb_hash_edge(uint32_t parent, uint32_t rune) { return jb_hash_fin((parent * 0x9E3779B1u) ^ (rune * 0x85EBCA6Bu)); }
+// Slot hash of a key = a fold over its RUNES (not over the parent's slot), so that the slots of successive
+// prefixes of a text position can all be computed -- and fetched -- before any of them has been looked at:
+//   state after the first rune r0:  JB_PARENT_FIRST(r0) for a BMP rune, jb_hash_next(JB_PARENT_ROOT, r0) otherwise
+//   state after one more rune r:    jb_hash_next(state, r);  the key's home slot is state & hash_mask
+JB_HD uint32_t jb_hash_next(uint32_t h, uint32_t rune) { return jb_hash_fin((h * 0x9E3779B1u) ^ (rune * 0x85EBCA6Bu)); }
 JB_HD uint32_t jb_bloom_bit(uint32_t r) { return ((r * 0x9E3779B1u) >> 27) & 31u; }  // first-rune table, 32 bits
 JB_HD uint32_t jb_bloom11(uint32_t r) {                                                // hash entries, 11 bits
   uint32_t b = (r * 0x9E3779B1u) >> 28;
@@ -83,11 +88,13 @@ JB_HD bool jb_w_positive(double w) { return w > -1.0e308; }
 #define JB_MAX_SUPP_RANGES 16
 
 #if defined(__CUDACC__)
-// One trie-edge lookup: termFreq[prefix + rune] where `parent` identifies termFreq[prefix].
-// Returns the slot (>= 0) and fills w / rb, or -1 when the key is missing.  One 16-byte load per step.
-__device__ __forceinline__ int jb_probe_edge(const JbEntry* __restrict__ entries, uint32_t mask, uint32_t parent, uint32_t rune,
-                                             double* w, uint32_t* rb) {
-  uint32_t slot = jb_hash_edge(parent, rune) & mask;
+// One trie-edge lookup: termFreq[prefix + rune] where `parent` identifies termFreq[prefix] and `hs` is the
+// hash state of the prefix (updated to the state of prefix + rune).  Returns the slot (>= 0) and fills
+// w / rb, or -1 when the key is missing.  One 16-byte load per step.
+__device__ __forceinline__ int jb_probe_edge(const JbEntry* __restrict__ entries, uint32_t mask, uint32_t& hs, uint32_t parent,
+                                             uint32_t rune, double* w, uint32_t* rb) {
+  hs = jb_hash_next(hs, rune);
+  uint32_t slot = hs & mask;
   for (;;) {
     const uint4 e = __ldg(reinterpret_cast<const uint4*>(entries + slot));
     if (e.z == JB_PARENT_EMPTY) return -1;

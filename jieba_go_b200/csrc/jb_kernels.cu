@@ -412,6 +412,7 @@ __device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, 
       mask = 1u << (d1 - 1);
       // first probe: termFreq[string(iRune)] (tokenizer.go:468-472)
       uint32_t info, child, parent;
+      uint32_t hs = r0 < 0x10000 ? JB_PARENT_FIRST(r0) : JB_PARENT_ROOT;  // hash state of the prefix (jb_hash_next)
       if (r0 < 0x10000) {
         const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));
         wv[0] = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
@@ -421,7 +422,7 @@ __device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, 
       } else {
         double pw;
         uint32_t prb;
-        int ps = jb_probe_edge(T.entries, T.hash_mask, JB_PARENT_ROOT, r0, &pw, &prb);
+        int ps = jb_probe_edge(T.entries, T.hash_mask, hs, JB_PARENT_ROOT, r0, &pw, &prb);
         if (ps >= 0 && jb_w_positive(pw)) {
           wv[0] = pw;
           info = (uint32_t)JB_MAX_DELTA << 8;
@@ -449,7 +450,7 @@ __device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, 
           if (!may) break;
           double pw;
           uint32_t prb;
-          int ps = jb_probe_edge(T.entries, T.hash_mask, parent, rl, &pw, &prb);
+          int ps = jb_probe_edge(T.entries, T.hash_mask, hs, parent, rl, &pw, &prb);
           if (ps < 0) break;  // !found -> break (tokenizer.go:476-478)
           L++;
           qi += len;
@@ -487,10 +488,11 @@ __device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, 
           wtile[excl] = wv[0];
           uint32_t o = 1;
           uint32_t parent = JB_PARENT_FIRST(r0);
+          uint32_t hs2 = r0 < 0x10000 ? JB_PARENT_FIRST(r0) : JB_PARENT_ROOT;
           if (r0 >= 0x10000) {
             double pw;
             uint32_t prb;
-            parent = (uint32_t)jb_probe_edge(T.entries, T.hash_mask, JB_PARENT_ROOT, r0, &pw, &prb);
+            parent = (uint32_t)jb_probe_edge(T.entries, T.hash_mask, hs2, JB_PARENT_ROOT, r0, &pw, &prb);
           }
           int qi = i + len0;
           while (o < cnt) {
@@ -498,7 +500,7 @@ __device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, 
             uint32_t rl = d_decode(&S.t.sb[qi], len);
             double pw;
             uint32_t prb;
-            int ps = jb_probe_edge(T.entries, T.hash_mask, parent, rl, &pw, &prb);
+            int ps = jb_probe_edge(T.entries, T.hash_mask, hs2, parent, rl, &pw, &prb);
             if (ps < 0) break;
             qi += len;
             if (jb_w_positive(pw)) wtile[excl + o++] = pw;
@@ -1132,6 +1134,7 @@ __global__ void k_debug_lookup(const JbTables T, const uint32_t* runes, int L, i
   // walks the key the way buildDag reaches it: through every prefix (a key whose prefix is missing is unreachable)
   uint32_t r0 = runes[0];
   uint32_t parent;
+  uint32_t hs = r0 < 0x10000 ? JB_PARENT_FIRST(r0) : JB_PARENT_ROOT;
   double cw = 0;
   int k = 0;
   if (r0 < 0x10000) {
@@ -1142,13 +1145,13 @@ __global__ void k_debug_lookup(const JbTables T, const uint32_t* runes, int L, i
     parent = JB_PARENT_FIRST(r0);
   } else {
     uint32_t rb;
-    int ps = jb_probe_edge(T.entries, T.hash_mask, JB_PARENT_ROOT, r0, &cw, &rb);
+    int ps = jb_probe_edge(T.entries, T.hash_mask, hs, JB_PARENT_ROOT, r0, &cw, &rb);
     k = ps < 0 ? 0 : (jb_w_positive(cw) ? 2 : 1);
     parent = (uint32_t)ps;
   }
   for (int j = 1; j < L && k != 0; j++) {
     uint32_t rb;
-    int ps = jb_probe_edge(T.entries, T.hash_mask, parent, runes[j], &cw, &rb);
+    int ps = jb_probe_edge(T.entries, T.hash_mask, hs, parent, runes[j], &cw, &rb);
     k = ps < 0 ? 0 : (jb_w_positive(cw) ? 2 : 1);
     parent = (uint32_t)ps;
   }

@@ -22,6 +22,7 @@ struct ScanSmem {
   uint32_t HANL[kScThreads];     // Han rune starts
   uint32_t ALN[kScThreads];      // ASCII [a-zA-Z0-9] bytes
   uint32_t BND[kScThreads];      // first byte of every block (Han or not), end of text
+  uint32_t HS[kScThreads];       // first rune of every Han block
   uint32_t OTE[kScThreads + 1];  // last byte of every non-Han, non-alnum, non-space rune
   uint32_t S[kScThreads + 1], E[kScThreads + 1];
   uint32_t wsum[kScThreads / 32];
@@ -305,9 +306,11 @@ __global__ void __launch_bounds__(kScThreads, 4) k_scan(const JbTables T, const 
     S.BND[wj] = BND;
     S.S[wj] = ALN & (D | ~prevAl);  // an alnum run is one token (T:298-299)
     S.E[wj] = ALN & ~nextAl;
+    S.HS[wj] = HS;
     if (Pw < (int64_t)n) A.hs_bits[(uint32_t)(Pw >> 5)] = HS;
   } else {
     S.BND[wj] = 0;
+    S.HS[wj] = 0;
   }
   // Han block ends -> list, in text order within the tile
   {
@@ -341,7 +344,13 @@ __global__ void __launch_bounds__(kScThreads, 4) k_scan(const JbTables T, const 
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      if (o < A.blocks_cap) A.blocks[o] = make_uint2((uint32_t)Pw + b, 0u);
+      // the block's length in runes, when its first rune lies in this tile (else 0: k_route finds it in hs_bits)
+      uint32_t nr = 0;
+      uint32_t hm = S.HS[wj] & ((b == 31) ? FULL : ((2u << b) - 1u));
+      int ws = wj;
+      while (!hm && ws > 1) hm = S.HS[--ws];
+      if (hm) nr = (uint32_t)((wj - ws) * 32 + b - (31 - __clz(hm))) / 3u + 1u;
+      if (o < A.blocks_cap) A.blocks[o] = make_uint2((uint32_t)Pw + b, nr);
       o++;
     }
   }
@@ -413,30 +422,24 @@ int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st) {
 }
 
 // ==========================================================================================
-// k_route: buildDag + calcDagProba + maxIndexProba, one lane per Han block, right to left.
-//
-// Lane state machine, one step per loop iteration (sections separated by __syncwarp(), otherwise the
-// compiler threads the exits of one section into the next and the lanes run them a few at a time):
-//   POS     consumes the two loads that were issued when the lane ADVANCED to this rune -- the first-rune
-//           table entry (T:468-472) and the hash entry of the 2-rune prefix (its address needs only the two
-//           runes, so it is fetched speculatively, before the gate / Bloom test says whether buildDag
-//           would look at it) -- and turns them into the first candidates of maxIndexProba's running
-//           (prev, best) pair: pieceFreq + next.proba (T:519-529), compared with the previous one (T:569).
-//   PROBE   one more trie-edge probe = one turn of `for j := range textRunes[i:]` (T:473-482), or one
-//           more step of linear probing when the slot held a foreign entry.
-//   COMMIT  the position's selected (length, value) -> route ring + 4-bit path entry; first rune of the
-//           block reached (start bitmap) -> hand the block to k_emit; else advance: decode the next rune
-//           from the register window, issue its two table loads and the next text word.
-// No load is consumed in the iteration that issues it, and a lane that finishes its block takes the next
-// one from the warp's queue, so all 32 lanes stay busy whatever the block lengths.
-// Per-lane shared memory: the last RING route values and runes.
+// k_route: buildDag + calcDagProba + maxIndexProba, one lane per Han block, right to left,
+// ONE POSITION PER LOOP ITERATION per lane, in straight-line code:
+//   * when a lane advances to a rune it issues every load the position will need and looks at none of
+//     them: the first-rune table entry (T:468-472), the hash entries of the 2- and 3-rune prefixes (their
+//     slots depend on the runes only -- jb_hash_next -- so they are fetched speculatively, before the gate /
+//     Bloom tests say whether buildDag would look at them) and the next 8 bytes of text;
+//   * the next iteration consumes them: candidates in ascending length, pieceFreq + next.proba (T:519-529),
+//     folded into maxIndexProba's running (prev, best) pair (T:565-578); a 4th rune or a hash collision
+//     (about one position in eight) goes on in a short loop of dependent probes;
+//   * commit: selected (length, value) -> route ring + 4-bit path entry; first rune of the block -> the block
+//     is handed to k_emit and the lane takes the next block from the warp's queue.
+// All 32 lanes stay busy whatever the block lengths.  Per-lane shared memory: the last RING route values and runes.
 // ==========================================================================================
 constexpr int kRtThreads = 128;
 constexpr int kRtQueue = 32;
-enum : int { ST_IDLE = 0, ST_POS = 1, ST_PROBE = 2 };
 
 template <int RING, int PB>
-__global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const RouteArgs A) {
+__global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const RouteArgs A) {
   __shared__ double ring[RING][kRtThreads];
   __shared__ uint32_t rr[RING][kRtThreads];
   constexpr uint32_t M = RING - 1;
@@ -448,47 +451,48 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kRtThreads / 32);
   const uint32_t chunk = min((uint32_t)kRtQueue, max(1u, (nblocks + nwarps - 1) / nwarps));
-  const uintptr_t tbase = reinterpret_cast<uintptr_t>(A.text);
+  // text is read through 8-byte aligned words: offsets are relative to the aligned base
+  const uint32_t tmis = (uint32_t)(reinterpret_cast<uintptr_t>(A.text) & 7);
+  const uint2* __restrict__ text8 = reinterpret_cast<const uint2*>(A.text - tmis);
   const uint4* __restrict__ first = reinterpret_cast<const uint4*>(T.first);
   const uint4* __restrict__ entries = reinterpret_cast<const uint4*>(T.entries);
   const uint32_t hmask = T.hash_mask;
+  double* const sring = &ring[0][tid];   // this lane's ring cells: index * kRtThreads
+  uint32_t* const srr = &rr[0][tid];
   uint32_t qh = 0, qt = 0;
-  bool exhausted = false;
-  int st = ST_IDLE;
-  uint32_t bi = 0, p = 0, kq = 0, e3 = 0;  // block index, lead byte of the current rune, runes to its right, end / 3
-  uint32_t r0 = 0;                         // the current rune
-  uint4 f = make_uint4(0, 0, 0, 0);        // its first-rune table entry (in flight until POS)
-  uint4 e = make_uint4(0, 0, 0, 0);        // the hash entry in flight: 2-rune prefix (POS) or the chain's next probe (PROBE)
-  uint32_t slot = 0;                       // where e was loaded from
-  uint32_t L = 0, parent = 0, rl = 0, maxlen = 0;
-  uint32_t best_d = 0, last_d = 0;
-  double best_v = 0.0, last_v = 0.0, prev_v = 0.0;
-  uint32_t tw_lo = 0, tw_hi = 0;
-  uintptr_t ta = 1;  // address of the aligned 8-byte text window held in (tw_lo, tw_hi)
-  uint32_t hsw = 0, hst = 0xFFFFFFFFu;
+  bool exhausted = false, active = false;
+  uint32_t bi = 0, p = 0, kq = 0, e3i = 0, nr = 0;  // block index, lead byte of the current rune (+ tmis), runes to its right, end / 3, runes (0: unknown)
+  uint32_t r0 = 0;                                  // the current rune
+  uint4 f = make_uint4(0, 0, 0, 0), e2 = f, e3 = f; // in flight: first-rune entry, entries of the 2- and 3-rune prefixes
+  uint32_t h2 = 0, h3 = 0;                          // their hash states
+  uint32_t w0 = 0, w1 = 0, wn = 0, wc = 0xFFFFFFFFu;  // text window: 8-byte word wc in (w0, w1), first 4 bytes of word wc + 1 in wn
+  uint2 tp = make_uint2(0, 0);                        // in flight: 8-byte word wc - 1
   uint32_t acc = 0, accw = 0xFFFFFFFFu;
+  // A position that needs more probes than the two prefetched ones stays for further iterations (one dependent
+  // probe each, in flight in e2); meanwhile its selector state is parked in the registers of f / e3 / h2 / h3.
+  bool chain = false;
+  uint32_t cs = 0;  // L | maxlen << 8 | best_d << 16 | last_d << 24
 
-  // the lane now stands on the rune at p (inside the text window): decode it, issue its table loads and the
-  // text word the next rune to the left needs
-  auto setup_pos = [&]() {
-    const uintptr_t ap = tbase + p;
-    const uint32_t x = __funnelshift_r(tw_lo, tw_hi, (uint32_t)(ap & 3) * 8u);
+  // the lane now stands on the rune at p: decode it from the window, issue its table loads (first = true: last
+  // rune of a block, nothing to its right)
+  auto setup_pos = [&](const bool first_rune) {
+    const uint32_t o = p & 7u;
+    const uint32_t x = __funnelshift_r(o & 4u ? w1 : w0, o & 4u ? wn : w1, (o & 3u) * 8u);
+    const uint32_t r1 = r0;
     r0 = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
-    rr[kq & M][tid] = r0;
+    srr[(kq & M) * kRtThreads] = r0;
     f = __ldg(first + r0);
-    if (p >= 3u) {
-      const uintptr_t a = (ap - 3) & ~(uintptr_t)3;
-      if (a != ta) {
-        tw_hi = tw_lo;
-        tw_lo = __ldg(reinterpret_cast<const uint32_t*>(a));
-        ta = a;
-      }
+    if (!first_rune) {  // (with one rune to the right the 3-rune slot is computed from a stale rune: loaded, never looked at)
+      h2 = jb_hash_next(JB_PARENT_FIRST(r0), r1);
+      e2 = __ldg(entries + (h2 & hmask));
+      h3 = jb_hash_next(h2, srr[((kq - 2u) & M) * kRtThreads]);
+      e3 = __ldg(entries + (h3 & hmask));
     }
   };
 
   for (;;) {
     // ---- refill idle lanes from the warp's queue of block indexes ----
-    const uint32_t nm = __ballot_sync(FULL, st == ST_IDLE);
+    const uint32_t nm = __ballot_sync(FULL, !active);
     if (nm) {
       if (qh == qt && !exhausted) {
         uint32_t b0 = 0;
@@ -500,119 +504,179 @@ __global__ void __launch_bounds__(kRtThreads) k_route(const JbTables T, const Ro
           qt = min(b0 + chunk, nblocks);
         }
       }
-      if (st == ST_IDLE) {
+      if (!active) {
         const uint32_t mine = qh + __popc(nm & lt_mask);
         if (mine < qt) {
           bi = mine;
-          p = A.blocks[bi].x;
-          e3 = p / 3u;
+          const uint2 bd = A.blocks[bi];
+          e3i = bd.x / 3u;
+          nr = bd.y;
+          p = bd.x + tmis;
           kq = 0;
-          const uintptr_t a = (tbase + p) & ~(uintptr_t)3;
-          tw_lo = __ldg(reinterpret_cast<const uint32_t*>(a));
-          tw_hi = __ldg(reinterpret_cast<const uint32_t*>(a + 4));
-          ta = a;
-          setup_pos();
-          st = ST_POS;
+          wc = p >> 3;
+          const uint2 t0 = __ldg(text8 + wc);
+          w0 = t0.x;
+          w1 = t0.y;
+          if ((p & 7u) >= 6u) wn = __ldg(reinterpret_cast<const uint32_t*>(text8 + wc + 1));  // the rune's tail (never past the text)
+          if (wc) tp = __ldg(text8 + wc - 1);
+          setup_pos(true);
+          chain = false;
+          active = true;
         }
       }
       qh = min(qt, qh + (uint32_t)__popc(nm));
-      if (exhausted && __all_sync(FULL, st == ST_IDLE)) break;
+      if (exhausted && __all_sync(FULL, !active)) break;
     }
-    // ---- 1. a lane that advanced: its first-rune entry has arrived -> candidate (i,i+1), gate (T:468-472) ----
-    bool probing = st == ST_PROBE, done = false;
-    if (st == ST_POS) {
-      const double w0 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
-      const double nxt = kq ? ring[(kq - 1u) & M][tid] : 0.0;
-      const double v = w0 + nxt;
-      last_d = 1;
-      last_v = v;
-      prev_v = v;
-      best_v = v;
-      best_d = (v >= JB_MINF) ? 1u : 0u;  // first comparison is against minFloat (T:566,569)
-      maxlen = min(min((f.z >> 8) & 0xFFu, 31u), kq + 1u);
-      // the 2-rune prefix's entry was fetched speculatively; buildDag looks at it only past the gate (the
-      // Bloom filter of second runes only spares work: a miss means the entry cannot match)
-      probing = !(f.z & JB_FIRST_GATE) && maxlen > 1 && ((f.w >> jb_bloom_bit(rl)) & 1);
-      done = !probing;
-      st = ST_PROBE;
-    }
-    __syncwarp();
-    // ---- 2. one turn of `for j := range textRunes[i:]` (T:473-482) on the hash entry that has arrived ----
-    bool issue = false, foreign = false;
-    if (probing) {
-      if (e.z == JB_PARENT_EMPTY) {  // !found -> break (T:476-478)
-        done = true;
-      } else if (e.z == parent && JB_RB_RUNE(e.w) == rl) {
-        L++;
-        const double pw = __longlong_as_double(((long long)e.y << 32) | (long long)e.x);
-        if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481); maxIndexProba's loop body (T:568-572)
-          const double nxt = (L > kq) ? 0.0 : ring[(kq - L) & M][tid];  // {j, 0.0} at the end of the block (T:522)
-          const double v = pw + nxt;                                    // pieceFreq + nextBestPiece.proba (T:529)
-          if (v >= prev_v) {
-            best_d = L;
-            best_v = v;
-          }
-          prev_v = v;
-          last_d = L;
-          last_v = v;
+    double best_v, last_v, prev_v;
+    uint32_t best_d, last_d, L, parent, rl, slot, hs, maxlen;
+    bool more;
+    const bool chained = active && chain;
+    // ---- a position on a longer prefix or a hash collision: one more turn of the loop (T:473-482) on the entry in e2 ----
+    if (chained) {
+      best_v = __hiloint2double((int)e3.y, (int)e3.x);
+      last_v = __hiloint2double((int)e3.w, (int)e3.z);
+      prev_v = __hiloint2double((int)f.y, (int)f.x);
+      parent = f.z;
+      rl = f.w;
+      hs = h2;
+      slot = h3;
+      L = cs & 0xFFu;
+      maxlen = (cs >> 8) & 0xFFu;
+      best_d = (cs >> 16) & 0xFFu;
+      last_d = cs >> 24;
+      const bool hit = e2.z == parent && JB_RB_RUNE(e2.w) == rl;
+      const bool foreign = !hit && e2.z != JB_PARENT_EMPTY;  // linear probing goes on; an empty slot ends the loop (T:476-478)
+      const double pw = __longlong_as_double(((long long)e2.y << 32) | (long long)e2.x);
+      L += hit ? 1u : 0u;
+      const uint32_t rn = srr[((kq - L) & M) * kRtThreads];
+      if (hit && jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481); maxIndexProba's loop body (T:568-572)
+        const double v = pw + ((L > kq) ? 0.0 : sring[((kq - L) & M) * kRtThreads]);
+        if (v >= prev_v) {
+          best_d = L;
+          best_v = v;
         }
-        done = true;
-        if (L < maxlen) {
-          const uint32_t rn = rr[(kq - L) & M][tid];
-          if (((e.w >> 21) >> jb_bloom11(rn)) & 1) {  // some key extends this prefix by rn
-            parent = slot;
-            rl = rn;
-            issue = true;
-            done = false;
-          }
-        }
-      } else {  // foreign entry: linear probing
-        foreign = true;
-        issue = true;
+        prev_v = v;
+        last_d = L;
+        last_v = v;
       }
+      const bool deeper = hit && L < maxlen && (((e2.w >> 21) >> jb_bloom11(rn)) & 1);
+      if (deeper) {
+        parent = slot;
+        rl = rn;
+        hs = jb_hash_next(hs, rl);
+      }
+      slot = deeper ? (hs & hmask) : ((slot + 1) & hmask);
+      more = deeper || foreign;
     }
     __syncwarp();
-    // ---- 3. commit the position; advance to the rune on the left ----
-    if (done) {
+    // ---- a fresh position, in straight-line predicated code: the first-rune entry (T:468-472) and the entries of
+    // the 2- and 3-rune prefixes are here; candidates in ascending length (T:515-529, 565-578) ----
+    if (active && !chained) {
+      const uint32_t k1 = ((kq - 1u) & M) * kRtThreads, k2 = ((kq - 2u) & M) * kRtThreads, k3 = ((kq - 3u) & M) * kRtThreads;
+      const double R1 = sring[k1], R2 = sring[k2], R3 = sring[k3];
+      const uint32_t r1 = srr[k1], r2 = srr[k2], r3 = srr[k3];
+      const double wt1 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
+      const double wt2 = __longlong_as_double(((long long)e2.y << 32) | (long long)e2.x);
+      const double wt3 = __longlong_as_double(((long long)e3.y << 32) | (long long)e3.x);
+      maxlen = min(min((f.z >> 8) & 0xFFu, 31u), kq + 1u);
+      const uint32_t par2 = JB_PARENT_FIRST(r0), slot2 = h2 & hmask, slot3 = h3 & hmask;
+      // which entries buildDag looks at, and what it finds
+      const bool g2 = !(f.z & JB_FIRST_GATE) && maxlen > 1u && ((f.w >> jb_bloom_bit(r1)) & 1u);
+      const bool m2 = g2 && e2.z == par2 && JB_RB_RUNE(e2.w) == r1;
+      const bool x2 = g2 && !m2 && e2.z != JB_PARENT_EMPTY;  // foreign entry: linear probing
+      const bool g3 = m2 && maxlen > 2u && (((e2.w >> 21) >> jb_bloom11(r2)) & 1u);
+      const bool m3 = g3 && e3.z == slot2 && JB_RB_RUNE(e3.w) == r2;
+      const bool x3 = g3 && !m3 && e3.z != JB_PARENT_EMPTY;
+      const bool g4 = m3 && maxlen > 3u && (((e3.w >> 21) >> jb_bloom11(r3)) & 1u);
+      // candidates: pieceFreq + nextBestPiece.proba ({j, 0.0} at the end of the block, T:522-529)
+      const double v1 = wt1 + (kq >= 1u ? R1 : 0.0);
+      const double v2 = wt2 + (kq >= 2u ? R2 : 0.0);
+      const double v3 = wt3 + (kq >= 3u ? R3 : 0.0);
+      const bool c2 = m2 && jb_w_positive(wt2), c3 = m3 && jb_w_positive(wt3);  // val > 0 -> edge (T:479-481)
+      // maxIndexProba (T:565-578): each candidate is compared with the previous one, first with minFloat
+      best_d = (v1 >= JB_MINF) ? 1u : 0u;
+      best_v = v1;
+      prev_v = v1;
+      last_d = 1u;
+      last_v = v1;
+      const bool b2 = c2 && v2 >= prev_v;
+      best_d = b2 ? 2u : best_d;
+      best_v = b2 ? v2 : best_v;
+      prev_v = c2 ? v2 : prev_v;
+      last_d = c2 ? 2u : last_d;
+      last_v = c2 ? v2 : last_v;
+      const bool b3 = c3 && v3 >= prev_v;
+      best_d = b3 ? 3u : best_d;
+      best_v = b3 ? v3 : best_v;
+      prev_v = c3 ? v3 : prev_v;
+      last_d = c3 ? 3u : last_d;
+      last_v = c3 ? v3 : last_v;
+      // anything beyond goes on in later iterations
+      more = x2 || x3 || g4;
+      L = m3 ? 3u : (m2 ? 2u : 1u);
+      parent = g4 ? slot3 : (x3 ? slot2 : par2);
+      rl = g4 ? r3 : (x3 ? r2 : r1);
+      hs = g4 ? jb_hash_next(h3, r3) : (x3 ? h3 : h2);
+      slot = g4 ? (hs & hmask) : (((x3 ? slot3 : slot2) + 1u) & hmask);
+    }
+    __syncwarp();
+    if (active && more) {  // park the selector state, issue the next probe
+      e3.x = (uint32_t)__double2loint(best_v);
+      e3.y = (uint32_t)__double2hiint(best_v);
+      e3.z = (uint32_t)__double2loint(last_v);
+      e3.w = (uint32_t)__double2hiint(last_v);
+      f.x = (uint32_t)__double2loint(prev_v);
+      f.y = (uint32_t)__double2hiint(prev_v);
+      f.z = parent;
+      f.w = rl;
+      h2 = hs;
+      h3 = slot;
+      cs = L | (maxlen << 8) | (best_d << 16) | (last_d << 24);
+      e2 = __ldg(entries + slot);
+      chain = true;
+    }
+    __syncwarp();
+    if (active && !more) {
+      chain = false;
+      // ---- commit the position ----
       if (best_d == 0) {  // best.index == -1 -> return prev (T:574-576)
         best_d = last_d;
         best_v = last_v;
       }
-      ring[kq & M][tid] = best_v;
-      const uint32_t idx = e3 - kq, pwd = idx / PPW;
+      sring[(kq & M) * kRtThreads] = best_v;
+      const uint32_t idx = e3i - kq, pwd = idx / PPW;
       if (pwd != accw) {
         if (acc) atomicOr(&A.path[accw], acc);
         acc = 0;
         accw = pwd;
       }
       acc |= (best_d - 1u) << ((idx % PPW) * PB);
-      if ((p >> 5) != hst) {
-        hst = p >> 5;
-        hsw = __ldg(A.hs_bits + hst);
+      bool start = kq + 1u == nr;
+      if (nr == 0) {  // the block began in another k_scan tile: its first rune is marked in the start bitmap
+        const uint32_t q = p - tmis;
+        start = (__ldg(A.hs_bits + (q >> 5)) >> (q & 31)) & 1;
       }
-      if ((hsw >> (p & 31)) & 1) {  // first rune of the block
+      if (start) {  // first rune of the block
         if (acc) atomicOr(&A.path[accw], acc);
         acc = 0;
         accw = 0xFFFFFFFFu;
-        A.blocks[bi] = make_uint2(p, kq + 1u);
-        st = ST_IDLE;
+        A.blocks[bi] = make_uint2(p - tmis, kq + 1u);
+        active = false;
       } else {
+        // ---- advance to the rune on the left ----
         p -= 3u;
         kq++;
-        rl = r0;  // the rune right of the new position: second rune of its 2-rune prefix
-        setup_pos();
-        parent = JB_PARENT_FIRST(r0);
-        L = 1;
-        issue = true;
-        st = ST_POS;
+        if ((p >> 3) != wc) {  // into the next 8-byte word (fetched when the lane entered this one)
+          wn = w0;
+          w0 = tp.x;
+          w1 = tp.y;
+          wc--;
+          if (wc) tp = __ldg(text8 + wc - 1);
+        }
+        setup_pos(false);
       }
     }
     __syncwarp();
-    // ---- 4. issue the next hash probe (consumed in a later iteration) ----
-    if (issue) {
-      slot = foreign ? ((slot + 1) & hmask) : (jb_hash_edge(parent, rl) & hmask);
-      e = __ldg(entries + slot);
-    }
   }
 }
 
