@@ -34,8 +34,10 @@ struct __attribute__((aligned(16))) JbFirst {
 //   parent id: slot index of the parent entry (< 0x80000000)
 //              0x80000000 | r0   for 2-rune keys whose first rune r0 is in the BMP (first-rune table)
 //              0xC0000000        for 1-rune keys outside the BMP (root)
-//   rb       : bits 0..20 last rune, bits 21..31 an 11-bit Bloom filter of the next rune over the
-//              keys that extend this key by one rune (a miss ends the loop without a memory access)
+//   rb       : bits 0..20 last rune, bits 21..30 a 10-bit Bloom filter of the next rune over the
+//              keys that extend this key by one rune (a miss ends the loop without a memory access),
+//              bit 31 CONT: some key whose home slot is THIS slot lives further down the probe sequence
+//              (clear => a lookup that finds a foreign entry in its home slot can stop: the key is absent)
 //   w        : log(freq) - log(size); -Inf marks a key with freq 0 (prefix-only, tokenizer.go:360)
 // ---------------------------------------------------------------------------------------
 struct __attribute__((aligned(16))) JbEntry {
@@ -47,6 +49,7 @@ struct __attribute__((aligned(16))) JbEntry {
 #define JB_PARENT_ROOT 0xC0000000u
 #define JB_PARENT_FIRST(r0) (0x80000000u | (r0))
 #define JB_RB_RUNE(rb) ((rb) & 0x1FFFFFu)
+#define JB_RB_CONT 0x80000000u
 
 JB_HD uint32_t jb_hash_fin(uint32_t h) {
   h ^= h >> 15;
@@ -62,9 +65,9 @@ JB_HD uint32_t jb_hash_fin(uint32_t h) {
 //   state after one more rune r:    jb_hash_next(state, r);  the key's home slot is state & hash_mask
 JB_HD uint32_t jb_hash_next(uint32_t h, uint32_t rune) { return jb_hash_fin((h * 0x9E3779B1u) ^ (rune * 0x85EBCA6Bu)); }
 JB_HD uint32_t jb_bloom_bit(uint32_t r) { return ((r * 0x9E3779B1u) >> 27) & 31u; }  // first-rune table, 32 bits
-JB_HD uint32_t jb_bloom11(uint32_t r) {                                                // hash entries, 11 bits
+JB_HD uint32_t jb_bloom11(uint32_t r) {                                                // hash entries, 10 bits (21..30)
   uint32_t b = (r * 0x9E3779B1u) >> 28;
-  return b >= 11u ? b - 5u : b;
+  return b >= 10u ? b - 6u : b;
 }
 // +/-Inf test on the bits (w is -Inf exactly for freq-0 keys)
 JB_HD bool jb_w_positive(double w) { return w > -1.0e308; }
@@ -95,7 +98,7 @@ __device__ __forceinline__ int jb_probe_edge(const JbEntry* __restrict__ entries
                                              uint32_t rune, double* w, uint32_t* rb) {
   hs = jb_hash_next(hs, rune);
   uint32_t slot = hs & mask;
-  for (;;) {
+  for (bool home = true;; home = false) {
     const uint4 e = __ldg(reinterpret_cast<const uint4*>(entries + slot));
     if (e.z == JB_PARENT_EMPTY) return -1;
     if (e.z == parent && JB_RB_RUNE(e.w) == rune) {
@@ -103,6 +106,7 @@ __device__ __forceinline__ int jb_probe_edge(const JbEntry* __restrict__ entries
       *rb = e.w;
       return (int)slot;
     }
+    if (home && !(e.w & JB_RB_CONT)) return -1;  // nothing with this home slot was displaced
     slot = (slot + 1) & mask;
   }
 }

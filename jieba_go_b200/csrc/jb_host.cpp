@@ -648,6 +648,7 @@ int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int ver, Tabl
     uint32_t hs = k.runes[0] < 0x10000 ? JB_PARENT_FIRST(k.runes[0]) : jb_hash_next(JB_PARENT_ROOT, k.runes[0]);
     for (size_t j = 1; j < L; j++) hs = jb_hash_next(hs, k.runes[j]);
     uint32_t sidx = hs & hmask;
+    if (img.entries[sidx].parent != JB_PARENT_EMPTY) img.entries[sidx].rb |= JB_RB_CONT;  // displaced from its home slot
     while (img.entries[sidx].parent != JB_PARENT_EMPTY) sidx = (sidx + 1) & hmask;
     img.entries[sidx].w = k.freq > 0 ? k.w : -INFINITY;
     img.entries[sidx].parent = parent;

@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   // A position that needs more probes than the two prefetched ones stays for further iterations (one dependent
   // probe each, in flight in e2); meanwhile its selector state is parked in the registers of f / e3 / h2 / h3.
   bool chain = false;
-  uint32_t cs = 0;  // L | maxlen << 8 | best_d << 16 | last_d << 24
+  uint32_t cs = 0;  // L | home-slot flag << 7 | maxlen << 8 | best_d << 16 | last_d << 24
 
   // the lane now stands on the rune at p: decode it from the window, issue its table loads (first = true: last
   // rune of a block, nothing to its right)
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     }
     double best_v, last_v, prev_v;
     uint32_t best_d, last_d, L, parent, rl, slot, hs, maxlen;
-    bool more;
+    bool more, home = false;  // home: the next probe looks at the home slot of its key
     const bool chained = active && chain;
     // ---- a position on a longer prefix or a hash collision: one more turn of the loop (T:473-482) on the entry in e2 ----
     if (chained) {
@@ -540,12 +540,14 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       rl = f.w;
       hs = h2;
       slot = h3;
-      L = cs & 0xFFu;
+      L = cs & 0x7Fu;
       maxlen = (cs >> 8) & 0xFFu;
       best_d = (cs >> 16) & 0xFFu;
       last_d = cs >> 24;
       const bool hit = e2.z == parent && JB_RB_RUNE(e2.w) == rl;
-      const bool foreign = !hit && e2.z != JB_PARENT_EMPTY;  // linear probing goes on; an empty slot ends the loop (T:476-478)
+      // linear probing goes on past a foreign entry (past the home slot only if a key was displaced from it);
+      // an empty slot ends the loop (T:476-478)
+      const bool foreign = !hit && e2.z != JB_PARENT_EMPTY && (!(cs & 0x80u) || (e2.w & JB_RB_CONT));
       const double pw = __longlong_as_double(((long long)e2.y << 32) | (long long)e2.x);
       L += hit ? 1u : 0u;
       const uint32_t rn = srr[((kq - L) & M) * kRtThreads];
@@ -567,6 +569,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       }
       slot = deeper ? (hs & hmask) : ((slot + 1) & hmask);
       more = deeper || foreign;
+      home = deeper;
     }
     __syncwarp();
     // ---- a fresh position, in straight-line predicated code: the first-rune entry (T:468-472) and the entries of
@@ -583,10 +586,10 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       // which entries buildDag looks at, and what it finds
       const bool g2 = !(f.z & JB_FIRST_GATE) && maxlen > 1u && ((f.w >> jb_bloom_bit(r1)) & 1u);
       const bool m2 = g2 && e2.z == par2 && JB_RB_RUNE(e2.w) == r1;
-      const bool x2 = g2 && !m2 && e2.z != JB_PARENT_EMPTY;  // foreign entry: linear probing
+      const bool x2 = g2 && !m2 && e2.z != JB_PARENT_EMPTY && (e2.w & JB_RB_CONT);  // foreign entry in the home slot and a displaced key: linear probing
       const bool g3 = m2 && maxlen > 2u && (((e2.w >> 21) >> jb_bloom11(r2)) & 1u);
       const bool m3 = g3 && e3.z == slot2 && JB_RB_RUNE(e3.w) == r2;
-      const bool x3 = g3 && !m3 && e3.z != JB_PARENT_EMPTY;
+      const bool x3 = g3 && !m3 && e3.z != JB_PARENT_EMPTY && (e3.w & JB_RB_CONT);
       const bool g4 = m3 && maxlen > 3u && (((e3.w >> 21) >> jb_bloom11(r3)) & 1u);
       // candidates: pieceFreq + nextBestPiece.proba ({j, 0.0} at the end of the block, T:522-529)
       const double v1 = wt1 + (kq >= 1u ? R1 : 0.0);
@@ -613,6 +616,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       last_v = c3 ? v3 : last_v;
       // anything beyond goes on in later iterations
       more = x2 || x3 || g4;
+      home = g4;
       L = m3 ? 3u : (m2 ? 2u : 1u);
       parent = g4 ? slot3 : (x3 ? slot2 : par2);
       rl = g4 ? r3 : (x3 ? r2 : r1);
@@ -631,7 +635,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       f.w = rl;
       h2 = hs;
       h3 = slot;
-      cs = L | (maxlen << 8) | (best_d << 16) | (last_d << 24);
+      cs = L | (home ? 0x80u : 0u) | (maxlen << 8) | (best_d << 16) | (last_d << 24);
       e2 = __ldg(entries + slot);
       chain = true;
     }
