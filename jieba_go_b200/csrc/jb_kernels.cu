@@ -923,12 +923,13 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const JbTables T, const W
 
 // ------------------------------------------------------------------------------------------
 // Token ranking: start/end bitmaps -> (start,end) arrays in document order, doc-relative.
+// Rank tiles of 32 KiB of text (1024 bitmap words, one per thread).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRankWords) k_rank_count(const uint32_t* __restrict__ s_bits, const uint32_t* __restrict__ e_bits,
                                                           uint32_t nwords, uint32_t* __restrict__ cnt) {
   __shared__ uint32_t red[2][kRankWords / 32];
-  uint32_t w = blockIdx.x * kRankWords + threadIdx.x;
-  uint32_t c = w < nwords ? __popc(s_bits[w]) : 0, e = w < nwords ? __popc(e_bits[w]) : 0;
+  const uint32_t w = blockIdx.x * kRankWords + threadIdx.x;
+  uint32_t c = w < nwords ? __popc(__ldg(s_bits + w)) : 0, e = w < nwords ? __popc(__ldg(e_bits + w)) : 0;
   c = __reduce_add_sync(FULL, c);
   e = __reduce_add_sync(FULL, e);
   if ((threadIdx.x & 31) == 0) {
@@ -936,9 +937,13 @@ __global__ void __launch_bounds__(kRankWords) k_rank_count(const uint32_t* __res
     red[1][threadIdx.x >> 5] = e;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    cnt[2 * blockIdx.x] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-    cnt[2 * blockIdx.x + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  if (threadIdx.x < 32) {
+    c = __reduce_add_sync(FULL, red[0][threadIdx.x]);
+    e = __reduce_add_sync(FULL, red[1][threadIdx.x]);
+    if (threadIdx.x == 0) {
+      cnt[2 * blockIdx.x] = c;
+      cnt[2 * blockIdx.x + 1] = e;
+    }
   }
 }
 
@@ -999,7 +1004,7 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
                                                             const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ doc_off32,
                                                             uint64_t ndocs, uint32_t* __restrict__ out_start, uint32_t* __restrict__ out_end,
                                                             uint64_t cap, uint64_t* __restrict__ doc_tok, uint64_t tok_base) {
-  __shared__ uint32_t sS[kRankWords], sPS[kRankWords], sPE[kRankWords];
+  __shared__ uint32_t sS[kRankWords], sPS[kRankWords];
   __shared__ uint32_t wsum[2][kRankWords / 32];
   __shared__ int32_t wmax[kRankWords / 32];
   __shared__ uint32_t s_dpos0;
@@ -1008,7 +1013,7 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
   const uint32_t tile = blockIdx.x;
   const uint32_t w = tile * kRankWords + tid;
   const uint32_t t0 = tile * (uint32_t)kRankBytes;
-  const uint32_t S = w < nwords ? s_bits[w] : 0, E = w < nwords ? e_bits[w] : 0, D = w < nwords ? ds_bits[w] : 0;
+  const uint32_t S = w < nwords ? __ldg(s_bits + w) : 0, E = w < nwords ? __ldg(e_bits + w) : 0, D = w < nwords ? __ldg(ds_bits + w) : 0;
   if (tid == 0) {
     // last document start <= t0, and first document index with doc_off >= t0
     uint64_t lo = 0, hi = ndocs + 1;  // upper_bound(doc_off32, t0)
@@ -1026,9 +1031,9 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
     }
     s_dlo = lo2;
   }
-  // exclusive prefix of popc(S), popc(E) and running "last doc start" over the tile's 128 words
-  uint32_t cs = __popc(S), ce = __popc(E);
-  int32_t ld = D ? (int32_t)(tid * 32 + 31 - __clz(D)) : -1;  // tile-local position of the word's last doc start
+  // exclusive prefix of popc(S), popc(E) and running "last doc start" over the tile's words
+  const uint32_t cs = __popc(S), ce = __popc(E);
+  const int32_t ld = D ? (int32_t)(tid * 32 + 31 - __clz(D)) : -1;  // tile-local position of the word's last doc start
   uint32_t is = cs, ie = ce;
   int32_t im = ld;
 #pragma unroll
@@ -1047,43 +1052,63 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
     wmax[warp] = im;
   }
   __syncthreads();
-  uint32_t os = 0, oe = 0;
-  int32_t om = -1;
-  for (int j = 0; j < warp; j++) {
-    os += wsum[0][j];
-    oe += wsum[1][j];
-    om = max(om, wmax[j]);
+  if (warp == 0) {  // exclusive prefix over the 32 warps
+    uint32_t a = wsum[0][lane], b = wsum[1][lane];
+    int32_t c = wmax[lane];
+    uint32_t ia = a, ib = b;
+    int32_t ic = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t x = __shfl_up_sync(FULL, ia, o), y = __shfl_up_sync(FULL, ib, o);
+      int32_t z = __shfl_up_sync(FULL, ic, o);
+      if (lane >= o) {
+        ia += x;
+        ib += y;
+        ic = max(ic, z);
+      }
+    }
+    int32_t pc = __shfl_up_sync(FULL, ic, 1);
+    wsum[0][lane] = ia - a;
+    wsum[1][lane] = ib - b;
+    wmax[lane] = lane ? pc : -1;
   }
-  const uint32_t ps = tile_base[2 * tile] + os + is - cs, pe = tile_base[2 * tile + 1] + oe + ie - ce;
+  __syncthreads();
+  const uint32_t ls = wsum[0][warp] + is - cs, le = wsum[1][warp] + ie - ce;  // tile-local rank of this word's first start / end
+  const uint32_t base_s = tile_base[2 * tile], base_e = tile_base[2 * tile + 1];
   // last doc start strictly before this word (tile-local), or -1
   int32_t prev_ld = __shfl_up_sync(FULL, im, 1);
   if (lane == 0) prev_ld = -1;
-  prev_ld = max(prev_ld, om);
+  prev_ld = max(prev_ld, wmax[warp]);
   sS[tid] = S;
-  sPS[tid] = ps;
-  sPE[tid] = pe;
-  __syncthreads();
+  sPS[tid] = base_s + ls;
   const uint32_t dpos0 = s_dpos0;
-  uint32_t m = S;
-  while (m) {
-    uint32_t b = __ffs(m) - 1;
-    m &= m - 1;
-    uint32_t rank = ps + __popc(S & ((1u << b) - 1u));
-    uint32_t dm = D & ((b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u));
-    uint32_t dpos = dm ? t0 + tid * 32 + (31 - __clz(dm)) : (prev_ld >= 0 ? t0 + (uint32_t)prev_ld : dpos0);
-    if (rank < cap) out_start[rank] = t0 + tid * 32 + b - dpos;
-  }
-  m = E;
-  while (m) {
-    uint32_t b = __ffs(m) - 1;
-    m &= m - 1;
-    uint32_t rank = pe + __popc(E & ((1u << b) - 1u));
-    uint32_t dm = D & ((b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u));
-    uint32_t dpos = dm ? t0 + tid * 32 + (31 - __clz(dm)) : (prev_ld >= 0 ? t0 + (uint32_t)prev_ld : dpos0);
-    if (rank < cap) out_end[rank] = t0 + tid * 32 + b + 1 - dpos;
+  const uint32_t wpos = t0 + tid * 32;
+  // every thread writes the tokens of its word at their ranks (consecutive across the warp: L2 merges the sectors)
+  {
+    uint32_t m = S;
+    uint64_t r = (uint64_t)base_s + ls;
+    while (m) {
+      const uint32_t b = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t dm = D & ((b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u));
+      const uint32_t dpos = dm ? wpos + (31 - __clz(dm)) : (prev_ld >= 0 ? t0 + (uint32_t)prev_ld : dpos0);
+      if (r < cap) out_start[r] = wpos + b - dpos;
+      r++;
+    }
+    m = E;
+    r = (uint64_t)base_e + le;
+    while (m) {
+      const uint32_t b = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t dm = D & ((b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u));
+      const uint32_t dpos = dm ? wpos + (31 - __clz(dm)) : (prev_ld >= 0 ? t0 + (uint32_t)prev_ld : dpos0);
+      if (r < cap) out_end[r] = wpos + b + 1u - dpos;
+      r++;
+    }
   }
   // doc_tok_off for the documents that start inside this tile
   if (doc_tok) {
+    __syncthreads();
     const uint32_t t1 = min(n, t0 + (uint32_t)kRankBytes);
     for (uint64_t d = s_dlo + tid; d <= ndocs; d += kRankWords) {
       uint32_t p = doc_off32[d];
@@ -1095,7 +1120,7 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
 }
 
 // ------------------------------------------------------------------------------------------
-// Helpers around the fused fast path (jb_fused.cu)
+// Helpers around the streaming fast path (jb_stream.cu)
 // ------------------------------------------------------------------------------------------
 // gated non-Han tokens whose block left the tile: keep them iff the scan found an alnum on an open side
 __global__ void k_resolve_deferred(const uint4* __restrict__ deferred, const uint32_t* __restrict__ counters, uint32_t cap,

@@ -14,8 +14,8 @@ constexpr int kTileBytes = 3 * kTileSlots;
 constexpr int kHaloL = 16;
 constexpr int kHaloR = 144;  // >= longest Han key (90 B) + one rune + slack
 constexpr int kRegion = kHaloL + kTileBytes + kHaloR;
-// Token ranking tiles: 4096 bytes = 128 bitmap words
-constexpr int kRankWords = 128;
+// Token ranking tiles: 32 KiB of text = 1024 bitmap words
+constexpr int kRankWords = 1024;
 constexpr int kRankBytes = kRankWords * 32;
 
 enum Counter {

@@ -33,6 +33,7 @@ __device__ __forceinline__ bool s_is_alnum(uint32_t c) { return (c - '0' < 10u) 
 // unicode.IsSpace (T:302)
 __device__ __forceinline__ bool s_is_space(uint32_t cp) {
   if (cp <= 0xFF) return (cp - 9u < 5u) || cp == 0x20 || cp == 0x85 || cp == 0xA0;
+  if (cp > 0x3000u || cp < 0x1680u) return false;
   return cp == 0x1680 || (cp - 0x2000u <= 0xAu) || cp == 0x2028 || cp == 0x2029 || cp == 0x202F || cp == 0x205F || cp == 0x3000;
 }
 __device__ __forceinline__ bool s_is_han(uint32_t cp, const JbTables& T) {
@@ -714,17 +715,43 @@ struct BitAcc2 {  // token bits of one lane, flushed one 32-byte word at a time 
     }
     m |= 1u << (p & 31);
   }
+  __device__ __forceinline__ void set_word(uint32_t pw, uint32_t x) {
+    if (!x) return;
+    if (pw != w) {
+      if (m) atomicOr(&bits[w], m);
+      w = pw;
+      m = 0;
+    }
+    m |= x;
+  }
+  // bit j of x -> position p + j (x spans at most 48 bits)
+  __device__ __forceinline__ void set_span(uint32_t p, unsigned long long x) {
+    const uint32_t sh = p & 31u, pw = p >> 5;
+    const unsigned long long lo = x << sh;
+    set_word(pw, (uint32_t)lo);
+    set_word(pw + 1u, (uint32_t)(lo >> 32));
+    if (sh > 16u) set_word(pw + 2u, (uint32_t)(x >> (64u - sh)));
+  }
   __device__ __forceinline__ void flush() {
     if (m) atomicOr(&bits[w], m);
     m = 0;
     w = 0xFFFFFFFFu;
   }
 };
+// bit j of x (j < 16) -> bit 3j
+__device__ __forceinline__ unsigned long long spread3(uint32_t x16) {
+  unsigned long long x = x16 & 0xFFFFu;
+  x = (x | (x << 16)) & 0x0000FF0000FFull;
+  x = (x | (x << 8)) & 0x00F00F00F00Full;
+  x = (x | (x << 4)) & 0x0C30C30C30C3ull;
+  x = (x | (x << 2)) & 0x249249249249ull;
+  return x;
+}
 
 template <bool HMM, int PB>
 __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const EmitArgs A) {
   constexpr uint32_t PPW = 32 / PB, PMASK = (1u << PB) - 1u;
-  constexpr uint32_t kRegRun = 16;  // back-pointers of runs up to this length stay in registers
+  constexpr uint32_t kRegRun = 32;  // the four best paths of runs up to this length are carried in registers
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   if (A.counters[C_FLAGS] & 1u) return;
@@ -742,7 +769,9 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   uint32_t pw = 0, pt = 0xFFFFFFFFu;
   uint32_t run_n = 0, run_s = 0;
   double V[4] = {0.0, 0.0, 0.0, 0.0};
-  unsigned long long bplo = 0, bphi = 0;  // the last 16 back-pointer codes, newest in the low byte of bplo
+  // viterbi's fullPath (T:715-716) in bit form: per state, which runes of its best path are E or S (token ends),
+  // and the path's length (a route with from == "" restarts it)
+  uint32_t pm[4] = {0, 0, 0, 0}, plens = 0;
   for (;;) {
     // ---- refill idle lanes from the warp's queue of block indexes ----
     const uint32_t nm = __ballot_sync(FULL, !active);
@@ -794,9 +823,12 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           run_s = k;
 #pragma unroll
           for (int s = 0; s < 4; s++) V[s] = T.start[s] + em[s];
+          pm[0] = pm[1] = 0;
+          pm[2] = pm[3] = 1u;
+          plens = 0x01010101u;
         } else {
           double W[4];
-          uint32_t code = 0;
+          uint32_t code = 0, npm[4], nlens = 0;
 #pragma unroll
           for (int s = 0; s < 4; s++) {  // stateTransitionRoute (T:736-756): strict > from minFloat, list order
             const int pa = (s == 0 || s == 3) ? 2 : 0, pb = (s == 0 || s == 3) ? 3 : 1;
@@ -813,19 +845,19 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
             }
             W[s] = best + em[s];
             code |= from << (2 * s);
+            // fullPath[s] = fullPath[route.from] + [s]; fullPath[""] is nil (T:715-716)
+            const uint32_t m0 = from == 0 ? 0u : (from == 1 ? pm[pa] : pm[pb]);
+            const uint32_t l0 = from == 0 ? 0u : ((plens >> (8 * (from == 1 ? pa : pb))) & 0xFFu);
+            npm[s] = m0 | ((s >= 2 && run_n < 32u) ? (1u << run_n) : 0u);
+            nlens |= min(l0 + 1u, 255u) << (8 * s);
           }
 #pragma unroll
-          for (int s = 0; s < 4; s++) V[s] = W[s];
-          bphi = (bphi << 8) | (bplo >> 56);
-          bplo = (bplo << 8) | code;
-          if (run_n >= kRegRun - 1) {  // long run: the codes also go to HBM
-            if (run_n == kRegRun - 1)
-              for (uint32_t t = 1; t < kRegRun - 1; t++) {  // codes of steps 1..14 so far (step t sits kRegRun-1-t bytes back)
-                const uint32_t back = kRegRun - 1 - t;
-                A.bp[i0 + run_s + t] = (uint8_t)(back < 8 ? (bplo >> (8 * back)) : (bphi >> (8 * (back - 8))));
-              }
-            A.bp[pi] = (uint8_t)code;
+          for (int s = 0; s < 4; s++) {
+            V[s] = W[s];
+            pm[s] = npm[s];
           }
+          plens = nlens;
+          A.bp[pi] = (uint8_t)code;  // only read back for runs longer than the register window
         }
         run_n++;
       }
@@ -834,27 +866,19 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           sa.set(P0 + 3u * run_s);
           ea.set(P0 + 3u * run_s + 2);
         } else if (run_n <= kRegRun) {
-          int st2 = V[2] > V[3] ? 2 : 3;
-          uint32_t es = 0, plen = 0;
-          int j = (int)run_n - 1;
-          for (;;) {  // back-trace; stops early where route.from == "" (T:715-716)
-            es |= (st2 >= 2 ? 1u : 0u) << j;
-            plen++;
-            if (j == 0) break;
-            const uint32_t back = run_n - 1 - (uint32_t)j;
-            const uint32_t code = (uint32_t)(back < 8 ? (bplo >> (8 * back)) : (bphi >> (8 * (back - 8)))) & 0xFFu;
-            const int c = (code >> (2 * st2)) & 3;
-            if (c == 0) break;
-            st2 = (st2 == 0 || st2 == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
-            j--;
-          }
+          const int sf = V[2] > V[3] ? 2 : 3;  // T:723-729
+          const uint32_t plen = (plens >> (8 * sf)) & 0xFFu;
           // path[j] applies to rune j (T:277-283): a short path drops the run's tail
-          es >>= run_n - plen;
-          const uint32_t starts = (es << 1) | 1u;
-          for (uint32_t j2 = 0; j2 < plen; j2++) {
-            const uint32_t qq = P0 + 3u * (run_s + j2);
-            if ((starts >> j2) & 1) sa.set(qq);
-            if ((es >> j2) & 1) ea.set(qq + 2);
+          uint32_t es = (sf == 2 ? pm[2] : pm[3]) >> (run_n - plen);
+          const uint32_t lm = plen >= 32u ? FULL : ((1u << plen) - 1u);
+          es &= lm;
+          const uint32_t starts = ((es << 1) | 1u) & lm;
+          const uint32_t q0 = P0 + 3u * run_s;
+          sa.set_span(q0, spread3(starts));  // rune j starts at q0 + 3j ...
+          ea.set_span(q0 + 2u, spread3(es));  // ... and ends at q0 + 3j + 2
+          if (plen > 16u) {
+            sa.set_span(q0 + 48u, spread3(starts >> 16));
+            ea.set_span(q0 + 50u, spread3(es >> 16));
           }
         } else {
           int st2 = V[2] > V[3] ? 2 : 3;

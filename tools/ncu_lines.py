@@ -21,12 +21,12 @@ for l in sass:
 raw = subprocess.run(f"ncu -i {rep} --page source --csv", shell=True, capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.split('\n')))
 hdr = rows[1]
-ia, it, isamp, itag, isw = (hdr.index(x) for x in ('Instructions Executed', 'Thread Instructions Executed', '# Samples', 'L1 Tag Requests Global', 'L1 Wavefronts Shared'))
+ia, it, isamp, itag, isw = (hdr.index(x) if x in hdr else -1 for x in ('Instructions Executed', 'Thread Instructions Executed', '# Samples', 'L1 Tag Requests Global', 'L1 Wavefronts Shared'))
 data = [r for r in rows[2:] if len(r) > ia]
 agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])
 for i in range(min(len(seq), len(data))):
     a = agg[seq[i]]
-    for j, c in enumerate((ia, it, isamp, itag, isw)): a[j] += int(data[i][c] or 0)
+    for j, c in enumerate((ia, it, isamp, itag, isw)): a[j] += int(data[i][c] or 0) if c >= 0 else 0
 tot = [sum(v[j] for v in agg.values()) for j in range(5)]
 print('sass', len(seq), 'rows', len(data), 'warp-inst %d thread-inst %d (avg %.1f) samples %d L1tags %d smem-wf %d' % (tot[0], tot[1], tot[1] / max(1, tot[0]), tot[2], tot[3], tot[4]))
 src = open(f'{root}/jieba_go_b200/csrc/{srcfile}').read().split('\n')
