@@ -203,7 +203,7 @@ def main():
 
     sd = synth.make_dictionary(n_words=args.dict_words, seed=synth.SEED_BASE)
     emit = synth.make_emit(sd)
-    tk = Tokenizer.from_dict_text(sd.dict_txt(), 1, emit, device=local_rank)  # host batches: default 256 MiB sub-batches, pipelined
+    tk = Tokenizer.from_dict_text(sd.dict_txt(), 1, emit, device=local_rank)  # host batches: default 128 MiB sub-batches, three in flight
     L = _capi.lib()
     # each rank cuts its own shard (documents are independent; no collective on the data path)
     text, doc_off = synth.make_corpus(sd, cfg["kind"], args.bytes, synth.SEED_BASE + args.config + 1000 * rank, device=dev)

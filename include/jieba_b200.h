@@ -90,7 +90,7 @@ typedef struct {
 typedef struct {
   int device;               /* CUDA device ordinal; -1 = current device */
   int unicode_version;      /* 13 (Go 1.18-1.20) or 15 (Go >= 1.21; default when 0) for \p{Han}, T:21 */
-  uint64_t max_batch_bytes; /* device-side batch size for jb_cut_batch; 0 = default (256 MiB) */
+  uint64_t max_batch_bytes; /* device-side batch size for jb_cut_batch; 0 = default (128 MiB) */
 } jb_options;
 
 int jb_version(void);

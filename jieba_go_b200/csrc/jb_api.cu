@@ -48,7 +48,7 @@ struct jb_tokenizer {
   std::vector<void*> dev_allocs;
   void* table_base = nullptr;
   size_t table_bytes = 0;
-  uint64_t max_batch = 256ull << 20;
+  uint64_t max_batch = 128ull << 20;
   double w_per_slot = 3.0;
   int force_general = 0;  // 1: skip the streaming fast path (tests / debugging)
   std::mutex mu;
@@ -423,8 +423,8 @@ static WsSlot* take_slot(jb_tokenizer* tk) {
 }
 
 // Batched Cut over host memory.  Sub-batches of whole documents (<= max_batch bytes) flow through a
-// two-deep pipeline on two streams / workspaces: the H2D copy of batch i+1 and the D2H copy of batch i-1
-// overlap the kernels of batch i (separate copy engines).
+// pipeline of kPipeSlots streams / workspaces: the H2D copies of the next batches and the D2H copy of the
+// previous one overlap the kernels of batch i (separate copy engines).
 int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm, jb_result** out) {
   if (!tk || !out || !doc_off || (ndocs && doc_off[ndocs] > doc_off[0] && !text)) return fail(JB_EINVAL, "null argument");
   for (uint64_t d = 0; d < ndocs; d++) {
@@ -445,7 +445,9 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     chunks.push_back(Chunk{d0, d1, doc_off[d1] - doc_off[d0], 0, 0});
     d0 = d1;
   }
-  WsSlot* slots[2] = {take_slot(tk), chunks.size() > 1 ? take_slot(tk) : nullptr};
+  constexpr size_t kPipeSlots = 3;
+  WsSlot* slots[kPipeSlots] = {};
+  for (size_t i = 0; i < kPipeSlots && i < std::max<size_t>(chunks.size(), 1); i++) slots[i] = take_slot(tk);
   jb_result* res = new jb_result();
   res->ndocs = ndocs;
   auto done = [&](int code) {
@@ -463,7 +465,8 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     *out = res;
     return (int)JB_OK;
   };
-  if (!slots[0] || (chunks.size() > 1 && !slots[1])) return done(fail(JB_ECUDA, "stream / event creation failed"));
+  for (size_t i = 0; i < kPipeSlots && i < std::max<size_t>(chunks.size(), 1); i++)
+    if (!slots[i]) return done(fail(JB_ECUDA, "stream / event creation failed"));
   res->doc_tok = (uint64_t*)pin_alloc((ndocs + 1) * 8, &res->doc_bytes);
   if (!res->doc_tok) return done(fail(JB_ENOMEM, "pinned host allocation failed"));
   res->doc_tok[0] = 0;
@@ -475,7 +478,7 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
   // stage A: copy in, run the whole pipeline (scatter into the slot's device buffers), copy the count out
   auto enqueue = [&](size_t ci) -> int {
     Chunk& c = chunks[ci];
-    WsSlot* sl = slots[ci & 1];
+    WsSlot* sl = slots[ci % kPipeSlots];
     cudaStream_t st = sl->stream;
     int r = workspace_reserve(sl->ws, c.nb, c.d1 - c.d0, wps, true);
     if (r != JB_OK) return fail(r, "device workspace allocation failed");
@@ -503,17 +506,24 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
   };
 
   uint64_t base = 0;
-  if (!chunks.empty()) {
-    rc = enqueue(0);
-    if (rc != JB_OK) return done(rc);
-  }
+  size_t next_enq = 0;
   for (size_t ci = 0; ci < chunks.size(); ci++) {
-    if (ci + 1 < chunks.size()) {
-      rc = enqueue(ci + 1);
+    // keep the next batches enqueued ahead; a slot is reused by batch j + kPipeSlots: its copies must be done
+    // before that batch overwrites the buffers
+    while (next_enq < chunks.size() && next_enq < ci + kPipeSlots) {
+      if (next_enq >= kPipeSlots) {
+        Chunk& pc = chunks[next_enq - kPipeSlots];
+        cudaError_t se = cudaStreamSynchronize(slots[next_enq % kPipeSlots]->stream);
+        if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("copy failed: ") + cudaGetErrorString(se)));
+        // (doc_tok of that batch is final on the host now: make it absolute)
+        for (uint64_t d = pc.d0; d < pc.d1; d++) res->doc_tok[d] += pc.base;
+        pc.base = 0;
+      }
+      rc = enqueue(next_enq++);
       if (rc != JB_OK) return done(rc);
     }
     Chunk& c = chunks[ci];
-    WsSlot* sl = slots[ci & 1];
+    WsSlot* sl = slots[ci % kPipeSlots];
     cudaStream_t st = sl->stream;
     Workspace& ws = sl->ws;
     for (;;) {
@@ -558,14 +568,6 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     CUDA_TRY(cudaMemcpyAsync(res->doc_tok + c.d0, ws.out_doc_tok, (c.d1 - c.d0) * 8, cudaMemcpyDeviceToHost, st));
     base += nt;
     res->n_tokens = base;
-    // the slot is reused by batch ci+2: its copies must be done before that batch overwrites the buffers
-    if (ci + 2 < chunks.size()) {
-      cudaError_t se = cudaStreamSynchronize(st);
-      if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("copy failed: ") + cudaGetErrorString(se)));
-      // (doc_tok of this batch is final on the host now: make it absolute)
-      for (uint64_t d = c.d0; d < c.d1; d++) res->doc_tok[d] += c.base;
-      c.base = 0;
-    }
   }
   for (WsSlot* sl : slots)
     if (sl) {
