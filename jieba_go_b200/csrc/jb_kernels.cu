@@ -15,6 +15,7 @@
 #include "jb_stream.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1213,7 +1214,7 @@ static bool dalloc(T*& p, uint64_t count) {
 
 void workspace_free(Workspace& ws) {
   void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.rec, ws.gend, ws.wbuf, ws.ends,
-                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.deferred, ws.hs_bits, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
+                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.deferred, ws.tile_last_hs, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1238,7 +1239,7 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ok = ok && dalloc(ws.tile_sum, ntiles + 8) && dalloc(ws.tile_ctx, ntiles + 8);
     ws.deferred_cap = (uint32_t)(cap / 64 + 4096);
     ok = ok && dalloc(ws.deferred, (uint64_t)ws.deferred_cap);
-    ok = ok && dalloc(ws.hs_bits, nwords) && dalloc(ws.path, cap / 12 + 64) && dalloc(ws.bp, cap / 3 + 64);
+    ok = ok && dalloc(ws.tile_last_hs, cap / 8128 + 8) && dalloc(ws.path, cap / 12 + 64) && dalloc(ws.bp, cap / 3 + 64);
     ws.blocks_cap = (uint32_t)std::min<uint64_t>(ntiles * kTileSlots + 8, 0xFFFFFFF0ull);
     ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8));
     if (!ws.counters) ok = ok && dalloc(ws.counters, (uint64_t)C_NUM);
@@ -1393,7 +1394,7 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       sc.ds_bits = ws.ds_bits;
       sc.s_bits = ws.s_bits;
       sc.e_bits = ws.e_bits;
-      sc.hs_bits = ws.hs_bits;
+      sc.tile_last_hs = ws.tile_last_hs;
       sc.tile_sum = ws.tile_sum;
       sc.counters = ws.counters;
       sc.deferred = ws.deferred;
@@ -1405,11 +1406,12 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       PROF(2);
       RouteArgs ra;
       ra.text = d_text;
-      ra.hs_bits = ws.hs_bits;
+      ra.tile_last_hs = ws.tile_last_hs;
       ra.blocks = ws.ends;
       ra.blocks_cap = ws.blocks_cap;
       ra.counters = ws.counters;
       ra.path = ws.path;
+      ra.min_chunk = 16;  // measured on 10k-rune blocks: fuller warps beat more warps (instruction issue is per warp)
       launch_route(T, ra, g_num_sms, st);
       g_launches.fetch_add(1);
       PROF(3);
@@ -1422,6 +1424,7 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       ea.bp = ws.bp;
       ea.s_bits = ws.s_bits;
       ea.e_bits = ws.e_bits;
+      ea.min_chunk = 1;
       launch_emit(T, ea, use_hmm, g_num_sms, st);
       g_launches.fetch_add(1);
       JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, nt1, ws.counters, 0);

@@ -66,7 +66,7 @@ struct Workspace {
   uint8_t* tile_ctx = nullptr;   // per split tile: bit0 fwd, bit1 bwd
   uint4* deferred = nullptr;
   uint32_t deferred_cap = 0;
-  uint32_t* hs_bits = nullptr;   // Han-block start bitmap (k_scan -> k_route)
+  uint32_t* tile_last_hs = nullptr;  // per k_scan tile: last Han-block start (k_scan -> k_route)
   uint32_t* path = nullptr;      // chosen word length - 1 per rune (k_route -> k_emit)
   uint8_t* bp = nullptr;         // Viterbi back-pointers per rune (k_emit)
   uint32_t blocks_cap = 0;       // entries of `ends` usable as the stream path's block list

@@ -27,6 +27,7 @@ struct ScanSmem {
   uint32_t S[kScThreads + 1], E[kScThreads + 1];
   uint32_t wsum[kScThreads / 32];
   uint32_t ends_base;
+  int last_hs;  // tile-local byte of the last Han-block start in the tile, -1: none
 };
 
 __device__ __forceinline__ bool s_is_alnum(uint32_t c) { return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u); }
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(kScThreads, 4) k_scan(const JbTables T, const 
     S.S[tid] = 0;
     S.E[tid] = 0;
     if (tid == 0) {
+      S.last_hs = -1;
       S.OTE[kScThreads] = 0;
       S.S[kScThreads] = 0;
       S.E[kScThreads] = 0;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kScThreads, 4) k_scan(const JbTables T, const 
     S.S[wj] = ALN & (D | ~prevAl);  // an alnum run is one token (T:298-299)
     S.E[wj] = ALN & ~nextAl;
     S.HS[wj] = HS;
-    if (Pw < (int64_t)n) A.hs_bits[(uint32_t)(Pw >> 5)] = HS;
+    if (HS) atomicMax(&S.last_hs, (wj - 1) * 32 + 31 - __clz(HS));
   } else {
     S.BND[wj] = 0;
     S.HS[wj] = 0;
@@ -405,7 +407,10 @@ __global__ void __launch_bounds__(kScThreads, 4) k_scan(const JbTables T, const 
     }
     pre = __any_sync(FULL, pre);
     post = __any_sync(FULL, post);
-    if (lane == 0) A.tile_sum[tile] = (uint8_t)((lastw >= 0 ? 1 : 0) | (pre ? 2 : 0) | (post ? 4 : 0));
+    if (lane == 0) {
+      A.tile_sum[tile] = (uint8_t)((lastw >= 0 ? 1 : 0) | (pre ? 2 : 0) | (post ? 4 : 0));
+      A.tile_last_hs[tile] = S.last_hs >= 0 ? t0 + (uint32_t)S.last_hs : 0xFFFFFFFFu;
+    }
   }
   __syncthreads();
   // ---- publish the non-Han token bits (a rune may end in the next tile's first word) --------------
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   if (A.counters[C_FLAGS] & 1u) return;  // the general pipeline redoes this batch
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kRtThreads / 32);
-  const uint32_t chunk = min((uint32_t)kRtQueue, max(1u, (nblocks + nwarps - 1) / nwarps));
+  const uint32_t chunk = min((uint32_t)kRtQueue, max(A.min_chunk, (nblocks + nwarps - 1) / nwarps));
   // text is read through 8-byte aligned words: offsets are relative to the aligned base
   const uint32_t tmis = (uint32_t)(reinterpret_cast<uintptr_t>(A.text) & 7);
   const uint2* __restrict__ text8 = reinterpret_cast<const uint2*>(A.text - tmis);
@@ -512,6 +517,12 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
           const uint2 bd = A.blocks[bi];
           e3i = bd.x / 3u;
           nr = bd.y;
+          if (nr == 0) {  // the block began in an earlier k_scan tile: the nearest tile with a block start holds it
+            uint32_t t = bd.x / (uint32_t)kScTileBytes, sp;
+            do sp = __ldg(A.tile_last_hs + --t);
+            while (sp == 0xFFFFFFFFu);
+            nr = (bd.x - sp) / 3u + 1u;
+          }
           p = bd.x + tmis;
           kq = 0;
           wc = p >> 3;
@@ -656,12 +667,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
         accw = pwd;
       }
       acc |= (best_d - 1u) << ((idx % PPW) * PB);
-      bool start = kq + 1u == nr;
-      if (nr == 0) {  // the block began in another k_scan tile: its first rune is marked in the start bitmap
-        const uint32_t q = p - tmis;
-        start = (__ldg(A.hs_bits + (q >> 5)) >> (q & 31)) & 1;
-      }
-      if (start) {  // first rune of the block
+      if (kq + 1u == nr) {  // first rune of the block
         if (acc) atomicOr(&A.path[accw], acc);
         acc = 0;
         accw = 0xFFFFFFFFu;
@@ -758,7 +764,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   const uint32_t nblocks = min(A.counters[C_N_BLK], A.blocks_cap);
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kEmThreads / 32);
-  const uint32_t chunk = min(32u, max(1u, (nblocks + nwarps - 1) / nwarps));
+  const uint32_t chunk = min(32u, max(A.min_chunk, (nblocks + nwarps - 1) / nwarps));
   const uintptr_t tbase = reinterpret_cast<uintptr_t>(A.text);
   BitAcc2 sa, ea;
   sa.init(A.s_bits);

@@ -28,22 +28,23 @@ struct ScanArgs {
   const uint32_t* ds_bits;
   uint32_t* s_bits;
   uint32_t* e_bits;
-  uint32_t* hs_bits;      // bit at the lead byte of the first rune of every Han block (plain stores, every word)
+  uint32_t* tile_last_hs; // per tile: byte position of its last Han-block start, 0xFFFFFFFF if none
   uint8_t* tile_sum;
   uint32_t* counters;
   uint4* deferred;        // (byte pos, len, flags: 1 need fwd 2 need bwd, tile)
   uint32_t deferred_cap;
-  uint2* blocks;          // .x = lead byte of the LAST rune of a Han block (k_route rewrites the entry)
+  uint2* blocks;          // (lead byte of the LAST rune of a Han block, its runes or 0 = began in an earlier tile)
   uint32_t blocks_cap;
 };
 
 struct RouteArgs {
   const uint8_t* text;
-  const uint32_t* hs_bits;
-  uint2* blocks;          // in: .x = last rune; out: (lead byte of the first rune, runes)
+  const uint32_t* tile_last_hs;
+  uint2* blocks;          // in: (last rune, runes or 0 when the block began in an earlier tile); out: (lead byte of the first rune, runes)
   uint32_t blocks_cap;
   uint32_t* counters;
   uint32_t* path;         // chosen word length - 1 per rune, index = lead byte / 3
+  uint32_t min_chunk;     // blocks a warp takes from the queue at least (few long blocks: lanes per warp vs warps per SM)
 };
 
 struct EmitArgs {
@@ -55,6 +56,7 @@ struct EmitArgs {
   uint8_t* bp;            // Viterbi back-pointers / state flags per rune, index = lead byte / 3
   uint32_t* s_bits;
   uint32_t* e_bits;
+  uint32_t min_chunk;
 };
 
 int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st);
