@@ -447,7 +447,7 @@ constexpr int kRtQueue = 32;
 template <int RING, int PB>
 __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const RouteArgs A) {
   __shared__ double ring[RING][kRtThreads];
-  __shared__ uint32_t rr[RING][kRtThreads];
+  __shared__ uint16_t rr[RING][kRtThreads];  // (3-byte runes: BMP) -- shared memory not used here is L1 for the tables
   constexpr uint32_t M = RING - 1;
   constexpr uint32_t PPW = 32 / PB;  // path entries per word
   const int tid = threadIdx.x, lane = tid & 31;
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   const uint4* __restrict__ entries = reinterpret_cast<const uint4*>(T.entries);
   const uint32_t hmask = T.hash_mask;
   double* const sring = &ring[0][tid];   // this lane's ring cells: index * kRtThreads
-  uint32_t* const srr = &rr[0][tid];
+  uint16_t* const srr = &rr[0][tid];
   uint32_t qh = 0, qt = 0;
   bool exhausted = false, active = false;
   uint32_t bi = 0, p = 0, kq = 0, e3i = 0, nr = 0;  // block index, lead byte of the current rune (+ tmis), runes to its right, end / 3, runes (0: unknown)
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     const uint32_t x = __funnelshift_r(o & 4u ? w1 : w0, o & 4u ? wn : w1, (o & 3u) * 8u);
     const uint32_t r1 = r0;
     r0 = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
-    srr[(kq & M) * kRtThreads] = r0;
+    srr[(kq & M) * kRtThreads] = (uint16_t)r0;
     f = __ldg(first + r0);
     if (!first_rune) {  // (with one rune to the right the 3-rune slot is computed from a stale rune: loaded, never looked at)
       h2 = jb_hash_next(JB_PARENT_FIRST(r0), r1);
@@ -539,101 +539,71 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       qh = min(qt, qh + (uint32_t)__popc(nm));
       if (exhausted && __all_sync(FULL, !active)) break;
     }
-    double best_v, last_v, prev_v;
-    uint32_t best_d, last_d, L, parent, rl, slot, hs, maxlen;
-    bool more, home = false;  // home: the next probe looks at the home slot of its key
-    const bool chained = active && chain;
-    // ---- a position on a longer prefix or a hash collision: one more turn of the loop (T:473-482) on the entry in e2 ----
-    if (chained) {
-      best_v = __hiloint2double((int)e3.y, (int)e3.x);
-      last_v = __hiloint2double((int)e3.w, (int)e3.z);
-      prev_v = __hiloint2double((int)f.y, (int)f.x);
-      parent = f.z;
-      rl = f.w;
-      hs = h2;
-      slot = h3;
-      L = cs & 0x7Fu;
-      maxlen = (cs >> 8) & 0xFFu;
-      best_d = (cs >> 16) & 0xFFu;
-      last_d = cs >> 24;
-      const bool hit = e2.z == parent && JB_RB_RUNE(e2.w) == rl;
-      // linear probing goes on past a foreign entry (past the home slot only if a key was displaced from it);
-      // an empty slot ends the loop (T:476-478)
-      const bool foreign = !hit && e2.z != JB_PARENT_EMPTY && (!(cs & 0x80u) || (e2.w & JB_RB_CONT));
-      const double pw = __longlong_as_double(((long long)e2.y << 32) | (long long)e2.x);
-      L += hit ? 1u : 0u;
-      const uint32_t rn = srr[((kq - L) & M) * kRtThreads];
-      if (hit && jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481); maxIndexProba's loop body (T:568-572)
-        const double v = pw + ((L > kq) ? 0.0 : sring[((kq - L) & M) * kRtThreads]);
-        if (v >= prev_v) {
-          best_d = L;
-          best_v = v;
-        }
-        prev_v = v;
-        last_d = L;
-        last_v = v;
-      }
-      const bool deeper = hit && L < maxlen && (((e2.w >> 21) >> jb_bloom11(rn)) & 1);
-      if (deeper) {
-        parent = slot;
-        rl = rn;
-        hs = jb_hash_next(hs, rl);
-      }
-      slot = deeper ? (hs & hmask) : ((slot + 1) & hmask);
-      more = deeper || foreign;
-      home = deeper;
-    }
-    __syncwarp();
-    // ---- a fresh position, in straight-line predicated code: the first-rune entry (T:468-472) and the entries of
-    // the 2- and 3-rune prefixes are here; candidates in ascending length (T:515-529, 565-578) ----
-    if (active && !chained) {
-      const uint32_t k1 = ((kq - 1u) & M) * kRtThreads, k2 = ((kq - 2u) & M) * kRtThreads, k3 = ((kq - 3u) & M) * kRtThreads;
-      const double R1 = sring[k1], R2 = sring[k2], R3 = sring[k3];
-      const uint32_t r1 = srr[k1], r2 = srr[k2], r3 = srr[k3];
+    // ---- one straight-line, predicated section for every active lane.  A FRESH lane (it advanced last iteration)
+    // holds its first-rune entry (T:468-472) and the entries of its 2- and 3-rune prefixes; a CHAINED lane holds
+    // the next entry of its prefix chain in e2 and its selector state parked in f / e3 / h2 / h3 / cs.
+    // Candidates in ascending length: pieceFreq + nextBestPiece.proba (T:519-529) into maxIndexProba's running
+    // (prev, best) pair: each candidate is compared with the previous one, first with minFloat (T:565-578). ----
+    double best_v = 0.0, last_v = 0.0, prev_v = 0.0;
+    uint32_t best_d = 0, last_d = 0, L = 0, parent = 0, slot = 0, hs = 0, maxlen = 0;
+    bool more = false, home = false;  // home: the next probe looks at the home slot of its key
+    if (active) {
+      const bool chained = chain, fresh = !chain;
+      const uint32_t L0 = chained ? (cs & 0x7Fu) : 1u;  // runes of the prefix matched so far
+      maxlen = chained ? ((cs >> 8) & 0xFFu) : min(min((f.z >> 8) & 0xFFu, 31u), kq + 1u);
+      const uint32_t parA = chained ? f.z : JB_PARENT_FIRST(r0);
+      const uint32_t slotA = chained ? h3 : (h2 & hmask), slot3 = h3 & hmask;
+      const bool homeA = fresh || (cs & 0x80u);
+      const uint32_t kA = ((kq - L0) & M) * kRtThreads, kB = ((kq - L0 - 1u) & M) * kRtThreads, kC = ((kq - 3u) & M) * kRtThreads;
+      const double RA = sring[kA], RB = sring[kB], RC = sring[kC];
+      const uint32_t rA = srr[kA], rB = srr[kB], rC = srr[kC];  // the runes after a prefix of L0, L0 + 1, 3 runes
       const double wt1 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
-      const double wt2 = __longlong_as_double(((long long)e2.y << 32) | (long long)e2.x);
+      const double wtA = __longlong_as_double(((long long)e2.y << 32) | (long long)e2.x);
       const double wt3 = __longlong_as_double(((long long)e3.y << 32) | (long long)e3.x);
-      maxlen = min(min((f.z >> 8) & 0xFFu, 31u), kq + 1u);
-      const uint32_t par2 = JB_PARENT_FIRST(r0), slot2 = h2 & hmask, slot3 = h3 & hmask;
-      // which entries buildDag looks at, and what it finds
-      const bool g2 = !(f.z & JB_FIRST_GATE) && maxlen > 1u && ((f.w >> jb_bloom_bit(r1)) & 1u);
-      const bool m2 = g2 && e2.z == par2 && JB_RB_RUNE(e2.w) == r1;
-      const bool x2 = g2 && !m2 && e2.z != JB_PARENT_EMPTY && (e2.w & JB_RB_CONT);  // foreign entry in the home slot and a displaced key: linear probing
-      const bool g3 = m2 && maxlen > 2u && (((e2.w >> 21) >> jb_bloom11(r2)) & 1u);
-      const bool m3 = g3 && e3.z == slot2 && JB_RB_RUNE(e3.w) == r2;
-      const bool x3 = g3 && !m3 && e3.z != JB_PARENT_EMPTY && (e3.w & JB_RB_CONT);
-      const bool g4 = m3 && maxlen > 3u && (((e3.w >> 21) >> jb_bloom11(r3)) & 1u);
-      // candidates: pieceFreq + nextBestPiece.proba ({j, 0.0} at the end of the block, T:522-529)
-      const double v1 = wt1 + (kq >= 1u ? R1 : 0.0);
-      const double v2 = wt2 + (kq >= 2u ? R2 : 0.0);
-      const double v3 = wt3 + (kq >= 3u ? R3 : 0.0);
-      const bool c2 = m2 && jb_w_positive(wt2), c3 = m3 && jb_w_positive(wt3);  // val > 0 -> edge (T:479-481)
-      // maxIndexProba (T:565-578): each candidate is compared with the previous one, first with minFloat
-      best_d = (v1 >= JB_MINF) ? 1u : 0u;
-      best_v = v1;
-      prev_v = v1;
-      last_d = 1u;
-      last_v = v1;
-      const bool b2 = c2 && v2 >= prev_v;
-      best_d = b2 ? 2u : best_d;
-      best_v = b2 ? v2 : best_v;
-      prev_v = c2 ? v2 : prev_v;
-      last_d = c2 ? 2u : last_d;
-      last_v = c2 ? v2 : last_v;
-      const bool b3 = c3 && v3 >= prev_v;
-      best_d = b3 ? 3u : best_d;
-      best_v = b3 ? v3 : best_v;
-      prev_v = c3 ? v3 : prev_v;
-      last_d = c3 ? 3u : last_d;
-      last_v = c3 ? v3 : last_v;
-      // anything beyond goes on in later iterations
-      more = x2 || x3 || g4;
-      home = g4;
-      L = m3 ? 3u : (m2 ? 2u : 1u);
-      parent = g4 ? slot3 : (x3 ? slot2 : par2);
-      rl = g4 ? r3 : (x3 ? r2 : r1);
-      hs = g4 ? jb_hash_next(h3, r3) : (x3 ? h3 : h2);
-      slot = g4 ? (hs & hmask) : (((x3 ? slot3 : slot2) + 1u) & hmask);
+      // candidate (i, i+1) of a fresh lane, or the parked selector state
+      const double v1 = wt1 + (kq >= 1u ? RA : 0.0);  // {j, 0.0} at the end of the block (T:522)
+      best_v = chained ? __hiloint2double((int)e3.y, (int)e3.x) : v1;
+      last_v = chained ? __hiloint2double((int)e3.w, (int)e3.z) : v1;
+      prev_v = chained ? wt1 : v1;
+      best_d = chained ? ((cs >> 16) & 0xFFu) : ((v1 >= JB_MINF) ? 1u : 0u);
+      last_d = chained ? (cs >> 24) : 1u;
+      // which entries buildDag looks at (T:469-482), and what it finds
+      const bool gA = chained || (!(f.z & JB_FIRST_GATE) && maxlen > 1u && ((f.w >> jb_bloom_bit(rA)) & 1u));
+      const bool mA = gA && e2.z == parA && JB_RB_RUNE(e2.w) == rA;
+      // a foreign entry: linear probing goes on (past the home slot only if a key was displaced from it); empty: break
+      const bool xA = gA && !mA && e2.z != JB_PARENT_EMPTY && (!homeA || (e2.w & JB_RB_CONT));
+      const uint32_t LA = L0 + 1u;
+      const bool cA = mA && jb_w_positive(wtA);  // val > 0 -> edge (T:479-481)
+      const double vA = wtA + (LA > kq ? 0.0 : RB);
+      const bool bA = cA && vA >= prev_v;
+      best_d = bA ? LA : best_d;
+      best_v = bA ? vA : best_v;
+      prev_v = cA ? vA : prev_v;
+      last_d = cA ? LA : last_d;
+      last_v = cA ? vA : last_v;
+      const bool contA = mA && LA < maxlen && (((e2.w >> 21) >> jb_bloom11(rB)) & 1u);  // some key extends the prefix by rB
+      // the 3-rune prefix of a fresh lane is here already
+      const bool gB = contA && fresh;
+      const bool mB = gB && e3.z == slotA && JB_RB_RUNE(e3.w) == rB;
+      const bool xB = gB && !mB && e3.z != JB_PARENT_EMPTY && (e3.w & JB_RB_CONT);
+      const bool cB = mB && jb_w_positive(wt3);
+      const double vB = wt3 + (kq >= 3u ? RC : 0.0);
+      const bool bB = cB && vB >= prev_v;
+      best_d = bB ? 3u : best_d;
+      best_v = bB ? vB : best_v;
+      prev_v = cB ? vB : prev_v;
+      last_d = cB ? 3u : last_d;
+      last_v = cB ? vB : last_v;
+      const bool contB = mB && maxlen > 3u && (((e3.w >> 21) >> jb_bloom11(rC)) & 1u);
+      // anything beyond goes on in later iterations, one dependent probe each
+      const bool deeperA = contA && chained;
+      more = xA || deeperA || xB || contB;
+      home = deeperA || contB;
+      L = mB ? 3u : (mA ? LA : L0);
+      parent = contB ? slot3 : ((deeperA || xB) ? slotA : parA);
+      const uint32_t hn = jb_hash_next(contB ? h3 : h2, contB ? rC : rB);
+      hs = home ? hn : (xB ? h3 : h2);
+      slot = home ? (hn & hmask) : (((xB ? slot3 : slotA) + 1u) & hmask);
     }
     __syncwarp();
     if (active && more) {  // park the selector state, issue the next probe
@@ -644,7 +614,6 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       f.x = (uint32_t)__double2loint(prev_v);
       f.y = (uint32_t)__double2hiint(prev_v);
       f.z = parent;
-      f.w = rl;
       h2 = hs;
       h3 = slot;
       cs = L | (home ? 0x80u : 0u) | (maxlen << 8) | (best_d << 16) | (last_d << 24);
