@@ -661,6 +661,10 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
 }
 
 int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st) {
+  // Shared memory that the 8 resident CTAs do not take is L1 for the dictionary tables, and the kernel is bound by
+  // the latency of its table loads: with 20.5 KB per CTA the driver's default carveout leaves ~84 KB of L1
+  // (6.4 ms/GB); with 24.5 KB per CTA (32-bit runes) it had to take the whole array (9.0 ms/GB).  Forcing other
+  // carveouts or fewer CTAs measured slower.
   const bool r16 = T.max_delta <= 16;
   const unsigned grid = (unsigned)num_sms * 8u;
   if (r16) k_route<16, 4><<<grid, kRtThreads, 0, st>>>(T, A);
