@@ -291,9 +291,18 @@ def main():
         A = nbytes + 8 * n_tok  # algorithmic bytes of one launch on this rank
         dom = max(kern_ms, key=lambda k: kern_ms[k])
         t_k = sum(kern_ms.values())
+        # DRAM traffic of the dominant kernel per launch: from the committed `ncu --set full` capture of the same
+        # workload (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), else null
+        traffic = None
+        try:
+            for rec in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))):
+                if rec["kernel"] == dom and rec["config"] == args.config and abs(rec["input_bytes"] - nbytes) <= 0.01 * nbytes:
+                    traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
+        except Exception:
+            pass
         roof = {
             "bound": "hbm", "kernel": dom, "achieved": A / (kern_ms[dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": A / (kern_ms[dom] * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "frac": A / (kern_ms[dom] * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": A,
             "pipeline_achieved": A / (t_k * 1e-3) / 1e9, "pipeline_frac": A / (t_k * 1e-3) / 1e9 / peak,
             "kernel_ms": {k: round(v, 4) for k, v in kern_ms.items()},

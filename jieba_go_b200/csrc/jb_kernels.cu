@@ -1000,6 +1000,28 @@ __global__ void __launch_bounds__(1024) k_rank_scan(uint32_t* __restrict__ cnt, 
   }
 }
 
+constexpr int kRankStage = 256;  // tokens a warp stages per pass
+// First index i in [0, cnt] with a[i] > key (strict) or a[i] >= key, a sorted: a 32-way search by one warp
+// (a one-thread binary search over the document offsets was the critical path of every rank tile).
+__device__ __forceinline__ uint64_t warp_first_true(const uint32_t* __restrict__ a, uint64_t cnt, uint32_t key, bool strict, int lane) {
+  uint64_t lo = 0, hi = cnt;  // every index < lo is false, index hi is true (or hi == cnt)
+  while (lo < hi) {
+    const uint64_t step = (hi - lo + 31) / 32;
+    const uint64_t q = lo + (uint64_t)(lane + 1) * step - 1;
+    bool pred = true;
+    if (q < hi) {
+      const uint32_t v = __ldg(a + q);
+      pred = strict ? v > key : v >= key;
+    }
+    const uint32_t bal = __ballot_sync(FULL, pred);
+    if (!bal) return hi;  // every probe below hi was false
+    const int f = __ffs(bal) - 1;
+    const uint64_t qf = lo + (uint64_t)(f + 1) * step - 1;
+    hi = min(hi, qf);
+    lo = lo + (uint64_t)f * step;
+  }
+  return lo;
+}
 __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __restrict__ s_bits, const uint32_t* __restrict__ e_bits,
                                                             const uint32_t* __restrict__ ds_bits, uint32_t nwords, uint32_t n,
                                                             const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ doc_off32,
@@ -1008,6 +1030,7 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
   __shared__ uint32_t sS[kRankWords], sPS[kRankWords];
   __shared__ uint32_t wsum[2][kRankWords / 32];
   __shared__ int32_t wmax[kRankWords / 32];
+  __shared__ uint32_t stage[kRankWords / 32][kRankStage];
   __shared__ uint32_t s_dpos0;
   __shared__ uint64_t s_dlo;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1015,22 +1038,13 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
   const uint32_t w = tile * kRankWords + tid;
   const uint32_t t0 = tile * (uint32_t)kRankBytes;
   const uint32_t S = w < nwords ? __ldg(s_bits + w) : 0, E = w < nwords ? __ldg(e_bits + w) : 0, D = w < nwords ? __ldg(ds_bits + w) : 0;
-  if (tid == 0) {
-    // last document start <= t0, and first document index with doc_off >= t0
-    uint64_t lo = 0, hi = ndocs + 1;  // upper_bound(doc_off32, t0)
-    while (lo < hi) {
-      uint64_t mid = (lo + hi) >> 1;
-      if (doc_off32[mid] <= t0) lo = mid + 1;
-      else hi = mid;
+  // last document start <= t0 (warp 0) and first document index with doc_off >= t0 (warp 1): 32-way searches
+  if (warp < 2) {
+    const uint64_t r = warp_first_true(doc_off32, ndocs + 1, t0, warp == 0, lane);
+    if (lane == 0) {
+      if (warp == 0) s_dpos0 = r ? doc_off32[r - 1] : 0;  // r = upper_bound(doc_off32, t0)
+      else s_dlo = r;                                      // r = lower_bound(doc_off32, t0)
     }
-    s_dpos0 = lo ? doc_off32[lo - 1] : 0;
-    uint64_t lo2 = 0, hi2 = lo;  // lower_bound(doc_off32, t0) is <= upper_bound
-    while (lo2 < hi2) {
-      uint64_t mid = (lo2 + hi2) >> 1;
-      if (doc_off32[mid] < t0) lo2 = mid + 1;
-      else hi2 = mid;
-    }
-    s_dlo = lo2;
   }
   // exclusive prefix of popc(S), popc(E) and running "last doc start" over the tile's words
   const uint32_t cs = __popc(S), ce = __popc(E);
@@ -1084,27 +1098,38 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
   sPS[tid] = base_s + ls;
   const uint32_t dpos0 = s_dpos0;
   const uint32_t wpos = t0 + tid * 32;
-  // every thread writes the tokens of its word at their ranks (consecutive across the warp: L2 merges the sectors)
+  // The tokens of a warp's 32 words have consecutive ranks: stage them in the warp's slice of shared memory in
+  // rank order and write them out 128 contiguous bytes per instruction (scattered 4-byte stores from the bit loops
+  // cost one L1 wavefront per token).
   {
-    uint32_t m = S;
-    uint64_t r = (uint64_t)base_s + ls;
-    while (m) {
-      const uint32_t b = __ffs(m) - 1;
-      m &= m - 1;
-      const uint32_t dm = D & ((b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u));
-      const uint32_t dpos = dm ? wpos + (31 - __clz(dm)) : (prev_ld >= 0 ? t0 + (uint32_t)prev_ld : dpos0);
-      if (r < cap) out_start[r] = wpos + b - dpos;
-      r++;
-    }
-    m = E;
-    r = (uint64_t)base_e + le;
-    while (m) {
-      const uint32_t b = __ffs(m) - 1;
-      m &= m - 1;
-      const uint32_t dm = D & ((b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u));
-      const uint32_t dpos = dm ? wpos + (31 - __clz(dm)) : (prev_ld >= 0 ? t0 + (uint32_t)prev_ld : dpos0);
-      if (r < cap) out_end[r] = wpos + b + 1u - dpos;
-      r++;
+    uint32_t* const wst = stage[warp];
+    const uint32_t wls = __shfl_sync(FULL, ls, 0), wle = __shfl_sync(FULL, le, 0);        // tile-local rank of the warp's first start / end
+    const uint32_t wts = __shfl_sync(FULL, is, 31), wte = __shfl_sync(FULL, ie, 31);      // tokens of the warp
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+      const uint32_t bits = which ? E : S, lr0 = (which ? le - wle : ls - wls), total = which ? wte : wts;
+      const uint64_t gbase = (uint64_t)(which ? base_e + wle : base_s + wls);
+      uint32_t* __restrict__ out = which ? out_end : out_start;
+      for (uint32_t c0 = 0; c0 < total; c0 += kRankStage) {
+        uint32_t m = bits, lr = lr0;
+        while (m) {
+          const uint32_t b = __ffs(m) - 1;
+          m &= m - 1;
+          if (lr - c0 < (uint32_t)kRankStage) {
+            const uint32_t dm = D & ((b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u));
+            const uint32_t dpos = dm ? wpos + (31 - __clz(dm)) : (prev_ld >= 0 ? t0 + (uint32_t)prev_ld : dpos0);
+            wst[lr - c0] = wpos + b + (uint32_t)which - dpos;
+          }
+          lr++;
+        }
+        __syncwarp();
+        const uint32_t cn = min((uint32_t)kRankStage, total - c0);
+        for (uint32_t i = lane; i < cn; i += 32) {
+          const uint64_t r = gbase + c0 + i;
+          if (r < cap) out[r] = wst[i];
+        }
+        __syncwarp();
+      }
     }
   }
   // doc_tok_off for the documents that start inside this tile
