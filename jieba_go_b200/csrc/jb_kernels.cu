@@ -66,7 +66,7 @@ __device__ __forceinline__ uint32_t d_slot(uint32_t p) { return (p + 2u) / 3u; }
 
 // ------------------------------------------------------------------------------------------
 __global__ void k_docstart(const uint64_t* __restrict__ doc_off, uint64_t ndocs, uint32_t n, uint32_t* __restrict__ doc_off32,
-                           uint32_t* __restrict__ ds_bits) {
+                           uint32_t* __restrict__ ds_bits, uint32_t* __restrict__ tile_first_doc) {
   uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (d > ndocs) return;
   uint64_t base = doc_off[0];
@@ -74,6 +74,14 @@ __global__ void k_docstart(const uint64_t* __restrict__ doc_off, uint64_t ndocs,
   uint32_t p = p64 > n ? n : (uint32_t)p64;
   doc_off32[d] = p;
   if (d < ndocs && p < n) atomicOr(&ds_bits[p >> 5], 1u << (p & 31));
+  // lower_bound(doc_off32, t * kRankBytes) for every rank tile t: document d answers for the tiles whose first byte
+  // lies in (doc_off[d-1], doc_off[d]]  (k_rank_scatter used to search for it, one thread per tile)
+  uint32_t t_lo = 0;
+  if (d) {
+    uint64_t q64 = doc_off[d - 1] - base;
+    t_lo = (q64 > n ? n : (uint32_t)q64) / (uint32_t)kRankBytes + 1u;
+  }
+  for (uint32_t t = t_lo; t <= p / (uint32_t)kRankBytes; t++) tile_first_doc[t] = (uint32_t)d;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1001,31 +1009,10 @@ __global__ void __launch_bounds__(1024) k_rank_scan(uint32_t* __restrict__ cnt, 
 }
 
 constexpr int kRankStage = 256;  // tokens a warp stages per pass
-// First index i in [0, cnt] with a[i] > key (strict) or a[i] >= key, a sorted: a 32-way search by one warp
-// (a one-thread binary search over the document offsets was the critical path of every rank tile).
-__device__ __forceinline__ uint64_t warp_first_true(const uint32_t* __restrict__ a, uint64_t cnt, uint32_t key, bool strict, int lane) {
-  uint64_t lo = 0, hi = cnt;  // every index < lo is false, index hi is true (or hi == cnt)
-  while (lo < hi) {
-    const uint64_t step = (hi - lo + 31) / 32;
-    const uint64_t q = lo + (uint64_t)(lane + 1) * step - 1;
-    bool pred = true;
-    if (q < hi) {
-      const uint32_t v = __ldg(a + q);
-      pred = strict ? v > key : v >= key;
-    }
-    const uint32_t bal = __ballot_sync(FULL, pred);
-    if (!bal) return hi;  // every probe below hi was false
-    const int f = __ffs(bal) - 1;
-    const uint64_t qf = lo + (uint64_t)(f + 1) * step - 1;
-    hi = min(hi, qf);
-    lo = lo + (uint64_t)f * step;
-  }
-  return lo;
-}
 __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __restrict__ s_bits, const uint32_t* __restrict__ e_bits,
                                                             const uint32_t* __restrict__ ds_bits, uint32_t nwords, uint32_t n,
                                                             const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ doc_off32,
-                                                            uint64_t ndocs, uint32_t* __restrict__ out_start, uint32_t* __restrict__ out_end,
+                                                            const uint32_t* __restrict__ tile_first_doc, uint64_t ndocs, uint32_t* __restrict__ out_start, uint32_t* __restrict__ out_end,
                                                             uint64_t cap, uint64_t* __restrict__ doc_tok, uint64_t tok_base) {
   __shared__ uint32_t sS[kRankWords], sPS[kRankWords];
   __shared__ uint32_t wsum[2][kRankWords / 32];
@@ -1038,13 +1025,12 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
   const uint32_t w = tile * kRankWords + tid;
   const uint32_t t0 = tile * (uint32_t)kRankBytes;
   const uint32_t S = w < nwords ? __ldg(s_bits + w) : 0, E = w < nwords ? __ldg(e_bits + w) : 0, D = w < nwords ? __ldg(ds_bits + w) : 0;
-  // last document start <= t0 (warp 0) and first document index with doc_off >= t0 (warp 1): 32-way searches
-  if (warp < 2) {
-    const uint64_t r = warp_first_true(doc_off32, ndocs + 1, t0, warp == 0, lane);
-    if (lane == 0) {
-      if (warp == 0) s_dpos0 = r ? doc_off32[r - 1] : 0;  // r = upper_bound(doc_off32, t0)
-      else s_dlo = r;                                      // r = lower_bound(doc_off32, t0)
-    }
+  if (tid == 0) {
+    // first document index with doc_off >= t0 (from k_docstart), last document start <= t0
+    uint64_t ub = tile_first_doc[tile];
+    s_dlo = ub;
+    while (ub <= ndocs && doc_off32[ub] == t0) ub++;  // (empty documents share an offset)
+    s_dpos0 = ub ? doc_off32[ub - 1] : 0;
   }
   // exclusive prefix of popc(S), popc(E) and running "last doc start" over the tile's words
   const uint32_t cs = __popc(S), ce = __popc(E);
@@ -1239,7 +1225,7 @@ static bool dalloc(T*& p, uint64_t count) {
 
 void workspace_free(Workspace& ws) {
   void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.rec, ws.gend, ws.wbuf, ws.ends,
-                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.deferred, ws.tile_last_hs, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
+                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.deferred, ws.tile_last_hs, ws.tile_first_doc, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1266,7 +1252,7 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ok = ok && dalloc(ws.deferred, (uint64_t)ws.deferred_cap);
     ok = ok && dalloc(ws.tile_last_hs, cap / 8128 + 8) && dalloc(ws.path, cap / 12 + 64) && dalloc(ws.bp, cap / 3 + 64);
     ws.blocks_cap = (uint32_t)std::min<uint64_t>(ntiles * kTileSlots + 8, 0xFFFFFFF0ull);
-    ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8));
+    ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8)) && dalloc(ws.tile_first_doc, cap / kRankBytes + 8);
     if (!ws.counters) ok = ok && dalloc(ws.counters, (uint64_t)C_NUM);
     if (host_staging) ok = ok && dalloc(ws.text, cap + 64);
     if (!ws.out_ntok) ok = ok && dalloc(ws.out_ntok, 2);
@@ -1364,7 +1350,7 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
   cudaMemsetAsync(ws.ds_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.s_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.e_bits, 0, ((uint64_t)nwords + 4) * 4, st);
-  JB_LAUNCH(k_docstart, (unsigned)((ndocs + 1 + 255) / 256), 256, 0, st, d_doc_off, ndocs, n, ws.doc_off32, ws.ds_bits);
+  JB_LAUNCH(k_docstart, (unsigned)((ndocs + 1 + 255) / 256), 256, 0, st, d_doc_off, ndocs, n, ws.doc_off32, ws.ds_bits, ws.tile_first_doc);
   PROF(1);
   if (n > 0) {
     const unsigned pgrid = (unsigned)g_num_sms * 8;
@@ -1494,7 +1480,7 @@ int run_scatter(Workspace& ws, uint32_t n, uint64_t ndocs, uint32_t* d_start, ui
   const uint32_t nwords = (n + 31) / 32;
   const uint32_t nrt = (n + kRankBytes - 1) / kRankBytes;
   if (n > 0)
-    JB_LAUNCH(k_rank_scatter, nrt, kRankWords, 0, st, ws.s_bits, ws.e_bits, ws.ds_bits, nwords, n, ws.rank_cnt, ws.doc_off32, ndocs,
+    JB_LAUNCH(k_rank_scatter, nrt, kRankWords, 0, st, ws.s_bits, ws.e_bits, ws.ds_bits, nwords, n, ws.rank_cnt, ws.doc_off32, ws.tile_first_doc, ndocs,
               d_start, d_end, cap_tokens, d_doc_tok_off, tok_base);
   PROF(8);
   if (ws.prof) ws.prof_pending = true;

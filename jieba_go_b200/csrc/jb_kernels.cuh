@@ -70,6 +70,7 @@ struct Workspace {
   uint32_t* path = nullptr;      // chosen word length - 1 per rune (k_route -> k_emit)
   uint8_t* bp = nullptr;         // Viterbi back-pointers per rune (k_emit)
   uint32_t blocks_cap = 0;       // entries of `ends` usable as the stream path's block list
+  uint32_t* tile_first_doc = nullptr;  // per rank tile: first document index with doc_off >= the tile's first byte
   uint32_t* rank_cnt = nullptr;  // per rank tile: token count, then exclusive prefix
   uint32_t* counters = nullptr;  // Counter
   double* dbg_proba = nullptr;   // optional: selected route value per slot
