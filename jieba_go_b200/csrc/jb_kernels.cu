@@ -1231,6 +1231,9 @@ void workspace_free(Workspace& ws) {
     if (p) cudaFree(p);
   for (auto& e : ws.ev)
     if (e) cudaEventDestroy(e);
+  if (ws.aux_stream) cudaStreamDestroy(ws.aux_stream);
+  if (ws.ev_fork) cudaEventDestroy(ws.ev_fork);
+  if (ws.ev_join) cudaEventDestroy(ws.ev_join);
   ws = Workspace();
 }
 
@@ -1279,7 +1282,7 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
 const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset",
                                                        "k_scan",
                                                        "k_route",
-                                                       "k_emit+k_tile_scan+k_resolve_deferred",
+                                                       "k_emit (k_tile_scan+k_resolve_deferred on a side stream)",
                                                        "general pipeline (flagged batches)",
                                                        "k_rank_count",
                                                        "k_rank_scan",
@@ -1415,6 +1418,29 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       launch_scan(T, sc, st);
       g_launches.fetch_add(1);
       PROF(2);
+      // the gated non-Han tokens that k_scan deferred only need the tile summaries: a one-CTA scan and a tiny kernel,
+      // run on a side stream under k_route instead of leaving the GPU idle for them
+      bool forked = false;
+      if (!ws.aux_stream) {
+        if (cudaStreamCreateWithFlags(&ws.aux_stream, cudaStreamNonBlocking) != cudaSuccess) ws.aux_stream = nullptr;
+        else if (cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                 cudaEventCreateWithFlags(&ws.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+          cudaStreamDestroy(ws.aux_stream);
+          ws.aux_stream = nullptr;
+        }
+      }
+      {
+        cudaStream_t sx = ws.aux_stream ? ws.aux_stream : st;
+        if (ws.aux_stream) {
+          cudaEventRecord(ws.ev_fork, st);
+          cudaStreamWaitEvent(sx, ws.ev_fork, 0);
+          forked = true;
+        }
+        JB_LAUNCH(k_tile_scan, 1, 1024, 0, sx, ws.tile_sum, ws.tile_ctx, nt1, ws.counters, 0);
+        JB_LAUNCH(k_resolve_deferred, (unsigned)g_num_sms, 256, 0, sx, ws.deferred, ws.counters, ws.deferred_cap, ws.tile_ctx, ws.s_bits,
+                  ws.e_bits);
+        if (forked) cudaEventRecord(ws.ev_join, sx);
+      }
       RouteArgs ra;
       ra.text = d_text;
       ra.tile_last_hs = ws.tile_last_hs;
@@ -1438,9 +1464,7 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       ea.min_chunk = 1;
       launch_emit(T, ea, use_hmm, g_num_sms, st);
       g_launches.fetch_add(1);
-      JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, nt1, ws.counters, 0);
-      JB_LAUNCH(k_resolve_deferred, (unsigned)g_num_sms, 256, 0, st, ws.deferred, ws.counters, ws.deferred_cap, ws.tile_ctx, ws.s_bits,
-                ws.e_bits);
+      if (forked) cudaStreamWaitEvent(st, ws.ev_join, 0);
       PROF(4);
       JB_LAUNCH(k_fallback_reset, (unsigned)g_num_sms * 4, 256, 0, st, ws.counters, ws.s_bits, ws.e_bits, nwords + 4);
     } else {

@@ -43,6 +43,9 @@ struct Workspace {
   cudaEvent_t ev[kNumProfKernels + 1] = {};
   double prof_ms[kNumProfKernels] = {};
   uint64_t prof_steps = 0;
+  // side stream for the tile-summary scan (forked after k_scan, joined before the ranking)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // dictionary tables (one allocation): L2 access-policy window set around the pipeline
   void* l2_base = nullptr;
   size_t l2_bytes = 0;
