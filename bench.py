@@ -196,6 +196,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # rank 0 prints exactly one JSON line on stdout: NCCL's own log lines (e.g. its version banner) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from jieba_go_b200 import _capi
