@@ -717,6 +717,18 @@ struct BitAcc2 {  // token bits of one lane, flushed one 32-byte word at a time 
     w = 0xFFFFFFFFu;
   }
 };
+// bits of lo -> positions p .., bits of hi -> positions p + 48 .. (lo spans at most 48 bits, hi 24): straight to
+// the bitmap, branch-free (a run of <= 24 runes touches at most four 32-byte words)
+__device__ __forceinline__ void or_span(uint32_t* __restrict__ bits, uint32_t p, unsigned long long lo, unsigned long long hi) {
+  const uint32_t sh = p & 31u, pw = p >> 5;
+  const unsigned long long v0 = lo | (hi << 48), v1 = hi >> 16;  // the 72-bit value
+  const unsigned long long s0 = v0 << sh, s1 = (v1 << sh) | (sh ? (v0 >> (64u - sh)) : 0ull);
+  const uint32_t x0 = (uint32_t)s0, x1 = (uint32_t)(s0 >> 32), x2 = (uint32_t)s1, x3 = (uint32_t)(s1 >> 32);
+  if (x0) atomicOr(&bits[pw], x0);
+  if (x1) atomicOr(&bits[pw + 1u], x1);
+  if (x2) atomicOr(&bits[pw + 2u], x2);
+  if (x3) atomicOr(&bits[pw + 3u], x3);
+}
 // bit j of x (j < 16) -> bit 3j
 __device__ __forceinline__ unsigned long long spread3(uint32_t x16) {
   unsigned long long x = x16 & 0xFFFFu;
@@ -730,7 +742,7 @@ __device__ __forceinline__ unsigned long long spread3(uint32_t x16) {
 template <bool HMM, int PB>
 __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const EmitArgs A) {
   constexpr uint32_t PPW = 32 / PB, PMASK = (1u << PB) - 1u;
-  constexpr uint32_t kRegRun = 32;  // the four best paths of runs up to this length are carried in registers
+  constexpr uint32_t kRegRun = 24;  // the four best paths of runs up to this length are carried in registers
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   if (A.counters[C_FLAGS] & 1u) return;
@@ -748,9 +760,9 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   uint32_t pw = 0, pt = 0xFFFFFFFFu;
   uint32_t run_n = 0, run_s = 0;
   double V[4] = {0.0, 0.0, 0.0, 0.0};
-  // viterbi's fullPath (T:715-716) in bit form: per state, which runes of its best path are E or S (token ends),
-  // and the path's length (a route with from == "" restarts it)
-  uint32_t pm[4] = {0, 0, 0, 0}, plens = 0;
+  // viterbi's fullPath (T:715-716) in bit form, per state: bits 0..23 = which runes of its best path are E or S
+  // (token ends), bits 24..31 = the path's length (a route with from == "" restarts it)
+  uint32_t pm[4] = {0, 0, 0, 0};
   for (;;) {
     // ---- refill idle lanes from the warp's queue of block indexes ----
     const uint32_t nm = __ballot_sync(FULL, !active);
@@ -802,12 +814,12 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           run_s = k;
 #pragma unroll
           for (int s = 0; s < 4; s++) V[s] = T.start[s] + em[s];
-          pm[0] = pm[1] = 0;
-          pm[2] = pm[3] = 1u;
-          plens = 0x01010101u;
+          pm[0] = pm[1] = 1u << 24;
+          pm[2] = pm[3] = (1u << 24) | 1u;
         } else {
           double W[4];
-          uint32_t code = 0, npm[4], nlens = 0;
+          uint32_t code = 0, npm[4];
+          const uint32_t step = (1u << 24) | (run_n < kRegRun ? (1u << run_n) : 0u);  // one more entry; E and S end a token
 #pragma unroll
           for (int s = 0; s < 4; s++) {  // stateTransitionRoute (T:736-756): strict > from minFloat, list order
             const int pa = (s == 0 || s == 3) ? 2 : 0, pb = (s == 0 || s == 3) ? 3 : 1;
@@ -825,17 +837,13 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
             W[s] = best + em[s];
             code |= from << (2 * s);
             // fullPath[s] = fullPath[route.from] + [s]; fullPath[""] is nil (T:715-716)
-            const uint32_t m0 = from == 0 ? 0u : (from == 1 ? pm[pa] : pm[pb]);
-            const uint32_t l0 = from == 0 ? 0u : ((plens >> (8 * (from == 1 ? pa : pb))) & 0xFFu);
-            npm[s] = m0 | ((s >= 2 && run_n < 32u) ? (1u << run_n) : 0u);
-            nlens |= min(l0 + 1u, 255u) << (8 * s);
+            npm[s] = (from == 0 ? 0u : (from == 1 ? pm[pa] : pm[pb])) + (s >= 2 ? step : (1u << 24));
           }
 #pragma unroll
           for (int s = 0; s < 4; s++) {
             V[s] = W[s];
             pm[s] = npm[s];
           }
-          plens = nlens;
           A.bp[pi] = (uint8_t)code;  // only read back for runs longer than the register window
         }
         run_n++;
@@ -845,20 +853,16 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           sa.set(P0 + 3u * run_s);
           ea.set(P0 + 3u * run_s + 2);
         } else if (run_n <= kRegRun) {
-          const int sf = V[2] > V[3] ? 2 : 3;  // T:723-729
-          const uint32_t plen = (plens >> (8 * sf)) & 0xFFu;
+          const uint32_t pf = V[2] > V[3] ? pm[2] : pm[3];  // T:723-729
+          const uint32_t plen = pf >> 24;
           // path[j] applies to rune j (T:277-283): a short path drops the run's tail
-          uint32_t es = (sf == 2 ? pm[2] : pm[3]) >> (run_n - plen);
-          const uint32_t lm = plen >= 32u ? FULL : ((1u << plen) - 1u);
-          es &= lm;
+          const uint32_t lm = (1u << plen) - 1u;
+          const uint32_t es = ((pf & 0xFFFFFFu) >> (run_n - plen)) & lm;
           const uint32_t starts = ((es << 1) | 1u) & lm;
           const uint32_t q0 = P0 + 3u * run_s;
-          sa.set_span(q0, spread3(starts));  // rune j starts at q0 + 3j ...
-          ea.set_span(q0 + 2u, spread3(es));  // ... and ends at q0 + 3j + 2
-          if (plen > 16u) {
-            sa.set_span(q0 + 48u, spread3(starts >> 16));
-            ea.set_span(q0 + 50u, spread3(es >> 16));
-          }
+          // rune j starts at q0 + 3j and ends at q0 + 3j + 2: spread the masks by 3 and OR them into the bitmaps
+          or_span(A.s_bits, q0, spread3(starts), spread3(starts >> 16));
+          or_span(A.e_bits, q0 + 2u, spread3(es), spread3(es >> 16));
         } else {
           int st2 = V[2] > V[3] ? 2 : 3;
           uint32_t kb = run_s + run_n - 1;
