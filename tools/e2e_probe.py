@@ -6,7 +6,7 @@ sd = synth.make_dictionary(n_words=349000, seed=synth.SEED_BASE)
 emit = synth.make_emit(sd)
 text, doc_off = synth.make_corpus(sd, 'freq', 1_000_000_000, synth.SEED_BASE + 2, device='cuda')
 h_text = text.cpu().pin_memory(); h_np = h_text.numpy(); h_off = doc_off.cpu().numpy().astype(np.uint64)
-for mb in (32 << 20, 64 << 20, 128 << 20, 256 << 20):
+for mb in (64 << 20, 128 << 20, 256 << 20):
     tk = Tokenizer.from_dict_text(sd.dict_txt(), 1, emit, device=0, max_batch_bytes=mb)
     tk.cut_batch_view(h_np, h_off, False).close()
     tk.cut_batch_view(h_np, h_off, False).close()
