@@ -166,7 +166,7 @@ __device__ uint32_t s_block_alnum(const uint32_t* BND, const uint32_t* ALN, int 
   return need ? (2u | need) : 0u;
 }
 
-__global__ void __launch_bounds__(kScThreads, 4) k_scan(const JbTables T, const ScanArgs A) {
+__global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const ScanArgs A) {
   __shared__ __align__(16) ScanSmem S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wj = tid;  // word index inside the staged region: 0 = halo before, 1..254 own, 255 = halo after
@@ -906,7 +906,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
 
 int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st) {
   const bool r16 = T.max_delta <= 16;
-  const unsigned grid = (unsigned)num_sms * 8u;
+  const unsigned grid = (unsigned)num_sms * (hmm ? 9u : 16u);  // resident CTAs per SM by register count (56 / 30)
   if (r16) {
     if (hmm) k_emit<true, 4><<<grid, kEmThreads, 0, st>>>(T, A);
     else k_emit<false, 4><<<grid, kEmThreads, 0, st>>>(T, A);
