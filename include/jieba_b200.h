@@ -160,7 +160,7 @@ int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, cons
                   uint64_t ndocs, int use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
                   uint64_t* d_doc_tok_off, uint64_t* d_n_tokens, void* cuda_stream);
 int jb_set_candidates_per_slot(jb_tokenizer* tk, double per_slot);
-/* 1: bypass the fused shared-memory fast path and run the general kernels on every block (testing) */
+/* 1: bypass the streaming fast path (k_scan / k_route / k_emit) and run the general kernels on every block (testing) */
 int jb_set_general_only(jb_tokenizer* tk, int on);
 
 /* ---- introspection (tests / bench) ------------------------------------------------------ */

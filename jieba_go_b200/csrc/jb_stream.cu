@@ -804,8 +804,9 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
       const bool single = HMM && d == 1;
       if (single) {  // collect singletons (T:233-234): one Viterbi step per rune (T:688-719)
         const uintptr_t ap = tbase + P0 + 3u * k, a4 = ap & ~(uintptr_t)3;
-        const uint32_t x = __funnelshift_r(__ldg(reinterpret_cast<const uint32_t*>(a4)), __ldg(reinterpret_cast<const uint32_t*>(a4 + 4)),
-                                           (uint32_t)(ap & 3) * 8u);
+        const uint32_t xl = __ldg(reinterpret_cast<const uint32_t*>(a4));
+        const uint32_t xh = (ap & 3) >= 2 ? __ldg(reinterpret_cast<const uint32_t*>(a4 + 4)) : 0u;  // (never a word past the text)
+        const uint32_t x = __funnelshift_r(xl, xh, (uint32_t)(ap & 3) * 8u);
         const uint32_t cp = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
         const double2* ep = reinterpret_cast<const double2*>(T.emit + (size_t)cp * 4);
         const double2 e0 = __ldg(ep), e1 = __ldg(ep + 1);
