@@ -1225,7 +1225,7 @@ static bool dalloc(T*& p, uint64_t count) {
 
 void workspace_free(Workspace& ws) {
   void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.rec, ws.gend, ws.wbuf, ws.ends,
-                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.deferred, ws.tile_last_hs, ws.tile_first_doc, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
+                  ws.walks, ws.tile_sum, ws.tile_ctx, ws.deferred, ws.tile_last_hs, ws.tile_first_doc, ws.wide_list, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1253,6 +1253,8 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ok = ok && dalloc(ws.tile_sum, ntiles + 8) && dalloc(ws.tile_ctx, ntiles + 8);
     ws.deferred_cap = (uint32_t)(cap / 64 + 4096);
     ok = ok && dalloc(ws.deferred, (uint64_t)ws.deferred_cap);
+    ws.wide_cap = (uint32_t)(cap / 256 + 4096);
+    ok = ok && dalloc(ws.wide_list, (uint64_t)ws.wide_cap);
     ok = ok && dalloc(ws.tile_last_hs, cap / 8128 + 8) && dalloc(ws.path, cap / 12 + 64) && dalloc(ws.bp, cap / 3 + 64);
     ws.blocks_cap = (uint32_t)std::min<uint64_t>(ntiles * kTileSlots + 8, 0xFFFFFFF0ull);
     ok = ok && dalloc(ws.rank_cnt, 2 * (cap / kRankBytes + 8)) && dalloc(ws.tile_first_doc, cap / kRankBytes + 8);
@@ -1281,7 +1283,7 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
 
 const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset",
                                                        "k_scan",
-                                                       "k_route",
+                                                       "k_route (+k_wide)",
                                                        "k_emit (k_tile_scan+k_resolve_deferred on a side stream)",
                                                        "general pipeline (flagged batches)",
                                                        "k_rank_count",
@@ -1448,9 +1450,28 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       ra.blocks_cap = ws.blocks_cap;
       ra.counters = ws.counters;
       ra.path = ws.path;
+      ra.wide_list = ws.wide_list;
+      ra.wide_cap = ws.wide_cap;
       ra.min_chunk = 16;  // measured on 10k-rune blocks: fuller warps beat more warps (instruction issue is per warp)
       launch_route(T, ra, g_num_sms, st);
       g_launches.fetch_add(1);
+      {
+        WideArgs wa2;
+        wa2.text = d_text;
+        wa2.n = n;
+        wa2.ds_bits = ws.ds_bits;
+        wa2.blocks = ws.ends;
+        wa2.wide_list = ws.wide_list;
+        wa2.wide_cap = ws.wide_cap;
+        wa2.counters = ws.counters;
+        wa2.R = ws.wbuf;
+        wa2.len8 = ws.bp;
+        wa2.code8 = reinterpret_cast<uint8_t*>(ws.rec);
+        wa2.s_bits = ws.s_bits;
+        wa2.e_bits = ws.e_bits;
+        launch_wide(T, wa2, use_hmm, g_num_sms, st);
+        g_launches.fetch_add(1);
+      }
       PROF(3);
       EmitArgs ea;
       ea.text = d_text;

@@ -25,6 +25,7 @@ enum Counter {
   C_STATUS = 3,    // bit0: candidate-weight buffer overflow
   C_N_TOKENS = 4,
   C_W_NEEDED = 5,  // max weights needed by any tile (to size a retry)
+  C_N_WIDE = 6,    // Han blocks with a 4-byte rune, handed to k_wide
   C_N_DEFER = 7,   // gated non-Han tokens waiting for the tile-summary scan
   C_FLAGS = 8,     // bit0: the batch must be redone by the general pipeline
   C_N_BLK = 12,    // Han blocks listed by k_scan for k_route / k_emit
@@ -73,6 +74,8 @@ struct Workspace {
   uint32_t* path = nullptr;      // chosen word length - 1 per rune (k_route -> k_emit)
   uint8_t* bp = nullptr;         // Viterbi back-pointers per rune (k_emit)
   uint32_t blocks_cap = 0;       // entries of `ends` usable as the stream path's block list
+  uint32_t* wide_list = nullptr; // k_route -> k_wide
+  uint32_t wide_cap = 0;
   uint32_t* tile_first_doc = nullptr;  // per rank tile: first document index with doc_off >= the tile's first byte
   uint32_t* rank_cnt = nullptr;  // per rank tile: token count, then exclusive prefix
   uint32_t* counters = nullptr;  // Counter

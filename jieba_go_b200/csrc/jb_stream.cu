@@ -23,6 +23,7 @@ struct ScanSmem {
   uint32_t ALN[kScThreads];      // ASCII [a-zA-Z0-9] bytes
   uint32_t BND[kScThreads];      // first byte of every block (Han or not), end of text
   uint32_t HS[kScThreads];       // first rune of every Han block
+  uint32_t HAN4[kScThreads];     // 4-byte Han rune starts (subset of HANL)
   uint32_t OTE[kScThreads + 1];  // last byte of every non-Han, non-alnum, non-space rune
   uint32_t S[kScThreads + 1], E[kScThreads + 1];
   uint32_t wsum[kScThreads / 32];
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const 
   const int base = 16 + 32 * wj;                           // its region index
   const bool live = Pw >= 0 && Pw < (int64_t)n;
   const uint32_t D = S.dsw[wj + 1];
-  uint32_t RS = 0, HANL = 0, ALN = 0, OTH = 0;
+  uint32_t RS = 0, HANL = 0, HAN4 = 0, ALN = 0, OTH = 0;
   if (live) {
     const uint32_t VM = (Pw + 32 <= (int64_t)n) ? FULL : ((1u << (uint32_t)(n - Pw)) - 1u);
     const uint4 qa = *reinterpret_cast<const uint4*>(&S.sb[base]), qb = *reinterpret_cast<const uint4*>(&S.sb[base + 16]);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const 
         RS |= 1u << b;
         if (cl == SC_HAN) {
           HANL |= 1u << b;
-          if (len == 4) atomicOr(&A.counters[C_FLAGS], 1u);  // 4-byte Han: the general pipeline redoes the batch
+          if (len == 4) HAN4 |= 1u << b;  // its block goes to k_wide
         } else if (cl == SC_ALNUM) {
           ALN |= 1u << b;
         } else if (cl != SC_SPACE) {
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const 
     }
   }
   S.HANL[wj] = HANL;
+  S.HAN4[wj] = HAN4;
   S.ALN[wj] = ALN;
   __syncthreads();
 
@@ -298,8 +300,10 @@ __global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const 
   uint32_t HE = 0;
   if (own) {
     const uint32_t Dn = S.dsw[wj + 2];
-    const uint32_t prevHan = __funnelshift_l(S.HANL[wj - 1], HANL, 3);              // rune right before is Han (3 bytes)
-    const uint32_t nextHan = __funnelshift_r(HANL & ~D, S.HANL[wj + 1] & ~Dn, 3);   // Han rune follows in the same document
+    // the rune right before is Han (3 or 4 bytes); a Han rune follows in the same document
+    const uint32_t H4p = S.HAN4[wj - 1], NX = HANL & ~D, NXn = S.HANL[wj + 1] & ~Dn;
+    const uint32_t prevHan = __funnelshift_l(S.HANL[wj - 1] & ~H4p, HANL & ~HAN4, 3) | __funnelshift_l(H4p, HAN4, 4);
+    const uint32_t nextHan = (~HAN4 & __funnelshift_r(NX, NXn, 3)) | (HAN4 & __funnelshift_r(NX, NXn, 4));
     uint32_t BND = RS & (D | (HANL ^ prevHan));
     if ((int64_t)n < Pw + 32) BND |= 1u << (uint32_t)(n - Pw);  // end of the text
     const uint32_t HS = HANL & (D | ~prevHan);
@@ -353,6 +357,7 @@ __global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const 
       int ws = wj;
       while (!hm && ws > 1) hm = S.HS[--ws];
       if (hm) nr = (uint32_t)((wj - ws) * 32 + b - (31 - __clz(hm))) / 3u + 1u;
+      if ((HAN4 >> b) & 1) nr = kWideBlock;  // ends with a 4-byte rune: k_route hands it to k_wide at once
       if (o < A.blocks_cap) A.blocks[o] = make_uint2((uint32_t)Pw + b, nr);
       o++;
     }
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
 
   // the lane now stands on the rune at p: decode it from the window, issue its table loads (first = true: last
   // rune of a block, nothing to its right)
-  auto setup_pos = [&](const bool first_rune) {
+  auto setup_pos = [&](const bool first_rune) -> bool {
     const uint32_t o = p & 7u;
     const uint32_t x = __funnelshift_r(o & 4u ? w1 : w0, o & 4u ? wn : w1, (o & 3u) * 8u);
     const uint32_t r1 = r0;
@@ -494,6 +499,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       h3 = jb_hash_next(h2, srr[((kq - 2u) & M) * kRtThreads]);
       e3 = __ldg(entries + (h3 & hmask));
     }
+    return (x & 0xF0u) == 0xE0u;  // inside a Han block every rune has 3 bytes -- or 4 (k_wide)
   };
 
   for (;;) {
@@ -517,6 +523,12 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
           const uint2 bd = A.blocks[bi];
           e3i = bd.x / 3u;
           nr = bd.y;
+          if (nr == kWideBlock) {  // ends with a 4-byte rune
+            const uint32_t wi = atomicAdd(&A.counters[C_N_WIDE], 1u);
+            if (wi < A.wide_cap) A.wide_list[wi] = bi;
+            else atomicOr(&A.counters[C_FLAGS], 1u);
+            A.blocks[bi].y = 0;  // nothing for k_emit
+          } else {
           if (nr == 0) {  // the block began in an earlier k_scan tile: the nearest tile with a block start holds it
             uint32_t t = bd.x / (uint32_t)kScTileBytes, sp;
             do sp = __ldg(A.tile_last_hs + --t);
@@ -534,6 +546,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
           setup_pos(true);
           chain = false;
           active = true;
+          }
         }
       }
       qh = min(qt, qh + (uint32_t)__popc(nm));
@@ -653,7 +666,16 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
           wc--;
           if (wc) tp = __ldg(text8 + wc - 1);
         }
-        setup_pos(false);
+        if (!setup_pos(false)) {  // not the lead of a 3-byte rune: the lane stepped into a 4-byte Han rune -> k_wide
+          const uint32_t wi = atomicAdd(&A.counters[C_N_WIDE], 1u);
+          if (wi < A.wide_cap) A.wide_list[wi] = bi;
+          else atomicOr(&A.counters[C_FLAGS], 1u);
+          A.blocks[bi].y = 0;  // nothing for k_emit (blocks[bi].x still is the block's last rune)
+          if (acc) atomicOr(&A.path[accw], acc);  // (path entries of the abandoned part are never read)
+          acc = 0;
+          accw = 0xFFFFFFFFu;
+          active = false;
+        }
       }
     }
     __syncwarp();
@@ -787,7 +809,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           k = 0;
           run_n = 0;
           pt = 0xFFFFFFFFu;
-          active = true;
+          active = npos != 0;  // 0: the block went to k_wide
         }
       }
       qh = min(qt, qh + (uint32_t)__popc(nm));
@@ -915,6 +937,227 @@ int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cud
     if (hmm) k_emit<true, 8><<<grid, kEmThreads, 0, st>>>(T, A);
     else k_emit<false, 8><<<grid, kEmThreads, 0, st>>>(T, A);
   }
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+
+// ==========================================================================================
+// k_wide: Han blocks that contain a 4-byte rune (CJK extension B and beyond).  k_route steps over 3-byte runes
+// only; it hands such a block over the moment it lands inside a 4-byte rune (k_scan does so for a block that
+// ENDS with one).  They are rare (about one rune in 1e5 in real text), so one lane takes a whole block and
+// restates the reference directly: buildDag (T:462-497), calcDagProba (T:502-548), maxIndexProba (T:565-578),
+// findDagPath (T:552-562), cutZh / viterbi / cutHMM (T:221-285, 668-756), with per-rune scratch in HBM
+// indexed by lead byte / 3.
+// ==========================================================================================
+struct WideCtx {
+  const uint8_t* text;
+  const uint32_t* ds_bits;
+  uint32_t n;
+  __device__ __forceinline__ bool ds_at(uint32_t p) const { return p >= n || ((ds_bits[p >> 5] >> (p & 31)) & 1); }
+  __device__ __forceinline__ uint32_t len_at(uint32_t p) const { return text[p] >= 0xF0 ? 4u : 3u; }  // inside a block
+  __device__ __forceinline__ uint32_t rune_at(uint32_t p) const {
+    const uint8_t* b = text + p;
+    if (b[0] >= 0xF0) return ((b[0] & 0x07u) << 18) | ((b[1] & 0x3Fu) << 12) | ((b[2] & 0x3Fu) << 6) | (b[3] & 0x3Fu);
+    return ((b[0] & 0x0Fu) << 12) | ((b[1] & 0x3Fu) << 6) | (b[2] & 0x3Fu);
+  }
+  __device__ __forceinline__ uint32_t prev_lead(uint32_t p) const { return (text[p - 3] & 0xF0) == 0xE0 ? p - 3 : p - 4; }  // inside a block
+};
+// lead byte of a Han rune that ends right before p in the same document, or 0xFFFFFFFF
+__device__ uint32_t w_han_before(const WideCtx& cx, const JbTables& T, uint32_t p) {
+  const uint8_t* t = cx.text;
+  if (p == 0 || cx.ds_at(p)) return 0xFFFFFFFFu;
+  if (p >= 3 && (t[p - 3] & 0xF0) == 0xE0) {
+    const uint32_t q = p - 3, L = t[q], c1 = t[q + 1], c2 = t[q + 2];
+    if ((c1 & 0xC0) != 0x80 || (c2 & 0xC0) != 0x80 || (L == 0xE0 && c1 < 0xA0) || (L == 0xED && c1 > 0x9F)) return 0xFFFFFFFFu;
+    if (cx.ds_at(q + 1) || cx.ds_at(q + 2)) return 0xFFFFFFFFu;
+    return s_is_han(((L & 0xFu) << 12) | ((c1 & 0x3Fu) << 6) | (c2 & 0x3Fu), T) ? q : 0xFFFFFFFFu;
+  }
+  if (p >= 4 && t[p - 4] >= 0xF0 && t[p - 4] <= 0xF4) {
+    const uint32_t q = p - 4, L = t[q], c1 = t[q + 1], c2 = t[q + 2], c3 = t[q + 3];
+    if ((c1 & 0xC0) != 0x80 || (c2 & 0xC0) != 0x80 || (c3 & 0xC0) != 0x80 || (L == 0xF0 && c1 < 0x90) || (L == 0xF4 && c1 > 0x8F)) return 0xFFFFFFFFu;
+    if (cx.ds_at(q + 1) || cx.ds_at(q + 2) || cx.ds_at(q + 3)) return 0xFFFFFFFFu;
+    return s_is_han(((L & 0x7u) << 18) | ((c1 & 0x3Fu) << 12) | ((c2 & 0x3Fu) << 6) | (c3 & 0x3Fu), T) ? q : 0xFFFFFFFFu;
+  }
+  return 0xFFFFFFFFu;
+}
+__device__ __forceinline__ void w_set(uint32_t* bits, uint32_t p) { atomicOr(&bits[p >> 5], 1u << (p & 31)); }
+__device__ void w_load_emit(const JbTables& T, uint32_t cp, double e[4]) {
+  if (cp < 0x10000) {
+    const double2* p = reinterpret_cast<const double2*>(T.emit + (size_t)cp * 4);
+    const double2 a = __ldg(p), b = __ldg(p + 1);
+    e[0] = a.x, e[1] = a.y, e[2] = b.x, e[3] = b.y;
+    return;
+  }
+  e[0] = e[1] = e[2] = e[3] = JB_MINF;  // missing emission (T:690-692)
+  int lo = 0, hi = (int)T.n_emit_supp - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const uint32_t r = __ldg(T.emit_supp_rune + mid);
+    if (r == cp) {
+      for (int s = 0; s < 4; s++) e[s] = __ldg(T.emit_supp + (size_t)mid * 4 + s);
+      return;
+    }
+    if (r < cp) lo = mid + 1;
+    else hi = mid - 1;
+  }
+}
+
+template <bool HMM>
+__global__ void __launch_bounds__(128) k_wide(const JbTables T, const WideArgs A) {
+  if (A.counters[C_FLAGS] & 1u) return;
+  const uint32_t nw = min(A.counters[C_N_WIDE], A.wide_cap);
+  const WideCtx cx{A.text, A.ds_bits, A.n};
+  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nw; wi += gridDim.x * blockDim.x) {
+    const uint32_t e = A.blocks[A.wide_list[wi]].x;  // lead byte of the block's last rune
+    const uint32_t blk_end = e + cx.len_at(e);
+    uint32_t start = e;
+    for (uint32_t q; (q = w_han_before(cx, T, start)) != 0xFFFFFFFFu;) start = q;
+    // ---- route DP, right to left ----
+    for (uint32_t q = e;; q = cx.prev_lead(q)) {
+      const uint32_t r0 = cx.rune_at(q);
+      uint32_t pos = q + cx.len_at(q);
+      double w0;
+      uint32_t info, child, parent, hs = r0 < 0x10000 ? JB_PARENT_FIRST(r0) : JB_PARENT_ROOT;
+      if (r0 < 0x10000) {  // termFreq[string(iRune)] (T:468-472)
+        const uint4 f = __ldg(reinterpret_cast<const uint4*>(T.first + r0));
+        w0 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
+        info = f.z;
+        child = f.w;
+        parent = JB_PARENT_FIRST(r0);
+      } else {
+        double pw;
+        uint32_t prb;
+        const int ps = jb_probe_edge(T.entries, T.hash_mask, hs, JB_PARENT_ROOT, r0, &pw, &prb);
+        if (ps >= 0 && jb_w_positive(pw)) {
+          w0 = pw;
+          info = (uint32_t)JB_MAX_DELTA << 8;
+        } else {
+          w0 = ps >= 0 ? pw : T.neg_log_total;  // freq 0: -Inf; missing: log(1) - total
+          info = JB_FIRST_GATE;
+        }
+        child = ps >= 0 ? (prb >> 21) : 0u;
+        parent = (uint32_t)ps;
+      }
+      double prev = JB_MINF, best_v = 0.0, v = w0 + (pos == blk_end ? 0.0 : A.R[pos / 3u]);
+      uint32_t best_b = 0, last_b = pos - q;
+      if (v >= prev) {  // maxIndexProba (T:565-578)
+        best_b = last_b;
+        best_v = v;
+      }
+      prev = v;
+      if (!(info & JB_FIRST_GATE)) {
+        const uint32_t maxlen = (info >> 8) & 0xFFu;
+        for (uint32_t L = 1; L < maxlen && pos < blk_end;) {  // for j := range textRunes[i:] (T:473-482)
+          const uint32_t rl = cx.rune_at(pos);
+          const bool may = (L == 1 && r0 < 0x10000) ? ((child >> jb_bloom_bit(rl)) & 1) : ((child >> jb_bloom11(rl)) & 1);
+          if (!may) break;
+          double pw;
+          uint32_t prb;
+          const int ps = jb_probe_edge(T.entries, T.hash_mask, hs, parent, rl, &pw, &prb);
+          if (ps < 0) break;
+          L++;
+          pos += cx.len_at(pos);
+          if (jb_w_positive(pw)) {
+            v = pw + (pos == blk_end ? 0.0 : A.R[pos / 3u]);
+            last_b = pos - q;
+            if (v >= prev) {
+              best_b = last_b;
+              best_v = v;
+            }
+            prev = v;
+          }
+          parent = (uint32_t)ps;
+          child = prb >> 21;
+        }
+      }
+      if (best_b == 0) {  // best.index == -1 -> return prev (T:574-576)
+        best_b = last_b;
+        best_v = prev;
+      }
+      A.R[q / 3u] = best_v;
+      A.len8[q / 3u] = (uint8_t)best_b;
+      if (q == start) break;
+    }
+    // ---- forward walk, HMM over runs of single-rune pieces ----
+    uint32_t run_n = 0, run_s = 0, run_l = 0;  // runes, lead byte of the first / last rune of the run
+    double V[4] = {0.0, 0.0, 0.0, 0.0};
+    for (uint32_t p = start; p < blk_end;) {
+      const uint32_t bl = A.len8[p / 3u], rlen = cx.len_at(p);
+      const bool single = HMM && bl == rlen;
+      if (single) {
+        double em[4];
+        w_load_emit(T, cx.rune_at(p), em);
+        if (run_n == 0) {
+          run_s = p;
+          for (int s = 0; s < 4; s++) V[s] = T.start[s] + em[s];
+        } else {
+          double W[4];
+          uint32_t code = 0;
+          for (int s = 0; s < 4; s++) {  // stateTransitionRoute (T:736-756)
+            const int pa = (s == 0 || s == 3) ? 2 : 0, pb = (s == 0 || s == 3) ? 3 : 1;
+            const double r0v = V[pa] + T.trans[s][0], r1v = V[pb] + T.trans[s][1];
+            double best = JB_MINF;
+            uint32_t from = 0;
+            if (r0v > best) {
+              best = r0v;
+              from = 1;
+            }
+            if (r1v > best) {
+              best = r1v;
+              from = 2;
+            }
+            W[s] = best + em[s];
+            code |= from << (2 * s);
+          }
+          for (int s = 0; s < 4; s++) V[s] = W[s];
+          A.code8[p / 3u] = (uint8_t)code;
+        }
+        run_l = p;
+        run_n++;
+      }
+      if (HMM && run_n && (!single || p + bl >= blk_end)) {  // viterbi's tail (T:723-729) + cutHMM (T:273-285)
+        if (run_n == 1) {
+          w_set(A.s_bits, run_s);
+          w_set(A.e_bits, run_s + cx.len_at(run_s) - 1u);
+        } else {
+          int st2 = V[2] > V[3] ? 2 : 3;
+          uint32_t kb = run_l, plen = 0;
+          for (;;) {  // back-trace; stops early where route.from == "" (T:715-716)
+            const uint8_t code = A.code8[kb / 3u];
+            A.code8[kb / 3u] = (uint8_t)(st2 >= 2 ? 0x80 : 0);
+            plen++;
+            if (kb == run_s) break;
+            const int c = (code >> (2 * st2)) & 3;
+            if (c == 0) break;
+            st2 = (st2 == 0 || st2 == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
+            kb = cx.prev_lead(kb);
+          }
+          // path[j] applies to rune j (T:277-283): entry j sits at rune j + (run_n - plen); kb is entry 0
+          uint32_t pr = run_s, pe = kb;
+          bool prev_es = true;
+          for (uint32_t j = 0; j < plen; j++) {
+            const bool es = A.code8[pe / 3u] & 0x80;
+            if (prev_es) w_set(A.s_bits, pr);
+            if (es) w_set(A.e_bits, pr + cx.len_at(pr) - 1u);
+            prev_es = es;
+            pr += cx.len_at(pr);
+            pe += cx.len_at(pe);
+          }
+        }
+        run_n = 0;
+      }
+      if (!single) {
+        w_set(A.s_bits, p);
+        w_set(A.e_bits, p + bl - 1u);
+      }
+      p += bl;
+    }
+  }
+}
+
+int launch_wide(const JbTables& T, const WideArgs& A, bool hmm, int num_sms, cudaStream_t st) {
+  if (hmm) k_wide<true><<<(unsigned)num_sms, 128, 0, st>>>(T, A);
+  else k_wide<false><<<(unsigned)num_sms, 128, 0, st>>>(T, A);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

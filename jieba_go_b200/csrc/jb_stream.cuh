@@ -9,8 +9,10 @@
 //                          chosen word length per rune (4 bits) goes to HBM.
 //   k_emit   (W, H, V, O)  one lane per Han block: findDagPath walk, Viterbi over single-rune runs, token bits.
 //
-// Handed to the general kernels (jb_kernels.cu): a batch that contains a well-formed 4-byte Han rune or
-// overflows a list (C_FLAGS bit0).  Blocks of any length stay on this path.
+//   k_wide   (all rows)    the rare Han blocks that contain a 4-byte rune: one lane restates the reference per block.
+//
+// Handed to the general kernels (jb_kernels.cu): a batch that overflows a list (C_FLAGS bit0).  Blocks of any
+// length stay on this path.
 #pragma once
 #include "jb_kernels.cuh"
 
@@ -21,6 +23,7 @@ constexpr int kScOwnWords = kScThreads - 2;   // 254 words = 8128 bytes per tile
 constexpr int kScTileBytes = kScOwnWords * 32;
 constexpr int kScLeft = 48;                   // staged bytes before the tile: 16 pad + the 32-byte halo word
 constexpr int kScRegion = kScLeft + kScTileBytes + 48;
+constexpr uint32_t kWideBlock = 0xFFFFFFFFu;  // block length marker: ends with a 4-byte Han rune
 
 struct ScanArgs {
   const uint8_t* text;
@@ -44,6 +47,8 @@ struct RouteArgs {
   uint32_t blocks_cap;
   uint32_t* counters;
   uint32_t* path;         // chosen word length - 1 per rune, index = lead byte / 3
+  uint32_t* wide_list;    // indexes of blocks with a 4-byte Han rune, for k_wide
+  uint32_t wide_cap;
   uint32_t min_chunk;     // blocks a warp takes from the queue at least (few long blocks: lanes per warp vs warps per SM)
 };
 
@@ -59,6 +64,22 @@ struct EmitArgs {
   uint32_t min_chunk;
 };
 
+struct WideArgs {
+  const uint8_t* text;
+  uint32_t n;
+  const uint32_t* ds_bits;
+  const uint2* blocks;
+  const uint32_t* wide_list;
+  uint32_t wide_cap;
+  const uint32_t* counters;
+  double* R;        // per-rune scratch, index = lead byte / 3: route value,
+  uint8_t* len8;    //   chosen word length in bytes,
+  uint8_t* code8;   //   Viterbi back-pointers / state flag
+  uint32_t* s_bits;
+  uint32_t* e_bits;
+};
+
+int launch_wide(const JbTables& T, const WideArgs& A, bool hmm, int num_sms, cudaStream_t st);
 int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st);
 int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st);
 int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st);

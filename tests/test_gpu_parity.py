@@ -363,3 +363,52 @@ def test_scan_tile_edges(small_synth, hmm):
     # ... and all of them in one batch (document starts near tile edges)
     text, off = pack_docs(docs)
     _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 2), text, off)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_four_byte_han_blocks(path):
+    """Han blocks with 4-byte runes (CJK extension B): k_route hands them to k_wide.  Dictionary words with such runes,
+    runs of them (Viterbi with supplementary-plane emissions), blocks that start / end with one, document boundaries
+    next to them, many of them in one batch."""
+    sd = synth.make_dictionary(n_words=3000, seed=synth.SEED_BASE + 93, total_freq=1.0e6, max_len=6)
+    emit = synth.make_emit(sd, seed=synth.SEED_BASE + 94)
+    ext = [chr(0x20000 + 37 * i) for i in range(40)]
+    emit = {st: dict(tab) for st, tab in emit.items()}
+    for i, c in enumerate(ext[:25]):  # some of them have emissions, in some states
+        for j, st in enumerate("BMES"):
+            if (i + j) % 3:
+                emit[st][ord(c)] = -3.0 - 0.37 * i - 0.11 * j
+    lines = [ln.decode() for ln in sd.lines()]
+    w = [x.decode() for x in sd.words]
+    lines += ["%s 800 n" % ext[0], "%s%s 500 n" % (ext[1], w[3][:1]), "%s%s%s 900 n" % (w[5][:1], ext[2], ext[3]),
+              "%s%s 300 n" % (ext[4], ext[5]), "%s%s%s%s 100 n" % (ext[4], ext[5], w[7][:1], ext[6])]
+    tk = _gpu_tokenizer(lines, emit, 1, path=path)
+    from oracle import c_oracle as co
+    hm = co.Hmm()
+    hm.set_emit_arrays(*emit_arrays(emit))
+    ora = co.Tokenizer(co.Dict.from_lines(lines, 1), hm)
+    rng = np.random.default_rng(14)
+    docs = []
+    for _ in range(400):
+        parts = []
+        for _ in range(int(rng.integers(1, 30))):
+            r = rng.random()
+            if r < 0.25:
+                parts.append(ext[int(rng.integers(0, len(ext)))])
+            elif r < 0.30:
+                parts.append("".join(ext[int(i)] for i in rng.integers(0, len(ext), int(rng.integers(2, 45)))))
+            elif r < 0.40:
+                parts.append(chr(int(rng.integers(0x4E00, 0x9FA6))))
+            elif r < 0.47:
+                parts.append(["，", "a1", " ", "\n", "é"][int(rng.integers(0, 5))])
+            else:
+                parts.append(w[int(rng.integers(0, len(w)))])
+        docs.append("".join(parts).encode())
+    docs += [ext[0].encode(), (ext[1] + w[3][:1]).encode(), (w[2] + ext[7]).encode(), (ext[8] + w[2]).encode()]
+    text, off = pack_docs(docs)
+    for hmm in (False, True):
+        _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 2), text, off)
+    # the same bytes as ONE document and cut at arbitrary positions (splits the 4-byte runes too)
+    cuts = np.unique(np.concatenate([[0, text.size], rng.integers(0, text.size, 300)])).astype(np.uint64)
+    for hmm in (False, True):
+        _assert_same(tk.cut_batch(text, cuts, hmm), ora.cut_batch(text, cuts, hmm, 2), text, cuts)
