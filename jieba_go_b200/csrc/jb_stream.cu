@@ -449,6 +449,13 @@ int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st) {
 constexpr int kRtThreads = 128;
 constexpr int kRtQueue = 32;
 
+// 16-byte read-only load that asks L1 to keep the line (the first-rune table is the hottest data of the kernel)
+__device__ __forceinline__ uint4 ldg_keep(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 template <int RING, int PB>
 __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const RouteArgs A) {
   __shared__ double ring[RING][kRtThreads];
@@ -492,7 +499,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     const uint32_t r1 = r0;
     r0 = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
     srr[(kq & M) * kRtThreads] = (uint16_t)r0;
-    f = __ldg(first + r0);
+    f = ldg_keep(first + r0);
     if (!first_rune) {  // (with one rune to the right the 3-rune slot is computed from a stale rune: loaded, never looked at)
       h2 = jb_hash_next(JB_PARENT_FIRST(r0), r1);
       e2 = __ldg(entries + (h2 & hmask));
