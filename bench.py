@@ -298,7 +298,7 @@ def main():
         traffic = None
         try:
             for rec in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))):
-                if rec["kernel"] == dom and rec["config"] == args.config and abs(rec["input_bytes"] - nbytes) <= 0.01 * nbytes:
+                if dom.startswith(rec["kernel"]) and rec["config"] == args.config and abs(rec["input_bytes"] - nbytes) <= 0.01 * nbytes:
                     traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
         except Exception:
             pass

@@ -8,7 +8,7 @@ python bench.py --config 3 --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_config
 python bench.py --config 4 --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_config4.json 2> gpurun_out/${TAG}_c4.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_ref.err
 # launch list of the bench command itself (per-launch times under ncu are cold-cache and serialised)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_ncu_launches_config2.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/${TAG}_ncu_launches_config2.csv \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_launches.log 2>&1
 for K in k_route k_scan k_emit k_rank_scatter; do
   ncu --set full --clock-control none --import-source on -k regex:^${K}\$ -s 3 -c 1 -o gpurun_out/${TAG}_${K}_c2 \
