@@ -54,9 +54,7 @@ struct __attribute__((aligned(16))) JbEntry {
 JB_HD uint32_t jb_hash_fin(uint32_t h) {
   h ^= h >> 15;
   h *= 0x2C1B3C6Du;
-  h ^= h >> 12;
-  h *= 0x297A2D39u;
-  h ^= h >> 15;
+  h ^= h >> 13;
   return h;
 }
 // Slot hash of a key = a fold over its RUNES (not over the parent's slot), so that the slots of successive
