@@ -891,8 +891,23 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           const uint32_t starts = ((es << 1) | 1u) & lm;
           const uint32_t q0 = P0 + 3u * run_s;
           // rune j starts at q0 + 3j and ends at q0 + 3j + 2: spread the masks by 3 and OR them into the bitmaps
-          or_span(A.s_bits, q0, spread3(starts), spread3(starts >> 16));
-          or_span(A.e_bits, q0 + 2u, spread3(es), spread3(es >> 16));
+          if (plen <= 10u) {  // almost every run: 30 bits, two words per bitmap
+            uint32_t x = es;  // bit j -> bit 3j
+            x = (x | (x << 16)) & 0x030000FFu;
+            x = (x | (x << 8)) & 0x0300F00Fu;
+            x = (x | (x << 4)) & 0x030C30C3u;
+            x = (x | (x << 2)) & 0x09249249u;
+            const uint32_t sm = ((x << 3) | 1u) & ((1u << (3u * plen)) - 1u);  // a token starts after every end, and at rune 0
+            const uint32_t sh = q0 & 31u, wq = q0 >> 5;
+            const unsigned long long ss = (unsigned long long)sm << sh, ee = ((unsigned long long)x << 2) << sh;
+            if ((uint32_t)ss) atomicOr(&A.s_bits[wq], (uint32_t)ss);
+            if ((uint32_t)(ss >> 32)) atomicOr(&A.s_bits[wq + 1u], (uint32_t)(ss >> 32));
+            if ((uint32_t)ee) atomicOr(&A.e_bits[wq], (uint32_t)ee);
+            if ((uint32_t)(ee >> 32)) atomicOr(&A.e_bits[wq + 1u], (uint32_t)(ee >> 32));
+          } else {
+            or_span(A.s_bits, q0, spread3(starts), spread3(starts >> 16));
+            or_span(A.e_bits, q0 + 2u, spread3(es), spread3(es >> 16));
+          }
         } else {
           int st2 = V[2] > V[3] ? 2 : 3;
           uint32_t kb = run_s + run_n - 1;
