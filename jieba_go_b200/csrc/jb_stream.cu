@@ -780,9 +780,19 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   const uint32_t nwarps = gridDim.x * (kEmThreads / 32);
   const uint32_t chunk = min(32u, max(A.min_chunk, (nblocks + nwarps - 1) / nwarps));
   const uintptr_t tbase = reinterpret_cast<uintptr_t>(A.text);
-  BitAcc2 sa, ea;
+  BitAcc2 sa, ea;  // HMM off: every lane emits a token per iteration, merged per 32-byte word
   sa.init(A.s_bits);
   ea.init(A.e_bits);
+  // HMM on: the lanes that emit in a given iteration are few and spread over several code sites; the per-lane word
+  // accumulator then costs more than it saves: straight atomics
+  auto set_s = [&](uint32_t q) {
+    if (HMM) atomicOr(&A.s_bits[q >> 5], 1u << (q & 31));
+    else sa.set(q);
+  };
+  auto set_e = [&](uint32_t q) {
+    if (HMM) atomicOr(&A.e_bits[q >> 5], 1u << (q & 31));
+    else ea.set(q);
+  };
   uint32_t qh = 0, qt = 0;
   bool exhausted = false, active = false;
   uint32_t P0 = 0, i0 = 0, npos = 0, k = 0;
@@ -880,8 +890,8 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
       }
       if (HMM && run_n && (!single || k + 1 >= npos)) {  // flush the run: viterbi's tail (T:723-729) + cutHMM (T:273-285)
         if (run_n == 1) {
-          sa.set(P0 + 3u * run_s);
-          ea.set(P0 + 3u * run_s + 2);
+          set_s(P0 + 3u * run_s);
+          set_e(P0 + 3u * run_s + 2);
         } else if (run_n <= kRegRun) {
           const uint32_t pf = V[2] > V[3] ? pm[2] : pm[3];  // T:723-729
           const uint32_t plen = pf >> 24;
@@ -927,21 +937,23 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           for (uint32_t j2 = 0; j2 < plen; j2++) {
             const bool es = A.bp[i0 + run_s + shift + j2] & 0x80;
             const uint32_t qq = P0 + 3u * (run_s + j2);
-            if (prev_es) sa.set(qq);
-            if (es) ea.set(qq + 2);
+            if (prev_es) set_s(qq);
+            if (es) set_e(qq + 2);
             prev_es = es;
           }
         }
         run_n = 0;
       }
       if (!single) {
-        sa.set(P0 + 3u * k);
-        ea.set(P0 + 3u * (k + d) - 1u);
+        set_s(P0 + 3u * k);
+        set_e(P0 + 3u * (k + d) - 1u);
       }
       k += d;
       if (k >= npos) {
-        sa.flush();
-        ea.flush();
+        if (!HMM) {
+          sa.flush();
+          ea.flush();
+        }
         active = false;
       }
     }
