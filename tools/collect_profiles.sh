@@ -17,3 +17,5 @@ done
 ncu --set full --clock-control none --import-source on -k regex:^k_emit\$ -s 3 -c 1 -o gpurun_out/${TAG}_k_emit_c3 \
   python bench.py --config 3 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_k_emit_c3.log 2>&1
 ls -la gpurun_out/${TAG}_* | head -30
+ncu --set full --clock-control none --import-source on -k regex:^k_route\$ -s 3 -c 1 -o gpurun_out/${TAG}_k_route_c3 \
+  python bench.py --config 3 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_k_route_c3.log 2>&1
