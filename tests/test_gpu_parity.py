@@ -412,3 +412,22 @@ def test_four_byte_han_blocks(path):
     cuts = np.unique(np.concatenate([[0, text.size], rng.integers(0, text.size, 300)])).astype(np.uint64)
     for hmm in (False, True):
         _assert_same(tk.cut_batch(text, cuts, hmm), ora.cut_batch(text, cuts, hmm, 2), text, cuts)
+
+
+@pytest.mark.parametrize("hmm", [False, True])
+def test_list_overflow_falls_back_to_general_kernels(small_synth, hmm):
+    """A megabyte of punctuation without any alnum: every rune is a gated token whose block leaves its k_scan tile, the
+    deferred list overflows, the batch is flagged on the device and the general kernels redo it (same results)."""
+    sd, emit = small_synth
+    tk = _gpu_tokenizer(sd, emit, 1)
+    ora = c_oracle_tokenizer(sd, emit, 1)
+    w = [x.decode() for x in sd.words[:50]]
+    docs = [("。，！？" * 90_000).encode(),                                   # dropped entirely (T:291-293)
+            ("。，！？" * 90_000 + "x" + "；" * 1000).encode(),                # one alnum far away: every rune is a token
+            ("".join(w) + "，" * 50_000 + "".join(w[::-1]) + " a1 " + "。" * 40_000).encode()]
+    for d in docs:
+        t = np.frombuffer(d, dtype=np.uint8)
+        off = np.array([0, len(d)], dtype=np.uint64)
+        _assert_same(tk.cut_batch(t, off, hmm), ora.cut_batch(t, off, hmm, 4), t, off)
+    text, off = pack_docs(docs)
+    _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 4), text, off)
