@@ -40,6 +40,8 @@ struct WsSlot {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;
   uint64_t* h_cnt = nullptr;  // pinned: token count + status of the batch in flight
+  uint64_t* h_doc = nullptr;  // pinned staging of the batch's document offsets (the caller's array is pageable:
+  uint64_t h_doc_cap = 0;     //  an async copy from it would block the host until the stream gets there)
 };
 
 struct jb_tokenizer {
@@ -342,6 +344,7 @@ static void free_slot(WsSlot* s) {
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->ev) cudaEventDestroy(s->ev);
   if (s->h_cnt) cudaFreeHost(s->h_cnt);
+  if (s->h_doc) cudaFreeHost(s->h_doc);
 }
 
 void jb_tokenizer_destroy(jb_tokenizer* tk) {
@@ -483,6 +486,15 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
   if (rc != JB_OK) return done(rc);
 
   // stage A: copy in, run the whole pipeline (scatter into the slot's device buffers), copy the count out
+  const bool timeline = getenv("JB_TIMELINE") != nullptr;
+  std::vector<cudaEvent_t> tl_ev;  // per chunk: start, h2d done, kernels done, d2h done
+  auto tl_rec = [&](size_t ci, int which, cudaStream_t s2) {
+    if (!timeline) return;
+    if (tl_ev.size() < (ci + 1) * 4) tl_ev.resize((ci + 1) * 4, nullptr);
+    cudaEvent_t& e = tl_ev[ci * 4 + which];
+    if (!e) cudaEventCreate(&e);
+    cudaEventRecord(e, s2);
+  };
   auto enqueue = [&](size_t ci) -> int {
     Chunk& c = chunks[ci];
     WsSlot* sl = slots[ci % kPipeSlots];
@@ -502,11 +514,24 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
         return fail(JB_ENOMEM, "device output allocation failed");
       ws.out_cap = want;
     }
+    tl_rec(ci, 0, st);
     if (c.nb) CUDA_TRY(cudaMemcpyAsync(ws.text, text + doc_off[c.d0], c.nb, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, doc_off + c.d0, (c.d1 - c.d0 + 1) * 8, cudaMemcpyHostToDevice, st));
+    const uint64_t nd1 = c.d1 - c.d0 + 1;
+    if (sl->h_doc_cap < nd1) {
+      if (sl->h_doc) cudaFreeHost(sl->h_doc);
+      sl->h_doc = nullptr;
+      sl->h_doc_cap = 0;
+      const uint64_t ncap = nd1 + nd1 / 4 + 1024;
+      if (cudaMallocHost(&sl->h_doc, ncap * 8) != cudaSuccess) return fail(JB_ENOMEM, "pinned host allocation failed");
+      sl->h_doc_cap = ncap;
+    }
+    memcpy(sl->h_doc, doc_off + c.d0, nd1 * 8);  // (the slot's previous batch is complete: its stream was synchronised)
+    CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, sl->h_doc, nd1 * 8, cudaMemcpyHostToDevice, st));
+    tl_rec(ci, 1, st);
     r = run_pipeline(tk->T, ws, ws.text, (uint32_t)c.nb, ws.doc_off64, c.d1 - c.d0, use_hmm != 0, ws.out_start, ws.out_end, ws.out_cap,
                      ws.out_doc_tok, 0, ws.out_ntok, st, tk->force_general != 0);
     if (r != JB_OK) return fail(r, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    tl_rec(ci, 2, st);
     CUDA_TRY(cudaMemcpyAsync(sl->h_cnt, ws.out_ntok, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(sl->ev, st));
     return JB_OK;
@@ -573,6 +598,7 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     }
     // (the batch's last entry belongs to the next batch's first document: copy d1-d0 entries, not one more)
     CUDA_TRY(cudaMemcpyAsync(res->doc_tok + c.d0, ws.out_doc_tok, (c.d1 - c.d0) * 8, cudaMemcpyDeviceToHost, st));
+    tl_rec(ci, 3, st);
     base += nt;
     res->n_tokens = base;
   }
@@ -581,6 +607,16 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
       cudaError_t se = cudaStreamSynchronize(sl->stream);
       if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("pipeline failed: ") + cudaGetErrorString(se)));
     }
+  if (timeline && !tl_ev.empty()) {
+    for (size_t ci = 0; ci * 4 + 3 < tl_ev.size(); ci++) {
+      float t[4] = {0, 0, 0, 0};
+      for (int w = 0; w < 4; w++)
+        if (tl_ev[ci * 4 + w]) cudaEventElapsedTime(&t[w], tl_ev[0], tl_ev[ci * 4 + w]);
+      fprintf(stderr, "chunk %zu: %7.1f MB  start %6.2f  h2d %6.2f  kernels %6.2f  d2h %6.2f ms\n", ci, chunks[ci].nb / 1e6, t[0], t[1], t[2], t[3]);
+    }
+    for (cudaEvent_t e : tl_ev)
+      if (e) cudaEventDestroy(e);
+  }
   for (Chunk& c : chunks)
     if (c.base)
       for (uint64_t d = c.d0; d < c.d1; d++) res->doc_tok[d] += c.base;
