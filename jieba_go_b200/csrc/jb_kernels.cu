@@ -1089,6 +1089,7 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
   // cost one L1 wavefront per token).
   {
     uint32_t* const wst = stage[warp];
+    const uint32_t dbase = prev_ld >= 0 ? t0 + (uint32_t)prev_ld : dpos0;  // last document start before this word
     const uint32_t wls = __shfl_sync(FULL, ls, 0), wle = __shfl_sync(FULL, le, 0);        // tile-local rank of the warp's first start / end
     const uint32_t wts = __shfl_sync(FULL, is, 31), wte = __shfl_sync(FULL, ie, 31);      // tokens of the warp
 #pragma unroll 1
@@ -1098,12 +1099,21 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
       uint32_t* __restrict__ out = which ? out_end : out_start;
       for (uint32_t c0 = 0; c0 < total; c0 += kRankStage) {
         uint32_t m = bits, lr = lr0;
+        if (D == 0) {  // no document starts in this word (almost always): one base for all its tokens
+          const uint32_t rel = wpos + (uint32_t)which - dbase;
+          while (m) {
+            const uint32_t b = __ffs(m) - 1;
+            m &= m - 1;
+            if (lr - c0 < (uint32_t)kRankStage) wst[lr - c0] = rel + b;
+            lr++;
+          }
+        }
         while (m) {
           const uint32_t b = __ffs(m) - 1;
           m &= m - 1;
           if (lr - c0 < (uint32_t)kRankStage) {
             const uint32_t dm = D & ((b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u));
-            const uint32_t dpos = dm ? wpos + (31 - __clz(dm)) : (prev_ld >= 0 ? t0 + (uint32_t)prev_ld : dpos0);
+            const uint32_t dpos = dm ? wpos + (31 - __clz(dm)) : dbase;
             wst[lr - c0] = wpos + b + (uint32_t)which - dpos;
           }
           lr++;

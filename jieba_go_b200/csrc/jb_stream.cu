@@ -564,8 +564,8 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     // the next entry of its prefix chain in e2 and its selector state parked in f / e3 / h2 / h3 / cs.
     // Candidates in ascending length: pieceFreq + nextBestPiece.proba (T:519-529) into maxIndexProba's running
     // (prev, best) pair: each candidate is compared with the previous one, first with minFloat (T:565-578). ----
-    double best_v = 0.0, last_v = 0.0, prev_v = 0.0;
-    uint32_t best_d = 0, last_d = 0, L = 0, parent = 0, slot = 0, hs = 0, maxlen = 0;
+    double best_v, last_v, prev_v;  // (all of these are written before they are read whenever the lane is active)
+    uint32_t best_d, last_d, L, parent, slot, hs, maxlen;
     bool more = false, home = false;  // home: the next probe looks at the home slot of its key
     if (active) {
       const bool chained = chain, fresh = !chain;
