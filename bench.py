@@ -148,6 +148,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: whatever libraries print there (NCCL's version banner, ...) is sent to
+    # stderr by pointing fd 1 at fd 2 for the run; the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit_line(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -187,7 +196,7 @@ def main():
             "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit_line(line)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -196,8 +205,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # rank 0 prints exactly one JSON line on stdout: NCCL's own log lines (e.g. its version banner) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from jieba_go_b200 import _capi
@@ -333,7 +340,7 @@ def main():
                                     "sample": "first %d B (%d docs) of the batch, C restatement of jieba-go (not Go), %d threads" % (
                                         len(st), len(so) - 1, cores)}
             line["parity"] = "bit-exact on the cpu_baseline sample" if same else "MISMATCH on the cpu_baseline sample"
-        print(json.dumps(line))
+        emit_line(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
