@@ -12,9 +12,12 @@
  *     thread-local message.  Nothing aborts or throws across this boundary (the reference
  *     log.Fatal/panics at load, T:397,443,656; the shim decides what to do with the code).
  *   - Inputs are borrowed for the duration of the call only (cgo pointer rule).
- *   - A jb_tokenizer is immutable after creation: any number of threads may call jb_cut*
- *     on it concurrently (mirrors pd.lock.RLock in Cut, T:152-153).  AddWord is
- *     "build a new tokenizer and swap" on the shim side, under its writer lock.
+ *   - A jb_tokenizer is immutable after creation: any number of threads may call jb_cut /
+ *     jb_cut_batch on it concurrently (mirrors pd.lock.RLock in Cut, T:152-153; every call takes
+ *     its own streams and device workspaces from a pool).  jb_cut_device calls may also come from
+ *     any thread / stream, but they share ONE device workspace per tokenizer and are therefore
+ *     serialised on the device (each call's stream waits for the previous call's kernels).
+ *     AddWord is "build a new tokenizer and swap" on the shim side, under its writer lock.
  *   - There is NO CPU fallback: if no CUDA device is usable, creation fails with
  *     JB_ECUDA.
  *   - Tokens are (start,end) byte offsets RELATIVE TO THEIR DOCUMENT, in document order,
@@ -23,6 +26,13 @@
  *     emitted by the reference as the 3-byte string "\xEF\xBF\xBD" (Go `range` decoding,
  *     T:301-305).  Such a token is exactly a 1-byte token whose byte is >= 0x80; use
  *     JB_TOKEN_IS_FFFD().
+ *
+ * Limits (fail loudly, never silently differ)
+ *   - Negative dictionary counts are rejected with JB_EFORMAT / JB_EINVAL by the loaders, jb_dict_add_term and
+ *     jb_tokenizer_create.  strconv.Atoi accepts them (T:414), but the reference then builds a DAG in which a rune
+ *     can have no edge at all (T:468-482: found, count != 0, val > 0 false) and Cut walks off it; there is no
+ *     behaviour to be bit-exact with.
+ *   - Han dictionary keys longer than 30 runes: JB_ELIMIT at creation.  One document < 2 GiB.
  */
 #ifndef JIEBA_B200_H
 #define JIEBA_B200_H
@@ -106,6 +116,10 @@ int jb_dict_load_gob(const uint8_t* data, uint64_t len, jb_dict_buf** out);
 int jb_dict_load_gob_file(const char* path, jb_dict_buf** out);
 /* addTerm (T:580-585): termFreq[term] = freq; size += freq (no prefix keys are added) */
 int jb_dict_add_term(jb_dict_buf* d, const uint8_t* term, uint64_t len, int64_t freq);
+/* suggestFreq (T:589-614): the frequency AddWord gives `term` when called with freq < 1.  pieces = the tokens of
+ * Cut(term, false), concatenated, with n_pieces+1 offsets (the shim cuts, the library does the float64 arithmetic). */
+int jb_dict_suggest_freq(const jb_dict_buf* d, const uint8_t* term, uint64_t term_len, const uint8_t* pieces,
+                         const uint64_t* piece_off, uint64_t n_pieces, int64_t* out);
 /* val, found := termFreq[key]: returns 1 and *freq if present, 0 if missing */
 int jb_dict_buf_lookup(const jb_dict_buf* d, const uint8_t* key, uint64_t len, int64_t* freq);
 /* view as a descriptor (pointers owned by the buffer); log_freq = NULL, log_total = NaN */
@@ -160,11 +174,21 @@ int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, cons
                   uint64_t ndocs, int use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
                   uint64_t* d_doc_tok_off, uint64_t* d_n_tokens, void* cuda_stream);
 int jb_set_candidates_per_slot(jb_tokenizer* tk, double per_slot);
-/* 1: bypass the streaming fast path (k_scan / k_route / k_emit) and run the general kernels on every block (testing) */
+/* 1: bypass the streaming fast path and run the general kernels on every block (testing) */
 int jb_set_general_only(jb_tokenizer* tk, int on);
+/* Kernel path of the Han blocks (testing / A-B measurements): 0 default (k_scan -> k_route -> k_emit, one lane per
+ * block), 1 general kernels only, 2 k_scan -> k_seg (CTA-cooperative: position-parallel dictionary probes into shared
+ * memory, then one lane per block; k_route + k_emit only for blocks longer than 1024 runes) */
+int jb_set_path(jb_tokenizer* tk, int path);
+/* Test knob for path 2: Han blocks longer than max_runes (<= 1024; 0 = default) are left to k_route / k_emit by k_seg */
+int jb_set_seg_max_runes(jb_tokenizer* tk, uint32_t max_runes);
 
 /* ---- introspection (tests / bench) ------------------------------------------------------ */
 uint64_t jb_kernel_launch_count(void); /* kernels launched by this library in this process */
+/* Results live in pinned host memory that jb_result_free keeps in a process-wide pool for the next call (pinning
+ * hundreds of MB costs more than a whole Cut).  Sets the pool's limit (default 4 GiB), frees what exceeds it and returns
+ * the bytes still held; jb_host_pool_limit(0) releases everything (call it when a service goes idle). */
+uint64_t jb_host_pool_limit(uint64_t max_bytes);
 /* Per-kernel timing of jb_cut_device with CUDA events on the launching stream (bench.py's roofline).
  * jb_profile_read sums milliseconds per kernel over the steps since the last reset. */
 int jb_profile_enable(jb_tokenizer* tk, int on);

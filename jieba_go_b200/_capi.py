@@ -41,6 +41,8 @@ SYMBOLS = {
     "jb_dict_load_gob_file": (C.c_int, [C.c_char_p, _PP]),
     "jb_dict_add_term": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_int64]),
     "jb_dict_buf_lookup": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.POINTER(C.c_int64)]),
+    "jb_dict_suggest_freq": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_char_p, _P, C.c_uint64, C.POINTER(C.c_int64)]),
+    "jb_host_pool_limit": (C.c_uint64, [C.c_uint64]),
     "jb_dict_buf_desc": (None, [_P, C.POINTER(DictDesc)]),
     "jb_dict_buf_set_size": (None, [_P, C.c_int64]),
     "jb_dict_buf_free": (None, [_P]),
@@ -63,6 +65,8 @@ SYMBOLS = {
     "jb_cut_device": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P, _P, C.c_uint64, _P, _P, _P]),
     "jb_set_candidates_per_slot": (C.c_int, [_P, C.c_double]),
     "jb_set_general_only": (C.c_int, [_P, C.c_int]),
+    "jb_set_path": (C.c_int, [_P, C.c_int]),
+    "jb_set_seg_max_runes": (C.c_int, [_P, C.c_uint32]),
     "jb_kernel_launch_count": (C.c_uint64, []),
     "jb_profile_enable": (C.c_int, [_P, C.c_int]),
     "jb_profile_num_kernels": (C.c_int, []),

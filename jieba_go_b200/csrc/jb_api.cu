@@ -52,10 +52,15 @@ struct jb_tokenizer {
   size_t table_bytes = 0;
   uint64_t max_batch = 128ull << 20;
   double w_per_slot = 3.0;
-  int force_general = 0;  // 1: skip the streaming fast path (tests / debugging)
+  int path = PATH_DEFAULT;  // PATH_GENERAL / PATH_SEG: tests and A/B measurements
+  uint32_t seg_max_runes = 0;
   std::mutex mu;
   std::vector<WsSlot*> free_ws;
-  WsSlot dev_ws;  // workspace of jb_cut_device (one caller at a time per tokenizer for the device API)
+  // jb_cut_device: ONE workspace per tokenizer.  Calls are serialised ON THE DEVICE: every call records dev_ws.ev at
+  // the end of its kernels and the next call's stream waits for it first, so two host threads (or two streams) never
+  // run on the same counters / bitmaps at the same time; dev_mu covers the enqueue.
+  WsSlot dev_ws;
+  bool dev_busy = false;
   std::mutex dev_mu;
 };
 
@@ -78,7 +83,7 @@ struct PinBuf {
 std::mutex g_pin_mu;
 std::vector<PinBuf> g_pin_pool;
 size_t g_pin_pooled = 0;
-const size_t kPinPoolMax = 6ull << 30;
+size_t g_pin_pool_max = 4ull << 30;  // jb_host_pool_limit
 
 void* pin_alloc(size_t bytes, size_t* got) {
   {
@@ -106,7 +111,7 @@ void pin_free(void* p, size_t bytes) {
   if (!p) return;
   {
     std::lock_guard<std::mutex> g(g_pin_mu);
-    if (g_pin_pooled + bytes <= kPinPoolMax && g_pin_pool.size() < 32) {
+    if (g_pin_pooled + bytes <= g_pin_pool_max && g_pin_pool.size() < 32) {
       g_pin_pool.push_back(PinBuf{p, bytes});
       g_pin_pooled += bytes;
       return;
@@ -115,6 +120,19 @@ void pin_free(void* p, size_t bytes) {
   cudaFreeHost(p);
 }
 }  // namespace
+
+static void pin_pool_trim(size_t keep) {
+  std::vector<PinBuf> drop;
+  {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    while (g_pin_pooled > keep && !g_pin_pool.empty()) {
+      drop.push_back(g_pin_pool.back());
+      g_pin_pooled -= g_pin_pool.back().bytes;
+      g_pin_pool.pop_back();
+    }
+  }
+  for (PinBuf& b : drop) cudaFreeHost(b.p);
+}
 
 // All tables live in ONE device allocation (256-byte aligned sub-ranges), so a single L2 access-policy
 // window can keep them resident while gigabytes of one-touch text and records stream through the cache.
@@ -139,6 +157,19 @@ const char* jb_last_error(void) { return g_err.c_str(); }
 void jb_hmm_defaults(jb_hmm_desc* h) { hmm_defaults(h); }
 double jb_go_log(double x) { return go_log(x); }
 uint64_t jb_kernel_launch_count(void) { return kernel_launch_count(); }
+uint64_t jb_host_pool_limit(uint64_t max_bytes) {
+  uint64_t held;
+  {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    g_pin_pool_max = (size_t)max_bytes;
+  }
+  pin_pool_trim((size_t)max_bytes);
+  {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    held = g_pin_pooled;
+  }
+  return held;
+}
 
 // ---- loaders ------------------------------------------------------------------------------
 int jb_dict_load_text(const uint8_t* data, uint64_t len, int mode, jb_dict_buf** out) {
@@ -185,6 +216,7 @@ int jb_dict_load_gob_file(const char* path, jb_dict_buf** out) {
 
 int jb_dict_add_term(jb_dict_buf* d, const uint8_t* term, uint64_t len, int64_t freq) {
   if (!d || (len && !term)) return fail(JB_EINVAL, "bad argument");
+  if (freq < 0) return fail(JB_EINVAL, "negative frequency");
   d->d.set(std::string((const char*)term, len), freq);  // termFreq[term] = freq (tokenizer.go:583)
   d->d.size += freq;                                    // size += freq        (tokenizer.go:584)
   return JB_OK;
@@ -195,6 +227,25 @@ int jb_dict_buf_lookup(const jb_dict_buf* d, const uint8_t* key, uint64_t len, i
   if (it == d->d.index.end()) return 0;
   if (freq) *freq = d->d.freq[it->second];
   return 1;
+}
+
+// suggestFreq (tokenizer.go:589-614).  The caller cuts `term` with HMM off and hands the pieces over; the float64
+// arithmetic lives here once for every shim: the pieces' shares of the dictionary are multiplied up in piece order,
+// scaled back by the size and truncated the way Go's int() does; an existing larger count wins.
+int jb_dict_suggest_freq(const jb_dict_buf* d, const uint8_t* term, uint64_t term_len, const uint8_t* pieces, const uint64_t* piece_off,
+                         uint64_t n_pieces, int64_t* out) {
+  if (!d || !out || (term_len && !term) || (n_pieces && (!pieces || !piece_off))) return fail(JB_EINVAL, "bad argument");
+  auto count_or_one = [&](const uint8_t* p, uint64_t n) -> int64_t {
+    auto it = d->d.index.find(std::string((const char*)p, n));
+    return it == d->d.index.end() ? 1 : d->d.freq[it->second];
+  };
+  const double total = d->d.size < 1 ? 1.0 : (double)d->d.size;
+  double share = 1.0;
+  for (uint64_t i = 0; i < n_pieces; i++) share *= (double)count_or_one(pieces + piece_off[i], piece_off[i + 1] - piece_off[i]) / total;
+  const int64_t wanted = (int64_t)(share * total) + 1;
+  const int64_t present = count_or_one(term, term_len);
+  *out = wanted > present ? wanted : present;
+  return JB_OK;
 }
 
 void jb_dict_buf_desc(const jb_dict_buf* d, jb_dict_desc* out) {
@@ -274,12 +325,6 @@ int jb_tokenizer_create(const jb_dict_desc* dict, const jb_hmm_desc* hmm, const 
   if (rc == JB_OK) rc = arena_put(tk, o_emit, img.emit, &T.emit);
   if (rc == JB_OK) rc = arena_put(tk, o_er, img.emit_supp_rune, &T.emit_supp_rune);
   if (rc == JB_OK) rc = arena_put(tk, o_es, img.emit_supp, &T.emit_supp);
-  {
-    // set aside L2 for persisting accesses (best effort; the window itself is set per stream at launch time)
-    int maxp = 0;
-    cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
-    if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxp, off + (8u << 20)));
-  }
   if (rc != JB_OK) {
     jb_tokenizer_destroy(tk);
     return rc;
@@ -435,7 +480,7 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     if (doc_off[d + 1] - doc_off[d] > tk->max_batch)
       return fail(JB_ELIMIT, "a document exceeds the device batch size (raise jb_options.max_batch_bytes; hard limit 2 GiB)");
   }
-  CUDA_TRY(cudaSetDevice(tk->device));
+  CUDA_TRY(cudaSetDevice(tk->device));  // (nothing acquired yet)
   // plan: greedy batches of whole documents
   struct Chunk {
     uint64_t d0, d1, nb, base;
@@ -502,8 +547,7 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     int r = workspace_reserve(sl->ws, c.nb, c.d1 - c.d0, wps, true);
     if (r != JB_OK) return fail(r, "device workspace allocation failed");
     Workspace& ws = sl->ws;
-    ws.l2_base = tk->table_base;
-    ws.l2_bytes = tk->table_bytes;
+    ws.seg_max_runes = tk->seg_max_runes;
     const uint64_t want = c.nb / 4 + 4096;
     if (ws.out_cap < want) {
       if (ws.out_start) cudaFree(ws.out_start);
@@ -529,7 +573,7 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, sl->h_doc, nd1 * 8, cudaMemcpyHostToDevice, st));
     tl_rec(ci, 1, st);
     r = run_pipeline(tk->T, ws, ws.text, (uint32_t)c.nb, ws.doc_off64, c.d1 - c.d0, use_hmm != 0, ws.out_start, ws.out_end, ws.out_cap,
-                     ws.out_doc_tok, 0, ws.out_ntok, st, tk->force_general != 0);
+                     ws.out_doc_tok, 0, ws.out_ntok, st, tk->path);
     if (r != JB_OK) return fail(r, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     tl_rec(ci, 2, st);
     CUDA_TRY(cudaMemcpyAsync(sl->h_cnt, ws.out_ntok, 16, cudaMemcpyDeviceToHost, st));
@@ -592,12 +636,15 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
       rc = result_grow(res, base + nt + (total_bytes - (doc_off[c.d1] - doc_off[0])) / 6);
       if (rc != JB_OK) return done(rc);
     }
+    // (an error here must still give the slots back and free the result: through done())
+    cudaError_t ce = cudaSuccess;
     if (nt) {
-      CUDA_TRY(cudaMemcpyAsync(res->start + base, ws.out_start, nt * 4, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaMemcpyAsync(res->end + base, ws.out_end, nt * 4, cudaMemcpyDeviceToHost, st));
+      ce = cudaMemcpyAsync(res->start + base, ws.out_start, nt * 4, cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(res->end + base, ws.out_end, nt * 4, cudaMemcpyDeviceToHost, st);
     }
     // (the batch's last entry belongs to the next batch's first document: copy d1-d0 entries, not one more)
-    CUDA_TRY(cudaMemcpyAsync(res->doc_tok + c.d0, ws.out_doc_tok, (c.d1 - c.d0) * 8, cudaMemcpyDeviceToHost, st));
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(res->doc_tok + c.d0, ws.out_doc_tok, (c.d1 - c.d0) * 8, cudaMemcpyDeviceToHost, st);
+    if (ce != cudaSuccess) return done(fail(JB_ECUDA, std::string("copy of the result failed: ") + cudaGetErrorString(ce)));
     tl_rec(ci, 3, st);
     base += nt;
     res->n_tokens = base;
@@ -637,19 +684,41 @@ int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, cons
   if (nbytes >= (1ull << 31)) return fail(JB_ELIMIT, "jb_cut_device handles < 2 GiB per call");
   CUDA_TRY(cudaSetDevice(tk->device));
   std::lock_guard<std::mutex> g(tk->dev_mu);
-  int rc = workspace_reserve(tk->dev_ws.ws, nbytes, ndocs, tk->w_per_slot, false);
+  WsSlot& sl = tk->dev_ws;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (!sl.ev) CUDA_TRY(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+  Workspace& ws = sl.ws;
+  if (tk->dev_busy) {
+    // the previous call may still be running (on another stream): growing the workspace frees buffers it uses, so
+    // that waits on the host; otherwise the wait is on the device only
+    const bool grows = nbytes > ws.cap_bytes || ndocs + 1 > ws.cap_docs;
+    if (grows) CUDA_TRY(cudaEventSynchronize(sl.ev));
+    else CUDA_TRY(cudaStreamWaitEvent(st, sl.ev, 0));
+  }
+  int rc = workspace_reserve(ws, nbytes, ndocs, tk->w_per_slot, false);
   if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
-  tk->dev_ws.ws.l2_base = tk->table_base;
-  tk->dev_ws.ws.l2_bytes = tk->table_bytes;
-  rc = run_pipeline(tk->T, tk->dev_ws.ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, d_start, d_end, cap_tokens,
-                    d_doc_tok_off, 0, d_n_tokens, (cudaStream_t)cuda_stream, tk->force_general != 0);
+  ws.seg_max_runes = tk->seg_max_runes;
+  rc = run_pipeline(tk->T, ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, d_start, d_end, cap_tokens,
+                    d_doc_tok_off, 0, d_n_tokens, st, tk->path);
+  cudaEventRecord(sl.ev, st);
+  tk->dev_busy = true;
   if (rc != JB_OK) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   return JB_OK;
 }
 
 int jb_set_general_only(jb_tokenizer* tk, int on) {
   if (!tk) return JB_EINVAL;
-  tk->force_general = on != 0;
+  tk->path = on ? PATH_GENERAL : PATH_DEFAULT;
+  return JB_OK;
+}
+int jb_set_path(jb_tokenizer* tk, int path) {
+  if (!tk || path < PATH_DEFAULT || path > PATH_SEG) return fail(JB_EINVAL, "path must be 0 (default), 1 (general) or 2 (seg)");
+  tk->path = path;
+  return JB_OK;
+}
+int jb_set_seg_max_runes(jb_tokenizer* tk, uint32_t max_runes) {
+  if (!tk) return JB_EINVAL;
+  tk->seg_max_runes = max_runes;
   return JB_OK;
 }
 int jb_profile_enable(jb_tokenizer* tk, int on) {
@@ -698,15 +767,47 @@ int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, u
   CUDA_TRY(cudaSetDevice(tk->device));
   std::lock_guard<std::mutex> g(tk->dev_mu);
   WsSlot& s = tk->dev_ws;
+  if (tk->dev_busy) CUDA_TRY(cudaDeviceSynchronize());
   int rc = workspace_reserve(s.ws, nbytes, 1, tk->w_per_slot, true);
   if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
   Workspace& ws = s.ws;
-  uint64_t nslots = (ws.cap_bytes / kTileBytes + 2) * kTileSlots + 64;
-  if (!ws.dbg_proba) CUDA_TRY(cudaMalloc(&ws.dbg_proba, nslots * 8));
+  ws.seg_max_runes = tk->seg_max_runes;
   uint64_t off[2] = {0, nbytes};
   CUDA_TRY(cudaMemcpy(ws.text, han_text, nbytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(ws.doc_off64, off, 16, cudaMemcpyHostToDevice));
-  rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, nullptr, nullptr, 0, ws.out_doc_tok, 0, ws.out_ntok, 0, true);
+  uint64_t o = 0;
+  if (tk->path != PATH_GENERAL) {
+    // streaming path (k_route, or k_seg with PATH_SEG): per rune, index = lead byte / 3.
+    // Only for text whose runes all have 3 bytes (a 4-byte rune sends its block to k_wide, which records nothing).
+    const uint64_t nr = nbytes / 3;
+    if (nr * 3 != nbytes) return fail(JB_EINVAL, "jb_debug_route on the streaming path needs 3-byte runes only");
+    for (uint64_t i = 0; i < nbytes; i += 3)
+      if ((han_text[i] & 0xF0) != 0xE0) return fail(JB_EINVAL, "jb_debug_route on the streaming path needs 3-byte runes only");
+    CUDA_TRY(cudaMalloc(&ws.dbg_R, (nr + 64) * 8));
+    CUDA_TRY(cudaMalloc(&ws.dbg_D, nr + 64));
+    CUDA_TRY(cudaMemset(ws.dbg_D, 0, nr + 64));
+    rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, nullptr, nullptr, 0, ws.out_doc_tok, 0, ws.out_ntok, 0, tk->path);
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<double> R(nr);
+    std::vector<uint8_t> D(nr);
+    CUDA_TRY(cudaMemcpy(R.data(), ws.dbg_R, nr * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(D.data(), ws.dbg_D, nr, cudaMemcpyDeviceToHost));
+    cudaFree(ws.dbg_R);
+    cudaFree(ws.dbg_D);
+    ws.dbg_R = nullptr;
+    ws.dbg_D = nullptr;
+    if (rc != JB_OK) return fail(rc, "kernel launch failed");
+    for (uint64_t j = 0; j < nr && o < cap; j++) {
+      if (!D[j]) return fail(JB_EINVAL, "jb_debug_route: the text is not one Han block");
+      best_end[o] = (uint32_t)(j + D[j]);
+      best_proba[o] = R[j];
+      o++;
+    }
+    return (int)o;
+  }
+  uint64_t nslots = (ws.cap_bytes / kTileBytes + 2) * kTileSlots + 64;
+  if (!ws.dbg_proba) CUDA_TRY(cudaMalloc(&ws.dbg_proba, nslots * 8));
+  rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, nullptr, nullptr, 0, ws.out_doc_tok, 0, ws.out_ntok, 0, PATH_GENERAL);
   CUDA_TRY(cudaDeviceSynchronize());
   // read back records + probabilities and translate slots to rune indexes
   uint64_t ns = (nbytes + 2) / 3 + 2;
@@ -726,7 +827,6 @@ int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, u
     i += wd;
   }
   rune_of_slot[(nbytes + 2) / 3] = (int64_t)nr;
-  uint64_t o = 0;
   for (uint64_t k = 0; k < ns && o < cap; k++) {
     if (rune_of_slot[k] < 0 || (uint64_t)rune_of_slot[k] >= nr) continue;
     best_end[o] = (uint32_t)rune_of_slot[k + (rec[k] & 0xFF)];

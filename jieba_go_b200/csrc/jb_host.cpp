@@ -200,6 +200,10 @@ int load_dict_text(const uint8_t* buf, uint64_t len, int mode, HostDict& d, std:
       err = "dict line " + std::to_string(lineno) + ": strconv.Atoi: invalid syntax";
       return JB_EFORMAT;
     }
+    if (cnt < 0) {  // Atoi takes it (tokenizer.go:414), but a negative count leaves a rune without any edge: see jieba_b200.h
+      err = "dict line " + std::to_string(lineno) + ": negative frequency";
+      return JB_EFORMAT;
+    }
     std::string word((const char*)buf + pos, s1 - pos);
     if (mode == JB_DICT_FILE_MODE) {
       if (!d.has(word)) {  // first duplicate wins, counted once (tokenizer.go:419-423)
@@ -299,6 +303,10 @@ int load_dict_gob(const uint8_t* data, uint64_t len, HostDict& d, std::string& e
       std::string key((const char*)data + m.i, kl);
       m.i += kl;
       int64_t v = m.int_();
+      if (v < 0) {
+        err = "gob: negative frequency";
+        return JB_EFORMAT;
+      }
       d.set(key, v);
     }
     if (!m.ok || m.i != mend) {
@@ -561,7 +569,8 @@ int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int ver, Tabl
     } else if (hk.freq == 0) {
       hk.w = -INFINITY;  // math.Log(0) - total
     } else {
-      hk.w = NAN;  // math.Log(negative) = NaN in Go; negative counts never occur in jieba data
+      err = "negative frequency in the dictionary (rejected: see jieba_b200.h, Limits)";
+      return JB_EFORMAT;
     }
     std::string ks((const char*)kp, kl);
     hk.bytes_key = ks;

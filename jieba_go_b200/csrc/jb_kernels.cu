@@ -1293,7 +1293,7 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
 
 const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset",
                                                        "k_scan",
-                                                       "k_route (+k_wide)",
+                                                       "k_route (+k_wide; k_seg with PATH_SEG)",
                                                        "k_emit (k_tile_scan+k_resolve_deferred on a side stream)",
                                                        "general pipeline (flagged batches)",
                                                        "k_rank_count",
@@ -1321,7 +1321,8 @@ static bool g_attr_done = false;
 
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t n, const uint64_t* d_doc_off, uint64_t ndocs,
                  bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens, uint64_t* d_doc_tok_off, uint64_t tok_base,
-                 uint64_t* d_n_tokens, cudaStream_t st, bool force_general) {
+                 uint64_t* d_n_tokens, cudaStream_t st, int path) {
+  const bool force_general = path == PATH_GENERAL;
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1342,25 +1343,6 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       if (!ws.ev[i]) cudaEventCreate(&ws.ev[i]);
   }
   PROF(0);
-  if (ws.l2_base && ws.l2_bytes) {
-    // keep the dictionary tables resident in L2: everything else that flows through the cache is one-touch
-    static int max_win = -1;
-    if (max_win < 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-    }
-    if (max_win > 0) {
-      cudaStreamAttrValue av;
-      memset(&av, 0, sizeof av);
-      av.accessPolicyWindow.base_ptr = ws.l2_base;
-      av.accessPolicyWindow.num_bytes = std::min<size_t>(ws.l2_bytes, (size_t)max_win);
-      av.accessPolicyWindow.hitRatio = 1.0f;
-      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-    }
-  }
   cudaMemsetAsync(ws.counters, 0, C_NUM * sizeof(uint32_t), st);
   cudaMemsetAsync(ws.ds_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.s_bits, 0, ((uint64_t)nwords + 4) * 4, st);
@@ -1453,11 +1435,36 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
                   ws.e_bits);
         if (forked) cudaEventRecord(ws.ev_join, sx);
       }
+      const bool legacy = path != PATH_SEG;  // lane-per-block kernels for every block
+      if (!legacy) {
+        SegArgs sg;
+        sg.text = d_text;
+        sg.n = n;
+        sg.tile_last_hs = ws.tile_last_hs;
+        sg.blocks = ws.ends;
+        sg.blocks_cap = ws.blocks_cap;
+        sg.counters = ws.counters;
+        sg.long_blocks = ws.walks;  // (the general path's walk list: unused unless the batch is flagged, and then rebuilt)
+        sg.long_cap = ws.blocks_cap;
+        sg.max_runes = ws.seg_max_runes ? std::min(ws.seg_max_runes, kSgMaxRunes) : kSgMaxRunes;
+        sg.wide_list = ws.wide_list;
+        sg.wide_cap = ws.wide_cap;
+        sg.s_bits = ws.s_bits;
+        sg.e_bits = ws.e_bits;
+        sg.dbg_R = ws.dbg_R;
+        sg.dbg_D = ws.dbg_D;
+        launch_seg(T, sg, use_hmm, g_num_sms, st);
+        g_launches.fetch_add(1);
+      }
+      // k_route / k_emit: every block, or (PATH_SEG) the blocks k_seg left
       RouteArgs ra;
       ra.text = d_text;
       ra.tile_last_hs = ws.tile_last_hs;
-      ra.blocks = ws.ends;
+      ra.blocks = legacy ? ws.ends : ws.walks;
       ra.blocks_cap = ws.blocks_cap;
+      ra.count_idx = legacy ? C_N_BLK : C_N_LONG;
+      ra.dbg_R = ws.dbg_R;
+      ra.dbg_D = ws.dbg_D;
       ra.counters = ws.counters;
       ra.path = ws.path;
       ra.wide_list = ws.wide_list;
@@ -1470,7 +1477,6 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
         wa2.text = d_text;
         wa2.n = n;
         wa2.ds_bits = ws.ds_bits;
-        wa2.blocks = ws.ends;
         wa2.wide_list = ws.wide_list;
         wa2.wide_cap = ws.wide_cap;
         wa2.counters = ws.counters;
@@ -1485,8 +1491,9 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
       PROF(3);
       EmitArgs ea;
       ea.text = d_text;
-      ea.blocks = ws.ends;
+      ea.blocks = legacy ? ws.ends : ws.walks;
       ea.blocks_cap = ws.blocks_cap;
+      ea.count_idx = legacy ? C_N_BLK : C_N_LONG;
       ea.counters = ws.counters;
       ea.path = ws.path;
       ea.bp = ws.bp;

@@ -28,6 +28,8 @@ enum Counter {
   C_N_WIDE = 6,    // Han blocks with a 4-byte rune, handed to k_wide
   C_N_DEFER = 7,   // gated non-Han tokens waiting for the tile-summary scan
   C_FLAGS = 8,     // bit0: the batch must be redone by the general pipeline
+  C_N_LONG = 9,    // Han blocks k_seg left to k_route / k_emit
+  C_CUR_SEG = 10,  // work cursor of k_seg
   C_N_BLK = 12,    // Han blocks listed by k_scan for k_route / k_emit
   C_CUR_ROUTE = 13,  // work cursors of k_route / k_emit
   C_CUR_EMIT = 14,
@@ -47,9 +49,6 @@ struct Workspace {
   // side stream for the tile-summary scan (forked after k_scan, joined before the ranking)
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  // dictionary tables (one allocation): L2 access-policy window set around the pipeline
-  void* l2_base = nullptr;
-  size_t l2_bytes = 0;
   // capacity
   uint64_t cap_bytes = 0;
   uint32_t w_per_tile = 0;  // candidate weights reserved per tile
@@ -79,7 +78,10 @@ struct Workspace {
   uint32_t* tile_first_doc = nullptr;  // per rank tile: first document index with doc_off >= the tile's first byte
   uint32_t* rank_cnt = nullptr;  // per rank tile: token count, then exclusive prefix
   uint32_t* counters = nullptr;  // Counter
-  double* dbg_proba = nullptr;   // optional: selected route value per slot
+  double* dbg_proba = nullptr;   // optional: selected route value per slot (general path)
+  double* dbg_R = nullptr;       // optional: selected route value / word length per rune (streaming path)
+  uint8_t* dbg_D = nullptr;
+  uint32_t seg_max_runes = 0;    // test knob: blocks longer than this go to k_route / k_emit (0: default)
   // outputs for host-memory batches
   uint32_t* out_start = nullptr;
   uint32_t* out_end = nullptr;
@@ -96,11 +98,14 @@ void workspace_free(Workspace& ws);
 //   Token (start,end) are written doc-relative into d_start/d_end (up to cap_tokens),
 //   d_doc_tok_off[ndocs+1] gets tok_base + rank, d_n_tokens[0] the batch's token count and
 //   d_n_tokens[1] the status word.
-//   force_general: skip the fast path and run the general kernels on everything.
+//   path: PATH_DEFAULT k_scan -> k_route -> k_emit (lane per block); PATH_GENERAL skip the fast path and run the general
+//   kernels on everything; PATH_SEG k_scan -> k_seg (CTA-cooperative, shared-memory candidates; k_route / k_emit only for
+//   the blocks it leaves).
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_doc_off,
                  uint64_t ndocs, bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
                  uint64_t* d_doc_tok_off, uint64_t tok_base, uint64_t* d_n_tokens, cudaStream_t stream,
-                 bool force_general = false);
+                 int path = 0);
+enum { PATH_DEFAULT = 0, PATH_GENERAL = 1, PATH_SEG = 2 };
 
 // Second phase when d_start/d_end were NULL in run_pipeline (count first, then scatter).
 int run_scatter(Workspace& ws, uint32_t nbytes, uint64_t ndocs, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,

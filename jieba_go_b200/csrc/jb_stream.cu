@@ -454,13 +454,6 @@ int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st) {
 constexpr int kRtThreads = 128;
 constexpr int kRtQueue = 32;
 
-// 16-byte read-only load that asks L1 to keep the line (the first-rune table is the hottest data of the kernel)
-__device__ __forceinline__ uint4 ldg_keep(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-
 template <int RING, int PB>
 __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const RouteArgs A) {
   __shared__ double ring[RING][kRtThreads];
@@ -469,7 +462,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   constexpr uint32_t PPW = 32 / PB;  // path entries per word
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t nblocks = min(A.counters[C_N_BLK], A.blocks_cap);
+  const uint32_t nblocks = min(A.counters[A.count_idx], A.blocks_cap);
   if (A.counters[C_FLAGS] & 1u) return;  // the general pipeline redoes this batch
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kRtThreads / 32);
@@ -537,7 +530,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
           nr = bd.y;
           if (nr == kWideBlock) {  // ends with a 4-byte rune
             const uint32_t wi = atomicAdd(&A.counters[C_N_WIDE], 1u);
-            if (wi < A.wide_cap) A.wide_list[wi] = bi;
+            if (wi < A.wide_cap) A.wide_list[wi] = bd.x;
             else atomicOr(&A.counters[C_FLAGS], 1u);
             A.blocks[bi].y = 0;  // nothing for k_emit
           } else {
@@ -661,6 +654,10 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
         accw = pwd;
       }
       acc |= (best_d - 1u) << ((idx % PPW) * PB);
+      if (A.dbg_R) {
+        A.dbg_R[idx] = best_v;
+        A.dbg_D[idx] = (uint8_t)best_d;
+      }
       if (kq + 1u == nr) {  // first rune of the block
         if (acc) atomicOr(&A.path[accw], acc);
         acc = 0;
@@ -680,9 +677,9 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
         }
         if (!setup_pos(false)) {  // not the lead of a 3-byte rune: the lane stepped into a 4-byte Han rune -> k_wide
           const uint32_t wi = atomicAdd(&A.counters[C_N_WIDE], 1u);
-          if (wi < A.wide_cap) A.wide_list[wi] = bi;
+          if (wi < A.wide_cap) A.wide_list[wi] = A.blocks[bi].x;  // (still the block's last rune)
           else atomicOr(&A.counters[C_FLAGS], 1u);
-          A.blocks[bi].y = 0;  // nothing for k_emit (blocks[bi].x still is the block's last rune)
+          A.blocks[bi].y = 0;  // nothing for k_emit
           if (acc) atomicOr(&A.path[accw], acc);  // (path entries of the abandoned part are never read)
           acc = 0;
           accw = 0xFFFFFFFFu;
@@ -711,68 +708,6 @@ int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_
 // ==========================================================================================
 constexpr int kEmThreads = 128;
 
-struct BitAcc2 {  // token bits of one lane, flushed one 32-byte word at a time (positions only grow)
-  uint32_t* bits;
-  uint32_t w, m;
-  __device__ __forceinline__ void init(uint32_t* b) {
-    bits = b;
-    w = 0xFFFFFFFFu;
-    m = 0;
-  }
-  __device__ __forceinline__ void set(uint32_t p) {
-    const uint32_t pw = p >> 5;
-    if (pw != w) {
-      if (m) atomicOr(&bits[w], m);
-      w = pw;
-      m = 0;
-    }
-    m |= 1u << (p & 31);
-  }
-  __device__ __forceinline__ void set_word(uint32_t pw, uint32_t x) {
-    if (!x) return;
-    if (pw != w) {
-      if (m) atomicOr(&bits[w], m);
-      w = pw;
-      m = 0;
-    }
-    m |= x;
-  }
-  // bit j of x -> position p + j (x spans at most 48 bits)
-  __device__ __forceinline__ void set_span(uint32_t p, unsigned long long x) {
-    const uint32_t sh = p & 31u, pw = p >> 5;
-    const unsigned long long lo = x << sh;
-    set_word(pw, (uint32_t)lo);
-    set_word(pw + 1u, (uint32_t)(lo >> 32));
-    if (sh > 16u) set_word(pw + 2u, (uint32_t)(x >> (64u - sh)));
-  }
-  __device__ __forceinline__ void flush() {
-    if (m) atomicOr(&bits[w], m);
-    m = 0;
-    w = 0xFFFFFFFFu;
-  }
-};
-// bits of lo -> positions p .., bits of hi -> positions p + 48 .. (lo spans at most 48 bits, hi 24): straight to
-// the bitmap, branch-free (a run of <= 24 runes touches at most four 32-byte words)
-__device__ __forceinline__ void or_span(uint32_t* __restrict__ bits, uint32_t p, unsigned long long lo, unsigned long long hi) {
-  const uint32_t sh = p & 31u, pw = p >> 5;
-  const unsigned long long v0 = lo | (hi << 48), v1 = hi >> 16;  // the 72-bit value
-  const unsigned long long s0 = v0 << sh, s1 = (v1 << sh) | (sh ? (v0 >> (64u - sh)) : 0ull);
-  const uint32_t x0 = (uint32_t)s0, x1 = (uint32_t)(s0 >> 32), x2 = (uint32_t)s1, x3 = (uint32_t)(s1 >> 32);
-  if (x0) atomicOr(&bits[pw], x0);
-  if (x1) atomicOr(&bits[pw + 1u], x1);
-  if (x2) atomicOr(&bits[pw + 2u], x2);
-  if (x3) atomicOr(&bits[pw + 3u], x3);
-}
-// bit j of x (j < 16) -> bit 3j
-__device__ __forceinline__ unsigned long long spread3(uint32_t x16) {
-  unsigned long long x = x16 & 0xFFFFu;
-  x = (x | (x << 16)) & 0x0000FF0000FFull;
-  x = (x | (x << 8)) & 0x00F00F00F00Full;
-  x = (x | (x << 4)) & 0x0C30C30C30C3ull;
-  x = (x | (x << 2)) & 0x249249249249ull;
-  return x;
-}
-
 template <bool HMM, int PB>
 __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const EmitArgs A) {
   constexpr uint32_t PPW = 32 / PB, PMASK = (1u << PB) - 1u;
@@ -780,7 +715,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   if (A.counters[C_FLAGS] & 1u) return;
-  const uint32_t nblocks = min(A.counters[C_N_BLK], A.blocks_cap);
+  const uint32_t nblocks = min(A.counters[A.count_idx], A.blocks_cap);
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kEmThreads / 32);
   const uint32_t chunk = min(32u, max(A.min_chunk, (nblocks + nwarps - 1) / nwarps));
@@ -1047,7 +982,7 @@ __global__ void __launch_bounds__(128) k_wide(const JbTables T, const WideArgs A
   const uint32_t nw = min(A.counters[C_N_WIDE], A.wide_cap);
   const WideCtx cx{A.text, A.ds_bits, A.n};
   for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nw; wi += gridDim.x * blockDim.x) {
-    const uint32_t e = A.blocks[A.wide_list[wi]].x;  // lead byte of the block's last rune
+    const uint32_t e = A.wide_list[wi];  // lead byte of the block's last rune
     const uint32_t blk_end = e + cx.len_at(e);
     uint32_t start = e;
     for (uint32_t q; (q = w_han_before(cx, T, start)) != 0xFFFFFFFFu;) start = q;

@@ -80,7 +80,9 @@ class Tokenizer:
         if old:
             L.jb_tokenizer_destroy(old)
         if getattr(self, "_path_mode", 0):
-            L.jb_set_general_only(self._h, self._path_mode)
+            L.jb_set_path(self._h, self._path_mode)
+        if getattr(self, "_seg_max_runes", 0):
+            L.jb_set_seg_max_runes(self._h, self._seg_max_runes)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -98,8 +100,15 @@ class Tokenizer:
 
     def set_general_only(self, on):
         """Bypass the streaming fast path (the general kernels then cut every block); for tests."""
-        self._path_mode = int(on)
-        check(self._L.jb_set_general_only(self._h, self._path_mode), "jb_set_general_only")
+        self.set_path(1 if on else 0)
+
+    def set_path(self, path, seg_max_runes=0):
+        """Kernel path of the Han blocks: 0 default (k_route/k_emit), 1 general kernels, 2 k_seg (k_route/k_emit only
+        for blocks longer than 1024 runes or seg_max_runes); for tests."""
+        self._path_mode = int(path)
+        self._seg_max_runes = int(seg_max_runes)
+        check(self._L.jb_set_path(self._h, self._path_mode), "jb_set_path")
+        check(self._L.jb_set_seg_max_runes(self._h, self._seg_max_runes), "jb_set_seg_max_runes")
 
     @property
     def handle(self):
@@ -190,21 +199,16 @@ class Tokenizer:
         return dd.size
 
     def suggest_freq(self, term):
-        """suggestFreq (T:589-614)."""
-        d_size = float(self.size)
-        if d_size < 1.0:
-            d_size = 1.0
-        freq = 1.0
-        for p in self.cut(term, False):
-            pf = self.lookup(p)
-            if pf is None:
-                pf = 1
-            freq *= float(pf) / d_size
-        a = int(freq * d_size) + 1
-        b = self.lookup(term)
-        if b is None:
-            b = 1
-        return a if a > b else b
+        """suggestFreq (T:589-614): Cut(term, false) on the GPU, the arithmetic in the library (jb_dict_suggest_freq)."""
+        b = term.encode("utf-8") if isinstance(term, str) else bytes(term)
+        toks = [b[s:e] if not f else "\ufffd".encode() for s, e, f in self.cut_offsets(b, False)]
+        off = np.zeros(len(toks) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(t) for t in toks])
+        out = C.c_int64()
+        with self._lock:
+            check(self._L.jb_dict_suggest_freq(self._dict_buf, b, len(b), b"".join(toks), off.ctypes.data, len(toks), C.byref(out)),
+                  "jb_dict_suggest_freq")
+        return out.value
 
     def add_word(self, word, freq: int):
         """AddWord (T:372-379).  The reference self-deadlocks here (Lock at T:376, then addTerm locks

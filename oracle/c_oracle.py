@@ -31,7 +31,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
+    src = os.path.join(_HERE, "jieba_oracle.c")
+    if not os.path.exists(_LIB_PATH) or (os.path.exists(src) and os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)):
         build()
     L = C.CDLL(_LIB_PATH)
     L.jbo_go_log.restype = C.c_double

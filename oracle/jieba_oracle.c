@@ -22,7 +22,8 @@
  * against every data-free golden vector in tokenizer_test.go through the
  * jbo_unit_* entry points, against SURVEY.md App. D micro-KATs, and against
  * the literal Python restatement oracle/py_oracle.py on randomised inputs.
- * Vectors that need the real dict/HMM files are gated on their sha256.
+ * Vectors that need the real dict/HMM files run when JIEBA_DATA_DIR holds them with
+ * the expected sha256 (tests/test_real_data.py), and are skipped otherwise.
  * math.Log bit-level parity with a real Go toolchain is unpinned by the
  * reference itself (no test holds log bits).
  *
@@ -286,7 +287,7 @@ static int go_atoi(const uint8_t* p, size_t n, int64_t* out) {
  *           becomes a key with 0 unless present, last duplicate wins, size
  *           counts every line.
  * Lines split like bufio.Scanner (strip trailing \r).  Returns 0 on success,
- * -(line number) on a malformed line (the reference would panic/log.Fatal).
+ * -(line number) on a malformed line (the reference would panic/log.Fatal) or a negative count.
  */
 int64_t jbo_dict_load_lines(jbo_dict* d, const uint8_t* buf, uint64_t len, int mode) {
   size_t pos = 0; int64_t lineno = 0;
@@ -304,6 +305,9 @@ int64_t jbo_dict_load_lines(jbo_dict* d, const uint8_t* buf, uint64_t len, int m
     while (s2 < le && buf[s2] != ' ') s2++;
     int64_t cnt;
     if (!go_atoi(buf + s1 + 1, s2 - (s1 + 1), &cnt)) return -lineno;
+    /* Atoi takes a negative count (T:414), but then a rune can end up with no DAG edge at all (T:468-482) and Cut
+     * walks off the DAG: no behaviour to restate.  Rejected here exactly as the product does (JB_EFORMAT). */
+    if (cnt < 0) return -lineno;
     const uint8_t* w = buf + pos; size_t wl = s1 - pos;
     if (mode == 0) {
       int64_t dummy;

@@ -16,8 +16,9 @@ stubs, so the reference itself cannot run here.  This restatement is pinned
 against every data-free vector in tokenizer_test.go (TestSplitText,
 TestMaxIndexProba, TestFindDagPath, TestStateTransitionRoute, TestCutHMM,
 TestCutNonZh, TestBuildPrefixDict, TestAddWord); vectors that need the real
-data files (TestCut, TestBuildDAG, TestCutDag, TestViterbi, TestLoadHMM) are
-gated on the files' sha256.  Float-level parity of math.Log is unpinned by
+data files (TestCut, TestBuildDAG, TestCutDag, TestViterbi, TestLoadHMM) run
+when JIEBA_DATA_DIR holds the files with the expected sha256
+(tests/test_real_data.py) and are skipped otherwise.  Float-level parity of math.Log is unpinned by
 the reference (no test holds log bits); see go_log().
 
 Text is handled as `bytes` (a Go string is a byte sequence).  Tokens are
@@ -251,6 +252,19 @@ class PrefixDictionary:
         self.term_freq[term] = freq
         self.size += freq
 
+    # suggestFreq (T:589-614); pieces = tk.Cut(term, false) as byte strings
+    def suggest_freq(self, term: bytes, pieces):
+        d_size = float(self.size)
+        if d_size < 1.0:
+            d_size = 1.0
+        freq = 1.0
+        for p in pieces:
+            piece_freq = self.term_freq.get(p, 1)
+            freq *= float(piece_freq) / d_size
+        a = int(freq * d_size) + 1
+        b = self.term_freq.get(term, 1)
+        return a if a > b else b
+
     # buildDag (T:462-497); runes = list of code points of a Han block.
     def build_dag(self, runes):
         pieces = []
@@ -298,12 +312,17 @@ class PrefixDictionary:
 
 
 def _atoi(b: bytes) -> int:
-    """strconv.Atoi: optional sign + decimal digits only."""
+    """strconv.Atoi: optional sign + decimal digits only.  A negative count is refused: Atoi takes it (T:414), but a
+    rune can then have no DAG edge at all (T:468-482) and Cut walks off the DAG -- there is nothing to restate; the
+    product rejects it too (JB_EFORMAT)."""
     s = b.decode("utf-8", errors="strict")
     t = s[1:] if s[:1] in "+-" else s
     if not t or not all("0" <= ch <= "9" for ch in t):
         raise ValueError("strconv.Atoi: parsing %r: invalid syntax" % s)
-    return int(s)
+    v = int(s)
+    if v < 0:
+        raise ValueError("negative frequency %r" % s)
+    return v
 
 
 def split_dict_lines(data: bytes):
@@ -477,6 +496,14 @@ class Tokenizer:
                 result.extend(self.cut_non_zh(b, bs, be))
         return result
 
+    # AddWord (T:372-379) as the code intends it (the reference deadlocks: Lock at T:376, then addTerm locks at T:581)
+    def add_word(self, word, freq: int):
+        b = word.encode("utf-8") if isinstance(word, str) else bytes(word)
+        if freq < 1:
+            pieces = [b"\xef\xbf\xbd" if f else b[s:e] for s, e, f in self.cut(b, False)]
+            freq = self.pd.suggest_freq(b, pieces)
+        self.pd.add_term(b, freq)
+
     def cut_strings(self, text, use_hmm: bool):
         b = text.encode("utf-8") if isinstance(text, str) else bytes(text)
         return materialise(b, self.cut(b, use_hmm))
@@ -487,4 +514,56 @@ def materialise(b: bytes, tokens):
     out = []
     for s, e, fffd in tokens:
         out.append("�" if fffd else b[s:e].decode("utf-8", errors="replace"))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# encoding/gob stream holding one map[string]int (prefix_dictionary.gob, T:439-458, written by
+# gob.NewEncoder(f).Encode(m), tokenizer_test.go:704-712).  Wire format as published in the
+# encoding/gob package documentation: a stream of length-prefixed messages; a
+# message with a negative type id defines a type (skipped: key and element are the builtin
+# string / int); the value message is "type id, 0 (singleton marker), count, count x (string, int)".
+# ---------------------------------------------------------------------------
+def _gob_uint(b: bytes, i: int):
+    x = b[i]
+    if x < 128:
+        return x, i + 1
+    n = 256 - x
+    if n < 1 or n > 8 or i + 1 + n > len(b):
+        raise ValueError("gob: bad unsigned integer")
+    return int.from_bytes(b[i + 1:i + 1 + n], "big"), i + 1 + n
+
+
+def _gob_int(b: bytes, i: int):
+    u, i = _gob_uint(b, i)
+    return (~(u >> 1) if u & 1 else u >> 1), i
+
+
+def read_gob_map_string_int(data: bytes) -> dict:
+    i, out = 0, None
+    while i < len(data):
+        mlen, i = _gob_uint(data, i)
+        end = i + mlen
+        if end > len(data):
+            raise ValueError("gob: truncated message")
+        tid, j = _gob_int(data, i)
+        if tid >= 0:
+            if out is not None:
+                raise ValueError("gob: more than one value")
+            marker, j = _gob_uint(data, j)
+            if marker != 0:
+                raise ValueError("gob: expected the singleton marker")
+            count, j = _gob_uint(data, j)
+            out = {}
+            for _ in range(count):
+                kl, j = _gob_uint(data, j)
+                key = data[j:j + kl]
+                j += kl
+                val, j = _gob_int(data, j)
+                out[key] = val
+            if j != end:
+                raise ValueError("gob: malformed map payload")
+        i = end
+    if out is None:
+        raise ValueError("gob: no value")
     return out

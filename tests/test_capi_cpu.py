@@ -127,7 +127,6 @@ def test_gob_loader_roundtrip(small_synth):
     sd, _ = small_synth
     want = po.PrefixDictionary.from_lines_prefix_mode(sd.lines()).term_freq
     want = dict(want)
-    want[b"neg"] = -7
     want[b"big"] = 2 ** 40 + 123
     data = gob_encode_map_string_int(want)
     L = _capi.lib()
@@ -136,6 +135,7 @@ def test_gob_loader_roundtrip(small_synth):
     assert L.jb_dict_load_gob(C.cast(buf, C.c_void_p), len(data), C.byref(db)) == 0, L.jb_last_error()
     got, size = _dump(db)
     assert got == want and size == 0     # size is not in the gob: the reference hard-codes it (T:454)
+    assert po.read_gob_map_string_int(data) == want   # the oracle's independent reader (tests/test_real_data.py uses it)
     L.jb_dict_buf_set_size(db, 60_101_967)
     assert _dump(db)[1] == 60_101_967
     L.jb_dict_buf_free(db)
@@ -197,3 +197,90 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(_capi.JiebaB200Error) as ei:
         Tokenizer.from_dict_text("甲 1\n".encode(), 1, {"B": {}, "M": {}, "E": {}, "S": {}})
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+# ---- negative counts: rejected everywhere (include/jieba_b200.h, Limits) ---------------------------
+def test_negative_counts_are_rejected():
+    L = _capi.lib()
+    for mode in (0, 1):
+        rc, _ = _load_text("甲 5\n乙 -3 n\n".encode(), mode)
+        assert rc == -3 and b"negative" in L.jb_last_error()
+        with pytest.raises(ValueError):
+            co.Dict.from_lines("甲 5\n乙 -3 n\n", mode)
+    with pytest.raises(ValueError):
+        po.PrefixDictionary.from_lines_prefix_mode(["甲 5", "乙 -3 n"])
+    with pytest.raises(ValueError):
+        po.PrefixDictionary.from_lines_file_mode(["甲 5", "乙 -3 n"])
+    data = gob_encode_map_string_int({b"a": 1, b"neg": -7})
+    db = C.c_void_p()
+    buf = (C.c_char * len(data)).from_buffer_copy(data)
+    assert L.jb_dict_load_gob(C.cast(buf, C.c_void_p), len(data), C.byref(db)) == -3
+    rc, db = _load_text("甲 5\n".encode(), 1)
+    assert rc == 0
+    assert L.jb_dict_add_term(db, "乙".encode(), 3, -1) == -1
+    L.jb_dict_buf_free(db)
+
+
+# ---- suggestFreq (T:589-614): the library's arithmetic against the oracle's restatement ---------------
+def test_suggest_freq_matches_oracle(small_synth):
+    sd, _ = small_synth
+    L = _capi.lib()
+    rc, db = _load_text(sd.dict_txt(), 1)
+    assert rc == 0
+    pd = po.PrefixDictionary.from_lines_prefix_mode(sd.lines())
+    rng = np.random.default_rng(21)
+    words = [w for w in sd.words]
+    for trial in range(300):
+        k = int(rng.integers(1, 6))
+        pieces = [words[int(i)] for i in rng.integers(0, len(words), k)]
+        if trial % 7 == 0:
+            pieces.append("龥龥".encode())          # a piece that is not a key: counts as 1
+        term = b"".join(pieces) if trial % 3 else words[int(rng.integers(0, len(words)))]
+        off = np.zeros(len(pieces) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(x) for x in pieces])
+        out = C.c_int64()
+        assert L.jb_dict_suggest_freq(db, term, len(term), b"".join(pieces), off.ctypes.data, len(pieces), C.byref(out)) == 0
+        assert out.value == pd.suggest_freq(term, pieces), (term, pieces)
+    # an empty dictionary: size < 1 counts as 1 (T:590-593)
+    rc, e = _load_text(b"", 1)
+    out = C.c_int64()
+    off = np.array([0, 3], dtype=np.uint64)
+    assert L.jb_dict_suggest_freq(e, "甲".encode(), 3, "甲".encode(), off.ctypes.data, 1, C.byref(out)) == 0
+    assert out.value == po.PrefixDictionary().suggest_freq("甲".encode(), ["甲".encode()]) == 2
+    L.jb_dict_buf_free(db)
+    L.jb_dict_buf_free(e)
+
+
+def test_host_pool_limit_without_device():
+    L = _capi.lib()
+    assert L.jb_host_pool_limit(0) == 0       # nothing pooled yet; releases everything
+    assert L.jb_host_pool_limit(4 << 30) == 0
+
+
+# ---- the real-data harness, exercised on synthetic stand-ins ------------------------------------------
+def test_real_data_harness_mechanics(tmp_path, monkeypatch, small_synth):
+    """tests/test_real_data.py only runs where the reference's LFS files exist.  Here its locator and fixtures run on
+    synthetic files whose digests are patched in, so that the harness itself is known to work."""
+    import hashlib
+    import realdata
+    import test_real_data as trd
+    sd, emit = small_synth
+    pd = po.PrefixDictionary.from_lines_prefix_mode(sd.lines())
+    files = {"dict.txt": sd.dict_txt(), "prefix_dictionary.gob": gob_encode_map_string_int(pd.term_freq),
+             "prob_emit.json": synth.emit_json(emit)}
+    for name, data in files.items():
+        (tmp_path / name).write_bytes(data)
+    monkeypatch.setattr(kv, "REAL_SHA256", {n: hashlib.sha256(d).hexdigest() for n, d in files.items()})
+    monkeypatch.setenv("JIEBA_DATA_DIR", str(tmp_path))
+    monkeypatch.setattr(realdata, "_cache", None)
+    paths, why = realdata.locate()
+    assert why is None and set(paths) == set(files)
+    paths, emit2, gob, ptk, ctk = trd.build_oracles(paths)
+    assert gob == pd.term_freq
+    text = (sd.words[3] + sd.words[10] + "，龥".encode() + sd.words[4]).decode()
+    for hmm in (False, True):
+        assert ptk.cut_strings(text, hmm) == ctk.cut_strings(text, hmm)
+    runes = [ord(c) for c in sd.words[3].decode() + sd.words[10].decode()]
+    assert ptk.pd.build_dag(runes) == ctk.build_dag("".join(map(chr, runes)))
+    assert ptk.hmm.viterbi(runes) == ctk.hmm.viterbi("".join(map(chr, runes)))
+    monkeypatch.setattr(realdata, "_cache", None)

@@ -12,7 +12,10 @@ from helpers import c_oracle_tokenizer, emit_arrays, fuzz_docs, pack_docs  # noq
 pytestmark = pytest.mark.gpu
 
 
-PATHS = ["stream", "general"]  # default streaming fast path (k_scan/k_route/k_emit) / general kernels only
+# default streaming path (k_scan/k_route/k_emit) / k_seg (CTA-cooperative) / the same with blocks over 12 runes handed to
+# k_route + k_emit / general kernels only
+PATHS = ["stream", "seg", "seg12", "general"]
+_PATH_ARGS = {"stream": (0, 0), "seg": (2, 0), "seg12": (2, 12), "general": (1, 0)}
 
 
 def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="stream", **kw):
@@ -22,8 +25,7 @@ def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="stream", **kw):
     else:
         data = sd_or_lines.dict_txt()
     tk = Tokenizer.from_dict_text(data, mode, emit, **kw)
-    if path == "general":
-        tk.set_general_only(True)
+    tk.set_path(*_PATH_ARGS[path])
     return tk
 
 
@@ -92,10 +94,14 @@ def c_oracle_tokenizer_lines(lines, emit):
     return co.Tokenizer(co.Dict.from_lines(lines, 1), co.Hmm(emit))
 
 
-def test_cut_parallel_contract(kat_tk):
+def test_cut_parallel_contract(kat_tk, kat_lines, kat_emit):
+    from oracle import py_oracle as po
+    ora = po.Tokenizer(po.PrefixDictionary.from_lines_prefix_mode(kat_lines), po.HiddenMarkovModel(kat_emit))
     t = "乙丙，a1 乙丙甲甲甲x 乙\t丙丁!"
-    assert kat_tk.cut_parallel(t, True, 6, True) == kat_tk.cut(t, True)   # ordered=true == Cut (T:110-125)
-    assert sorted(kat_tk.cut_parallel(t, True, 6, False)) == sorted(kat_tk.cut(t, True))
+    want = ora.cut_strings(t, True)
+    assert want == ["乙丙", "，", "a1", "乙丙", "甲甲", "甲", "x", "乙", "丙丁"]
+    assert kat_tk.cut_parallel(t, True, 6, True) == want                  # ordered=true == Cut (T:110-125)
+    assert sorted(kat_tk.cut_parallel(t, True, 6, False)) == sorted(want)  # any block order (T:126-133)
 
 
 def test_invalid_utf8(kat_tk, kat_lines, kat_emit):
@@ -129,12 +135,19 @@ def test_device_dictionary_matches_term_freq(synth_pair):
     assert tk.debug_lookup("龥龥龥")[0] == 0
 
 
-def test_route_values_bit_exact(synth_pair):
-    sd, emit, tk, ora = synth_pair
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("runes", [1, 2, 7, 300, 1024, 1025, 3000])
+def test_route_values_bit_exact(small_synth, path, runes):
+    """float64 route values R[i] = maxIndexProba(dagProba[i]) (T:502-548, 565-578), bit for bit, from the kernel that
+    cuts the block on each path: k_route (`stream`; `seg` beyond 1024 runes, `seg12` beyond 12), k_seg, k_route_dp (`general`)."""
+    sd, emit = small_synth
+    tk = _gpu_tokenizer(sd, emit, 1, path=path)
+    ora = c_oracle_tokenizer(sd, emit, 1)
     text, _ = synth.make_corpus(sd, "long", 40_000, synth.SEED_BASE + 40)
-    han = text.numpy()[:9000].tobytes()  # 3000 runes, Han only
+    han = text.numpy()[:3 * runes].tobytes()  # Han only
     ge, gp = tk.debug_route(han)
     oe, op = ora.route(han)
+    assert len(ge) == runes
     assert np.array_equal(ge, oe)
     assert np.array_equal(gp.view(np.uint64), op.view(np.uint64))
 
@@ -268,7 +281,7 @@ def test_fast_path_handover_routes(medium_pair, hmm):
     docs = [_mixed_corpus(sd, rng, 150_000) for _ in range(6)]
     text, off = pack_docs(docs)
     _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 8), text, off)
-    # a 4-byte Han rune flags the whole batch for the general pipeline; results must not change
+    # a 4-byte Han rune sends its block to k_wide; results must not change
     docs2 = docs[:2] + ["甲\U00020000乙".encode() + docs[2]] + docs[3:]
     text, off = pack_docs(docs2)
     _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 8), text, off)
@@ -431,3 +444,74 @@ def test_list_overflow_falls_back_to_general_kernels(small_synth, hmm):
         _assert_same(tk.cut_batch(t, off, hmm), ora.cut_batch(t, off, hmm, 4), t, off)
     text, off = pack_docs(docs)
     _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 4), text, off)
+
+
+# ---- the benchmark dictionary (349k words) at a size the oracle still finishes in seconds ---------------------
+@pytest.fixture(scope="module")
+def bench_pair():
+    sd = synth.make_dictionary(n_words=349_000, seed=synth.SEED_BASE)
+    emit = synth.make_emit(sd)
+    return sd, emit, _gpu_tokenizer(sd, emit), c_oracle_tokenizer(sd, emit)
+
+
+@pytest.mark.parametrize("kind,hmm", [("oov", True), ("long", True), ("freq", False)])
+def test_benchmark_dictionary_corpora(bench_pair, kind, hmm):
+    """BASELINE configs 3 / 4 / 2 with the dictionary bench.py uses, 64 MB each (several 16 MiB+ device sub-batches)."""
+    from oracle import c_oracle as co
+    sd, emit, tk, ora = bench_pair
+    text, doc_off = synth.make_corpus(sd, kind, 64_000_000, synth.SEED_BASE + {"freq": 2, "oov": 3, "long": 4}[kind])
+    t = text.numpy()
+    off = doc_off.numpy().astype(np.uint64)
+    _assert_same(tk.cut_batch(t, off, hmm), ora.cut_batch(t, off, hmm, co.num_procs()), t, off)
+
+
+# ---- AddWord with freq < 1: suggestFreq (T:372-379, 589-614) ---------------------------------------------------
+def test_add_word_suggested_frequency(small_synth):
+    from oracle import py_oracle as po
+    sd, emit = small_synth
+    tk = _gpu_tokenizer(sd, emit)
+    ora = po.Tokenizer(po.PrefixDictionary.from_lines_prefix_mode(sd.lines()), po.HiddenMarkovModel(emit))
+    rng = np.random.default_rng(41)
+    words = [w.decode() for w in sd.words if all(0x4E00 <= ord(c) <= 0x9FA5 for c in w.decode())]
+    for trial in range(12):
+        new = "".join(words[int(i)] for i in rng.integers(0, len(words), int(rng.integers(2, 4))))
+        if trial % 4 == 3:
+            new = words[int(rng.integers(0, len(words)))]   # an existing word: its count may only grow
+        nb = new.encode()
+        assert tk.suggest_freq(new) == ora.pd.suggest_freq(nb, [nb[s:e] for s, e, _ in ora.cut(nb, False)])
+        tk.add_word(new, 0)
+        ora.add_word(new, 0)
+        assert tk.lookup(new) == ora.pd.term_freq[new.encode()] and tk.size == ora.pd.size
+        ctx = words[int(rng.integers(0, len(words)))] + new + "，" + new + words[int(rng.integers(0, len(words)))]
+        for hmm in (False, True):
+            assert tk.cut(ctx, hmm) == ora.cut_strings(ctx, hmm)
+
+
+# ---- jb_cut_device from two streams at once: one workspace, serialised on the device ---------------------------
+def test_device_api_two_streams(medium_pair):
+    import torch
+    sd, emit, tk, ora = medium_pair
+    outs = []
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    wants = []
+    for i, s in enumerate(streams * 3):       # six calls, alternating streams, different sizes (the workspace grows once)
+        text, doc_off = synth.make_corpus(sd, "oov" if i % 2 else "freq", 400_000 + 300_000 * (i % 3), synth.SEED_BASE + 80 + i)
+        t = text.numpy()
+        off = doc_off.numpy().astype(np.uint64)
+        wants.append(ora.cut_batch(t, off, True, 8))
+        dt, ddo = text.cuda(), doc_off.cuda()
+        cap = len(wants[-1][0]) + 10
+        bufs = (torch.zeros(cap, dtype=torch.int32, device="cuda"), torch.zeros(cap, dtype=torch.int32, device="cuda"),
+                torch.zeros(off.size, dtype=torch.int64, device="cuda"), torch.zeros(2, dtype=torch.int64, device="cuda"), dt, ddo)
+        outs.append(bufs)
+    torch.cuda.synchronize()
+    for i, s in enumerate(streams * 3):       # no synchronisation between the calls
+        d_start, d_end, d_dto, d_nt, dt, ddo = outs[i]
+        with torch.cuda.stream(s):
+            tk.cut_device(dt, ddo, True, d_start, d_end, d_dto, d_nt, stream=s)
+    torch.cuda.synchronize()
+    for (d_start, d_end, d_dto, d_nt, _, _), (os_, oe, _, od) in zip(outs, wants):
+        assert d_nt.tolist() == [len(os_), 0]
+        assert np.array_equal(d_start[:len(os_)].cpu().numpy().astype(np.uint32), os_)
+        assert np.array_equal(d_end[:len(os_)].cpu().numpy().astype(np.uint32), oe)
+        assert np.array_equal(d_dto.cpu().numpy().astype(np.uint64), od)
