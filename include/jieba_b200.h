@@ -157,10 +157,44 @@ int jb_cut(jb_tokenizer* tk, const uint8_t* text, uint64_t nbytes, int use_hmm, 
 int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs,
                  int use_hmm, jb_result** out);
 uint64_t jb_result_num_tokens(const jb_result* r);
-const uint32_t* jb_result_start(const jb_result* r);        /* doc-relative byte offset */
+const uint32_t* jb_result_start(const jb_result* r);        /* doc-relative byte offset (NULL for a bitmap result) */
 const uint32_t* jb_result_end(const jb_result* r);          /* exclusive */
 const uint64_t* jb_result_doc_tok_off(const jb_result* r);  /* ndocs+1 entries */
 void jb_result_free(jb_result* r);
+
+/*
+ * The same batched Cut with the result as two BITMAPS over the batch's bytes (position 0 = doc_off[0]): bit p of the
+ * start bitmap <=> a token starts at byte p, bit p of the end bitmap <=> a token ends WITH byte p (tokens never overlap,
+ * so the k-th start bit pairs with the k-th end bit; documents never share a token).  2 bits per input byte travel
+ * back over PCIe instead of 8 bytes per token (about 1.1 bytes per input byte): end to end this call is bound by the
+ * copy of the text TO the device.  A Go / C caller walks the bits (count-trailing-zeros) where it would have walked
+ * the arrays; jb_result_expand materialises the arrays of jb_cut_batch on `nthreads` host threads.
+ * doc_tok_off is as in jb_cut_batch.  (ndocs+1 offsets are kept with the result.)
+ */
+int jb_cut_batch_bits(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs,
+                      int use_hmm, jb_result** out);
+const uint32_t* jb_result_start_bits(const jb_result* r);   /* (num_bytes + 31) / 32 words (NULL for an array result) */
+const uint32_t* jb_result_end_bits(const jb_result* r);
+uint64_t jb_result_num_bytes(const jb_result* r);           /* doc_off[ndocs] - doc_off[0] */
+int jb_result_expand(const jb_result* r, uint32_t* start, uint32_t* end, int nthreads); /* num_tokens entries each */
+/*
+ * One batch over SEVERAL devices (the CutParallel contract T:81-135 at the scale of a box): tks[i] is a tokenizer
+ * created on device i with the same dictionary; documents are split into n contiguous ranges of about equal bytes, one
+ * host thread + copy/compute pipeline per device, every device writing its own part of ONE bitmap result in document
+ * order -- no collective and no concatenation pass.  Host threads are bound to their device's NUMA node when the
+ * process may run there (jb_bind_thread_to_device).
+ */
+int jb_cut_batch_multi(jb_tokenizer* const* tks, int n_tokenizers, const uint8_t* text, const uint64_t* doc_off,
+                       uint64_t ndocs, int use_hmm, jb_result** out);
+/* Binds the calling thread to the CPUs local to `device` (sysfs numa_node / local_cpulist of its PCI function), so that
+ * the pinned buffers it allocates and the copies it drives stay on that socket.  Returns the NUMA node or -1. */
+int jb_bind_thread_to_device(int device);
+/*
+ * INPUT MEMORY.  text may be any host memory.  Page-locked memory (cudaMallocHost / cudaHostRegister) is read by the
+ * copy engine directly.  PAGEABLE memory -- a Go string, malloc, a numpy array -- is detected and staged: host threads
+ * copy each sub-batch into a pinned buffer of the pipeline slot (3 x max_batch_bytes of pinned memory per concurrent
+ * call) while the previous sub-batches are being cut; this costs one extra pass over the text in host memory.
+ */
 
 /*
  * Device-resident Cut: text, doc_off (uint64, ndocs+1) and all outputs are DEVICE pointers on
@@ -173,6 +207,10 @@ void jb_result_free(jb_result* r);
 int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, const uint64_t* d_doc_off,
                   uint64_t ndocs, int use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
                   uint64_t* d_doc_tok_off, uint64_t* d_n_tokens, void* cuda_stream);
+/* jb_cut_device with the bitmap result: d_start_bits / d_end_bits hold (nbytes / 32 + 8) words each (device memory) */
+int jb_cut_device_bits(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, const uint64_t* d_doc_off,
+                       uint64_t ndocs, int use_hmm, uint32_t* d_start_bits, uint32_t* d_end_bits,
+                       uint64_t* d_doc_tok_off, uint64_t* d_n_tokens, void* cuda_stream);
 int jb_set_candidates_per_slot(jb_tokenizer* tk, double per_slot);
 /* 1: bypass the streaming fast path and run the general kernels on every block (testing) */
 int jb_set_general_only(jb_tokenizer* tk, int on);

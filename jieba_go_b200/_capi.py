@@ -62,6 +62,14 @@ SYMBOLS = {
     "jb_result_end": (C.POINTER(C.c_uint32), [_P]),
     "jb_result_doc_tok_off": (C.POINTER(C.c_uint64), [_P]),
     "jb_result_free": (None, [_P]),
+    "jb_cut_batch_bits": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int, _PP]),
+    "jb_cut_batch_multi": (C.c_int, [_PP, C.c_int, _P, _P, C.c_uint64, C.c_int, _PP]),
+    "jb_result_start_bits": (C.POINTER(C.c_uint32), [_P]),
+    "jb_result_end_bits": (C.POINTER(C.c_uint32), [_P]),
+    "jb_result_num_bytes": (C.c_uint64, [_P]),
+    "jb_result_expand": (C.c_int, [_P, _P, _P, C.c_int]),
+    "jb_bind_thread_to_device": (C.c_int, [C.c_int]),
+    "jb_cut_device_bits": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P, _P, _P, _P, _P]),
     "jb_cut_device": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P, _P, C.c_uint64, _P, _P, _P]),
     "jb_set_candidates_per_slot": (C.c_int, [_P, C.c_double]),
     "jb_set_general_only": (C.c_int, [_P, C.c_int]),

@@ -6,9 +6,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <ctype.h>
+#include <sched.h>
+
 #include <algorithm>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/jieba_b200.h"
@@ -42,6 +46,8 @@ struct WsSlot {
   uint64_t* h_cnt = nullptr;  // pinned: token count + status of the batch in flight
   uint64_t* h_doc = nullptr;  // pinned staging of the batch's document offsets (the caller's array is pageable:
   uint64_t h_doc_cap = 0;     //  an async copy from it would block the host until the stream gets there)
+  uint8_t* h_text = nullptr;  // pinned staging of the batch's text, only when the caller's text is pageable
+  uint64_t h_text_cap = 0;
 };
 
 struct jb_tokenizer {
@@ -65,12 +71,18 @@ struct jb_tokenizer {
 };
 
 struct jb_result {
-  uint64_t n_tokens = 0, ndocs = 0;
+  uint64_t n_tokens = 0, ndocs = 0, nbytes = 0;
+  // (start, end) arrays (jb_cut, jb_cut_batch)
   uint32_t* start = nullptr;
   uint32_t* end = nullptr;
-  uint64_t* doc_tok = nullptr;
   uint64_t cap = 0;
-  size_t start_bytes = 0, end_bytes = 0, doc_bytes = 0;
+  // token bitmaps over the batch's bytes (jb_cut_batch_bits, jb_cut_batch_multi) + the documents' offsets (for jb_result_expand)
+  uint32_t* sbits = nullptr;
+  uint32_t* ebits = nullptr;
+  uint64_t nwords = 0;
+  std::vector<uint64_t> doc_off;
+  uint64_t* doc_tok = nullptr;
+  size_t start_bytes = 0, end_bytes = 0, sbits_bytes = 0, ebits_bytes = 0, doc_bytes = 0;
 };
 
 // Process-wide pool of pinned host buffers for results: cudaMallocHost of hundreds of MB costs more
@@ -390,6 +402,7 @@ static void free_slot(WsSlot* s) {
   if (s->ev) cudaEventDestroy(s->ev);
   if (s->h_cnt) cudaFreeHost(s->h_cnt);
   if (s->h_doc) cudaFreeHost(s->h_doc);
+  if (s->h_text) cudaFreeHost(s->h_text);
 }
 
 void jb_tokenizer_destroy(jb_tokenizer* tk) {
@@ -415,12 +428,70 @@ uint64_t jb_result_num_tokens(const jb_result* r) { return r->n_tokens; }
 const uint32_t* jb_result_start(const jb_result* r) { return r->start; }
 const uint32_t* jb_result_end(const jb_result* r) { return r->end; }
 const uint64_t* jb_result_doc_tok_off(const jb_result* r) { return r->doc_tok; }
+const uint32_t* jb_result_start_bits(const jb_result* r) { return r->sbits; }
+const uint32_t* jb_result_end_bits(const jb_result* r) { return r->ebits; }
+uint64_t jb_result_num_bytes(const jb_result* r) { return r->nbytes; }
 void jb_result_free(jb_result* r) {
   if (!r) return;
   pin_free(r->start, r->start_bytes);
   pin_free(r->end, r->end_bytes);
+  pin_free(r->sbits, r->sbits_bytes);
+  pin_free(r->ebits, r->ebits_bytes);
   pin_free(r->doc_tok, r->doc_bytes);
   delete r;
+}
+
+// Bitmap result -> (start, end) arrays, doc-relative, in document order: what jb_cut_batch returns directly.
+// Documents are independent, so `nthreads` host threads take contiguous ranges of them.
+int jb_result_expand(const jb_result* r, uint32_t* start, uint32_t* end, int nthreads) {
+  if (!r || !r->sbits || !r->ebits || (r->n_tokens && (!start || !end))) return fail(JB_EINVAL, "not a bitmap result, or null output");
+  const uint64_t nd = r->ndocs;
+  if (nthreads < 1) nthreads = 1;
+  if ((uint64_t)nthreads > nd) nthreads = nd ? (int)nd : 1;
+  auto work = [&](uint64_t d0, uint64_t d1) {
+    // bit positions of one bitmap between two byte offsets -> out[], relative to `rel`, plus `add`
+    auto unpack = [](const uint32_t* bits, uint64_t lo, uint64_t hi, uint64_t rel, uint32_t add, uint32_t* out) -> uint32_t* {
+      if (lo >= hi) return out;
+      uint64_t w = lo >> 5;
+      const uint64_t wl = (hi - 1) >> 5;
+      uint32_t m = bits[w] & (0xFFFFFFFFu << (lo & 31));
+      for (;;) {
+        if (w == wl && (hi & 31)) m &= (1u << (hi & 31)) - 1u;
+        const uint32_t base = (uint32_t)((w << 5) - rel) + add;
+        while (m) {
+          *out++ = base + (uint32_t)__builtin_ctz(m);
+          m &= m - 1;
+        }
+        if (w == wl) break;
+        m = bits[++w];
+      }
+      return out;
+    };
+    for (uint64_t d = d0; d < d1; d++) {
+      const uint64_t lo = r->doc_off[d], hi = r->doc_off[d + 1], t0 = r->doc_tok[d];
+      unpack(r->sbits, lo, hi, lo, 0u, start + t0);
+      unpack(r->ebits, lo, hi, lo, 1u, end + t0);  // end is exclusive: the bit sits on the token's last byte
+    }
+  };
+  if (nthreads == 1) {
+    work(0, nd);
+    return JB_OK;
+  }
+  // ranges balanced by bytes
+  std::vector<std::thread> th;
+  const uint64_t total = r->nbytes;
+  uint64_t d = 0;
+  for (int t = 0; t < nthreads; t++) {
+    const uint64_t target = total / nthreads * (t + 1);
+    uint64_t e = d;
+    if (t == nthreads - 1) e = nd;
+    else
+      while (e < nd && r->doc_off[e + 1] <= target) e++;
+    if (e > d) th.emplace_back(work, d, e);
+    d = e;
+  }
+  for (auto& x : th) x.join();
+  return JB_OK;
 }
 
 static int result_grow(jb_result* r, uint64_t need) {
@@ -470,41 +541,73 @@ static WsSlot* take_slot(jb_tokenizer* tk) {
   return slot;
 }
 
-// Batched Cut over host memory.  Sub-batches of whole documents (<= max_batch bytes) flow through a
-// pipeline of kPipeSlots streams / workspaces: the H2D copies of the next batches and the D2H copy of the
-// previous one overlap the kernels of batch i (separate copy engines).
-int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm, jb_result** out) {
-  if (!tk || !out || !doc_off || (ndocs && doc_off[ndocs] > doc_off[0] && !text)) return fail(JB_EINVAL, "null argument");
-  for (uint64_t d = 0; d < ndocs; d++) {
-    if (doc_off[d + 1] < doc_off[d]) return fail(JB_EINVAL, "doc_off must be non-decreasing");
-    if (doc_off[d + 1] - doc_off[d] > tk->max_batch)
-      return fail(JB_ELIMIT, "a document exceeds the device batch size (raise jb_options.max_batch_bytes; hard limit 2 GiB)");
+// Is this host pointer something the copy engines can read directly (cudaMallocHost / cudaHostRegister / managed)?
+// A Go string, a numpy array, malloc'd memory are PAGEABLE: cudaMemcpyAsync from them is staged by the driver through
+// its own small bounce buffer and blocks the calling thread; such input goes through the slots' pinned staging buffers.
+static bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
   }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeDevice;
+}
+
+static void parallel_memcpy(void* dst, const void* src, size_t n, int nthreads) {
+  if (nthreads <= 1 || n < (8u << 20)) {
+    memcpy(dst, src, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (n / nthreads + 4095) & ~(size_t)4095;
+  for (size_t o = per; o < n; o += per) th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, std::min(per, n - o)); });
+  memcpy(dst, src, std::min(per, n));
+  for (auto& x : th) x.join();
+}
+
+struct EdgeWord {  // a bitmap word shared by two sub-batches / shards: OR-ed into the result after every copy has landed
+  uint64_t word;
+  uint32_t s, e;
+};
+
+// Cut the documents [d_lo, d_hi) of a host-memory batch on tk's device.  Sub-batches of whole documents
+// (<= max_batch bytes) flow through a pipeline of kPipeSlots streams / workspaces: the H2D copies of the next
+// batches and the D2H copy of the previous one overlap the kernels of batch i (separate copy engines).
+//   bits == false: (start,end) arrays appended to res (one range per result only)
+//   bits == true : token bitmaps written straight into res->sbits / ebits at the range's GLOBAL bit positions
+//                  (position 0 = doc_off[0]), doc_tok relative to the range; *n_tok_out = tokens of the range.
+//                  Words that straddle two sub-batches come back in `edges`.
+static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t d_lo, uint64_t d_hi, int use_hmm, bool bits,
+                     jb_result* res, std::vector<EdgeWord>* edges, uint64_t* n_tok_out) {
   CUDA_TRY(cudaSetDevice(tk->device));  // (nothing acquired yet)
+  const uint64_t g0 = doc_off[0];
   // plan: greedy batches of whole documents
   struct Chunk {
     uint64_t d0, d1, nb, base;
     uint64_t nt;
+    uint32_t pad;
   };
   std::vector<Chunk> chunks;
   // Sub-batch sizes ramp up from 16 MiB and down again towards the end: the first H2D copy and the last D2H copy
   // are the only ones no kernel hides, so they are kept short (a document larger than the target still goes whole).
   const uint64_t kRamp0 = 16ull << 20;
   uint64_t ramp = kRamp0;
-  for (uint64_t d0 = 0; d0 < ndocs;) {
-    const uint64_t remaining = doc_off[ndocs] - doc_off[d0];
+  for (uint64_t d0 = d_lo; d0 < d_hi;) {
+    const uint64_t remaining = doc_off[d_hi] - doc_off[d0];
     const uint64_t target = std::min<uint64_t>(tk->max_batch, std::min<uint64_t>(ramp, std::max<uint64_t>(kRamp0, remaining / 2)));
     uint64_t d1 = d0 + 1;
-    while (d1 < ndocs && doc_off[d1 + 1] - doc_off[d0] <= target) d1++;
-    chunks.push_back(Chunk{d0, d1, doc_off[d1] - doc_off[d0], 0, 0});
+    while (d1 < d_hi && doc_off[d1 + 1] - doc_off[d0] <= target) d1++;
+    chunks.push_back(Chunk{d0, d1, doc_off[d1] - doc_off[d0], 0, 0, bits ? (uint32_t)((doc_off[d0] - g0) & 31) : 0u});
     d0 = d1;
     ramp = std::min<uint64_t>(ramp * 2, tk->max_batch);
   }
+  const bool pageable = d_hi > d_lo && doc_off[d_hi] > doc_off[d_lo] && !host_ptr_is_pinned(text + doc_off[d_lo]);
+  const int copy_threads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 4));
   constexpr size_t kPipeSlots = 3;  // measured: 5 slots are slower (31.9 vs 28.1 ms per GB end to end)
   WsSlot* slots[kPipeSlots] = {};
   for (size_t i = 0; i < kPipeSlots && i < std::max<size_t>(chunks.size(), 1); i++) slots[i] = take_slot(tk);
-  jb_result* res = new jb_result();
-  res->ndocs = ndocs;
+  uint32_t* h_edge = nullptr;  // pinned: first bitmap word (start, end) of every sub-batch
+  size_t h_edge_bytes = 0;
   auto done = [&](int code) {
     for (WsSlot* sl : slots)
       if (sl) cudaStreamSynchronize(sl->stream);
@@ -513,22 +616,21 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
       for (WsSlot* sl : slots)
         if (sl) tk->free_ws.push_back(sl);
     }
-    if (code != JB_OK) {
-      jb_result_free(res);
-      return code;
-    }
-    *out = res;
-    return (int)JB_OK;
+    pin_free(h_edge, h_edge_bytes);
+    return code;
   };
   for (size_t i = 0; i < kPipeSlots && i < std::max<size_t>(chunks.size(), 1); i++)
     if (!slots[i]) return done(fail(JB_ECUDA, "stream / event creation failed"));
-  res->doc_tok = (uint64_t*)pin_alloc((ndocs + 1) * 8, &res->doc_bytes);
-  if (!res->doc_tok) return done(fail(JB_ENOMEM, "pinned host allocation failed"));
-  res->doc_tok[0] = 0;
   double wps = tk->w_per_slot;
-  const uint64_t total_bytes = ndocs ? doc_off[ndocs] - doc_off[0] : 0;
-  int rc = result_grow(res, total_bytes / 6 + 1024);  // typical: one token per ~7 bytes; grows if needed
-  if (rc != JB_OK) return done(rc);
+  const uint64_t total_bytes = d_hi > d_lo ? doc_off[d_hi] - doc_off[d_lo] : 0;
+  int rc = JB_OK;
+  if (bits) {
+    h_edge = (uint32_t*)pin_alloc(chunks.size() * 8 + 8, &h_edge_bytes);
+    if (!h_edge) return done(fail(JB_ENOMEM, "pinned host allocation failed"));
+  } else {
+    rc = result_grow(res, total_bytes / 6 + 1024);  // typical: one token per ~7 bytes; grows if needed
+    if (rc != JB_OK) return done(rc);
+  }
 
   // stage A: copy in, run the whole pipeline (scatter into the slot's device buffers), copy the count out
   const bool timeline = getenv("JB_TIMELINE") != nullptr;
@@ -544,22 +646,39 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     Chunk& c = chunks[ci];
     WsSlot* sl = slots[ci % kPipeSlots];
     cudaStream_t st = sl->stream;
-    int r = workspace_reserve(sl->ws, c.nb, c.d1 - c.d0, wps, true);
+    const uint64_t dev_bytes = c.nb + c.pad;
+    int r = workspace_reserve(sl->ws, dev_bytes, c.d1 - c.d0, wps, true);
     if (r != JB_OK) return fail(r, "device workspace allocation failed");
     Workspace& ws = sl->ws;
     ws.seg_max_runes = tk->seg_max_runes;
-    const uint64_t want = c.nb / 4 + 4096;
-    if (ws.out_cap < want) {
-      if (ws.out_start) cudaFree(ws.out_start);
-      if (ws.out_end) cudaFree(ws.out_end);
-      ws.out_start = ws.out_end = nullptr;
-      ws.out_cap = 0;
-      if (cudaMalloc(&ws.out_start, want * 4) != cudaSuccess || cudaMalloc(&ws.out_end, want * 4) != cudaSuccess)
-        return fail(JB_ENOMEM, "device output allocation failed");
-      ws.out_cap = want;
+    if (!bits) {
+      const uint64_t want = c.nb / 4 + 4096;
+      if (ws.out_cap < want) {
+        if (ws.out_start) cudaFree(ws.out_start);
+        if (ws.out_end) cudaFree(ws.out_end);
+        ws.out_start = ws.out_end = nullptr;
+        ws.out_cap = 0;
+        if (cudaMalloc(&ws.out_start, want * 4) != cudaSuccess || cudaMalloc(&ws.out_end, want * 4) != cudaSuccess)
+          return fail(JB_ENOMEM, "device output allocation failed");
+        ws.out_cap = want;
+      }
     }
     tl_rec(ci, 0, st);
-    if (c.nb) CUDA_TRY(cudaMemcpyAsync(ws.text, text + doc_off[c.d0], c.nb, cudaMemcpyHostToDevice, st));
+    const uint8_t* src = text + doc_off[c.d0];
+    if (c.nb && pageable) {  // through the slot's pinned staging buffer (the slot's previous batch is complete)
+      if (sl->h_text_cap < c.nb) {
+        if (sl->h_text) cudaFreeHost(sl->h_text);
+        sl->h_text = nullptr;
+        sl->h_text_cap = 0;
+        const uint64_t ncap = std::max<uint64_t>(c.nb, std::min<uint64_t>(tk->max_batch, 2 * c.nb));
+        if (cudaMallocHost(&sl->h_text, ncap) != cudaSuccess) return fail(JB_ENOMEM, "pinned staging allocation failed");
+        sl->h_text_cap = ncap;
+      }
+      parallel_memcpy(sl->h_text, src, c.nb, copy_threads);
+      src = sl->h_text;
+    }
+    if (c.pad) CUDA_TRY(cudaMemsetAsync(ws.text, ' ', 32, st));  // the bytes before the first document: spaces (no tokens)
+    if (c.nb) CUDA_TRY(cudaMemcpyAsync(ws.text + c.pad, src, c.nb, cudaMemcpyHostToDevice, st));
     const uint64_t nd1 = c.d1 - c.d0 + 1;
     if (sl->h_doc_cap < nd1) {
       if (sl->h_doc) cudaFreeHost(sl->h_doc);
@@ -572,11 +691,37 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
     memcpy(sl->h_doc, doc_off + c.d0, nd1 * 8);  // (the slot's previous batch is complete: its stream was synchronised)
     CUDA_TRY(cudaMemcpyAsync(ws.doc_off64, sl->h_doc, nd1 * 8, cudaMemcpyHostToDevice, st));
     tl_rec(ci, 1, st);
-    r = run_pipeline(tk->T, ws, ws.text, (uint32_t)c.nb, ws.doc_off64, c.d1 - c.d0, use_hmm != 0, ws.out_start, ws.out_end, ws.out_cap,
-                     ws.out_doc_tok, 0, ws.out_ntok, st, tk->path);
+    PipeOut po;
+    po.d_doc_tok_off = ws.out_doc_tok;
+    po.d_n_tokens = ws.out_ntok;
+    if (bits) {
+      po.bits_only = true;
+      po.pos0 = c.pad;
+    } else {
+      po.d_start = ws.out_start;
+      po.d_end = ws.out_end;
+      po.cap_tokens = ws.out_cap;
+    }
+    r = run_pipeline(tk->T, ws, ws.text, (uint32_t)dev_bytes, ws.doc_off64, c.d1 - c.d0, use_hmm != 0, po, st, tk->path);
     if (r != JB_OK) return fail(r, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     tl_rec(ci, 2, st);
     CUDA_TRY(cudaMemcpyAsync(sl->h_cnt, ws.out_ntok, 16, cudaMemcpyDeviceToHost, st));
+    if (bits) {
+      // the result's size is known in advance: everything goes back without waiting for the count.  Word 0 of a
+      // sub-batch that does not start on a 32-byte boundary also holds the previous sub-batch's last tokens: it
+      // travels separately and is OR-ed in at the end.
+      const uint64_t nw = (dev_bytes + 31) / 32, gw0 = (doc_off[c.d0] - g0 - c.pad) / 32, skip = c.pad ? 1 : 0;
+      if (c.pad) {
+        CUDA_TRY(cudaMemcpyAsync(h_edge + 2 * ci, ws.s_bits, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_edge + 2 * ci + 1, ws.e_bits, 4, cudaMemcpyDeviceToHost, st));
+      }
+      if (nw > skip) {
+        CUDA_TRY(cudaMemcpyAsync(res->sbits + gw0 + skip, ws.s_bits + skip, (nw - skip) * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(res->ebits + gw0 + skip, ws.e_bits + skip, (nw - skip) * 4, cudaMemcpyDeviceToHost, st));
+      }
+      CUDA_TRY(cudaMemcpyAsync(res->doc_tok + c.d0, ws.out_doc_tok, (c.d1 - c.d0) * 8, cudaMemcpyDeviceToHost, st));
+      tl_rec(ci, 3, st);
+    }
     CUDA_TRY(cudaEventRecord(sl->ev, st));
     return JB_OK;
   };
@@ -591,7 +736,7 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
         Chunk& pc = chunks[next_enq - kPipeSlots];
         cudaError_t se = cudaStreamSynchronize(slots[next_enq % kPipeSlots]->stream);
         if (se != cudaSuccess) return done(fail(JB_ECUDA, std::string("copy failed: ") + cudaGetErrorString(se)));
-        // (doc_tok of that batch is final on the host now: make it absolute)
+        // (doc_tok of that batch is final on the host now: make it relative to the range)
         for (uint64_t d = pc.d0; d < pc.d1; d++) res->doc_tok[d] += pc.base;
         pc.base = 0;
       }
@@ -613,41 +758,44 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
       }
       break;
     }
+    if (sl->h_cnt[1]) return done(fail(JB_ECUDA, "the device pipeline reported status " + std::to_string(sl->h_cnt[1])));
     const uint64_t nt = sl->h_cnt[0];
     c.nt = nt;
     c.base = base;
-    if (nt > ws.out_cap) {  // more tokens than the output guess: enlarge and scatter again (the bitmaps are still there)
-      uint64_t ncap = nt + nt / 8 + 1024;
-      cudaFree(ws.out_start);
-      cudaFree(ws.out_end);
-      ws.out_start = ws.out_end = nullptr;
-      ws.out_cap = 0;
-      if (cudaMalloc(&ws.out_start, ncap * 4) != cudaSuccess || cudaMalloc(&ws.out_end, ncap * 4) != cudaSuccess)
-        return done(fail(JB_ENOMEM, "device output allocation failed"));
-      ws.out_cap = ncap;
-      rc = run_scatter(ws, (uint32_t)c.nb, c.d1 - c.d0, ws.out_start, ws.out_end, ws.out_cap, ws.out_doc_tok, 0, st);
-      if (rc != JB_OK) return done(fail(rc, "scatter launch failed"));
+    if (!bits) {
+      if (nt > ws.out_cap) {  // more tokens than the output guess: enlarge and scatter again (the bitmaps are still there)
+        uint64_t ncap = nt + nt / 8 + 1024;
+        cudaFree(ws.out_start);
+        cudaFree(ws.out_end);
+        ws.out_start = ws.out_end = nullptr;
+        ws.out_cap = 0;
+        if (cudaMalloc(&ws.out_start, ncap * 4) != cudaSuccess || cudaMalloc(&ws.out_end, ncap * 4) != cudaSuccess)
+          return done(fail(JB_ENOMEM, "device output allocation failed"));
+        ws.out_cap = ncap;
+        rc = run_scatter(ws, (uint32_t)c.nb, c.d1 - c.d0, ws.out_start, ws.out_end, ws.out_cap, ws.out_doc_tok, 0, st);
+        if (rc != JB_OK) return done(fail(rc, "scatter launch failed"));
+      }
+      if (base + nt > res->cap) {  // the pinned result must move: no copy may be in flight into the old one
+        for (WsSlot* s2 : slots)
+          if (s2 && s2 != sl) cudaStreamSynchronize(s2->stream);
+        cudaStreamSynchronize(st);
+        res->n_tokens = base;
+        rc = result_grow(res, base + nt + (total_bytes - (doc_off[c.d1] - doc_off[d_lo])) / 6);
+        if (rc != JB_OK) return done(rc);
+      }
+      // (an error here must still give the slots back: through done())
+      cudaError_t ce = cudaSuccess;
+      if (nt) {
+        ce = cudaMemcpyAsync(res->start + base, ws.out_start, nt * 4, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(res->end + base, ws.out_end, nt * 4, cudaMemcpyDeviceToHost, st);
+      }
+      // (the batch's last entry belongs to the next batch's first document: copy d1-d0 entries, not one more)
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(res->doc_tok + c.d0, ws.out_doc_tok, (c.d1 - c.d0) * 8, cudaMemcpyDeviceToHost, st);
+      if (ce != cudaSuccess) return done(fail(JB_ECUDA, std::string("copy of the result failed: ") + cudaGetErrorString(ce)));
+      tl_rec(ci, 3, st);
     }
-    if (base + nt > res->cap) {  // the pinned result must move: no copy may be in flight into the old one
-      for (WsSlot* s2 : slots)
-        if (s2 && s2 != sl) cudaStreamSynchronize(s2->stream);
-      cudaStreamSynchronize(st);
-      res->n_tokens = base;
-      rc = result_grow(res, base + nt + (total_bytes - (doc_off[c.d1] - doc_off[0])) / 6);
-      if (rc != JB_OK) return done(rc);
-    }
-    // (an error here must still give the slots back and free the result: through done())
-    cudaError_t ce = cudaSuccess;
-    if (nt) {
-      ce = cudaMemcpyAsync(res->start + base, ws.out_start, nt * 4, cudaMemcpyDeviceToHost, st);
-      if (ce == cudaSuccess) ce = cudaMemcpyAsync(res->end + base, ws.out_end, nt * 4, cudaMemcpyDeviceToHost, st);
-    }
-    // (the batch's last entry belongs to the next batch's first document: copy d1-d0 entries, not one more)
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(res->doc_tok + c.d0, ws.out_doc_tok, (c.d1 - c.d0) * 8, cudaMemcpyDeviceToHost, st);
-    if (ce != cudaSuccess) return done(fail(JB_ECUDA, std::string("copy of the result failed: ") + cudaGetErrorString(ce)));
-    tl_rec(ci, 3, st);
     base += nt;
-    res->n_tokens = base;
+    if (!bits) res->n_tokens = base;
   }
   for (WsSlot* sl : slots)
     if (sl) {
@@ -667,9 +815,45 @@ int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off,
   for (Chunk& c : chunks)
     if (c.base)
       for (uint64_t d = c.d0; d < c.d1; d++) res->doc_tok[d] += c.base;
-  res->n_tokens = base;
-  res->doc_tok[ndocs] = base;
+  if (bits && edges)
+    for (size_t ci = 0; ci < chunks.size(); ci++)
+      if (chunks[ci].pad) edges->push_back(EdgeWord{(doc_off[chunks[ci].d0] - g0) / 32, h_edge[2 * ci], h_edge[2 * ci + 1]});
+  *n_tok_out = base;
   return done(JB_OK);
+}
+
+static int check_batch_args(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, jb_result** out) {
+  if (!tk || !out || !doc_off || (ndocs && doc_off[ndocs] > doc_off[0] && !text)) return fail(JB_EINVAL, "null argument");
+  for (uint64_t d = 0; d < ndocs; d++) {
+    if (doc_off[d + 1] < doc_off[d]) return fail(JB_EINVAL, "doc_off must be non-decreasing");
+    if (doc_off[d + 1] - doc_off[d] > tk->max_batch)
+      return fail(JB_ELIMIT, "a document exceeds the device batch size (raise jb_options.max_batch_bytes; hard limit 2 GiB)");
+  }
+  return JB_OK;
+}
+
+int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm, jb_result** out) {
+  int rc = check_batch_args(tk, text, doc_off, ndocs, out);
+  if (rc != JB_OK) return rc;
+  jb_result* res = new jb_result();
+  res->ndocs = ndocs;
+  res->nbytes = ndocs ? doc_off[ndocs] - doc_off[0] : 0;
+  res->doc_tok = (uint64_t*)pin_alloc((ndocs + 1) * 8, &res->doc_bytes);
+  if (!res->doc_tok) {
+    jb_result_free(res);
+    return fail(JB_ENOMEM, "pinned host allocation failed");
+  }
+  res->doc_tok[0] = 0;
+  uint64_t nt = 0;
+  rc = cut_range(tk, text, doc_off, 0, ndocs, use_hmm, false, res, nullptr, &nt);
+  if (rc != JB_OK) {
+    jb_result_free(res);
+    return rc;
+  }
+  res->n_tokens = nt;
+  res->doc_tok[ndocs] = nt;
+  *out = res;
+  return JB_OK;
 }
 
 int jb_cut(jb_tokenizer* tk, const uint8_t* text, uint64_t nbytes, int use_hmm, jb_result** out) {
@@ -677,11 +861,123 @@ int jb_cut(jb_tokenizer* tk, const uint8_t* text, uint64_t nbytes, int use_hmm, 
   return jb_cut_batch(tk, text, off, 1, use_hmm, out);
 }
 
-int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, const uint64_t* d_doc_off, uint64_t ndocs, int use_hmm,
-                  uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens, uint64_t* d_doc_tok_off, uint64_t* d_n_tokens,
-                  void* cuda_stream) {
-  if (!tk || !d_doc_off || !d_n_tokens || (nbytes && !d_text)) return fail(JB_EINVAL, "null argument");
-  if (nbytes >= (1ull << 31)) return fail(JB_ELIMIT, "jb_cut_device handles < 2 GiB per call");
+// Bitmap-format batch over one or several tokenizers (one per device): contiguous, byte-balanced document ranges, one
+// host thread + pipeline per device, every shard writing its own words of ONE shared result (no concatenation pass).
+int jb_cut_batch_multi(jb_tokenizer* const* tks, int n_tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm,
+                       jb_result** out) {
+  if (!tks || n_tk < 1) return fail(JB_EINVAL, "no tokenizer");
+  for (int i = 0; i < n_tk; i++) {
+    int rc = check_batch_args(tks[i], text, doc_off, ndocs, out);
+    if (rc != JB_OK) return rc;
+  }
+  jb_result* res = new jb_result();
+  res->ndocs = ndocs;
+  res->nbytes = ndocs ? doc_off[ndocs] - doc_off[0] : 0;
+  res->nwords = (res->nbytes + 31) / 32 + 1;
+  res->doc_tok = (uint64_t*)pin_alloc((ndocs + 1) * 8, &res->doc_bytes);
+  res->sbits = (uint32_t*)pin_alloc(res->nwords * 4, &res->sbits_bytes);
+  res->ebits = (uint32_t*)pin_alloc(res->nwords * 4, &res->ebits_bytes);
+  if (!res->doc_tok || !res->sbits || !res->ebits) {
+    jb_result_free(res);
+    return fail(JB_ENOMEM, "pinned host allocation failed");
+  }
+  res->sbits[res->nwords - 1] = res->ebits[res->nwords - 1] = 0;
+  if (res->nwords >= 2) res->sbits[res->nwords - 2] = res->ebits[res->nwords - 2] = 0;  // (the last data word may be partly written)
+  res->doc_off.resize(ndocs + 1);
+  for (uint64_t d = 0; d <= ndocs; d++) res->doc_off[d] = doc_off[d] - doc_off[0];
+  // shards: contiguous document ranges balanced by bytes (dist.shard_docs does the same for one process per GPU)
+  std::vector<uint64_t> cut(n_tk + 1, ndocs);
+  cut[0] = 0;
+  for (int i = 1; i < n_tk; i++) {
+    const uint64_t target = doc_off[0] + res->nbytes / n_tk * i;
+    cut[i] = std::lower_bound(doc_off + cut[i - 1], doc_off + ndocs, target) - doc_off;
+  }
+  std::vector<int> rcs(n_tk, JB_OK);
+  std::vector<std::string> errs(n_tk);
+  std::vector<uint64_t> nts(n_tk, 0);
+  std::vector<std::vector<EdgeWord>> edges(n_tk);
+  auto shard = [&](int i) {
+    if (n_tk > 1) jb_bind_thread_to_device(tks[i]->device);
+    rcs[i] = cut_range(tks[i], text, doc_off, cut[i], cut[i + 1], use_hmm, true, res, &edges[i], &nts[i]);
+    if (rcs[i] != JB_OK) errs[i] = g_err;
+  };
+  if (n_tk == 1) {
+    shard(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_tk; i++) th.emplace_back(shard, i);
+    for (auto& x : th) x.join();
+  }
+  for (int i = 0; i < n_tk; i++)
+    if (rcs[i] != JB_OK) {
+      jb_result_free(res);
+      return fail(rcs[i], "shard " + std::to_string(i) + ": " + errs[i]);
+    }
+  uint64_t base = 0;
+  for (int i = 0; i < n_tk; i++) {
+    for (const EdgeWord& e : edges[i]) {
+      res->sbits[e.word] |= e.s;
+      res->ebits[e.word] |= e.e;
+    }
+    if (base)
+      for (uint64_t d = cut[i]; d < cut[i + 1]; d++) res->doc_tok[d] += base;
+    base += nts[i];
+  }
+  res->n_tokens = base;
+  res->doc_tok[ndocs] = base;
+  *out = res;
+  return JB_OK;
+}
+
+int jb_cut_batch_bits(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm, jb_result** out) {
+  return jb_cut_batch_multi(&tk, 1, text, doc_off, ndocs, use_hmm, out);
+}
+
+// Pins the calling thread to the CPUs of the NUMA node the device hangs off (pinned buffers allocated afterwards land
+// there too: first touch).  Best effort: returns the node, or -1 when it cannot be found / set.
+int jb_bind_thread_to_device(int device) {
+  char busid[32] = {0};
+  if (cudaDeviceGetPCIBusId(busid, sizeof busid, device) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  for (char* p = busid; *p; p++) *p = (char)tolower(*p);
+  std::string base = std::string("/sys/bus/pci/devices/") + busid;
+  FILE* f = fopen((base + "/numa_node").c_str(), "r");
+  int node = -1;
+  if (f) {
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+  }
+  f = fopen((base + "/local_cpulist").c_str(), "r");
+  if (!f) return -1;
+  char line[4096] = {0};
+  if (!fgets(line, sizeof line, f)) line[0] = 0;
+  fclose(f);
+  cpu_set_t want, have;
+  CPU_ZERO(&want);
+  for (char* p = line; *p;) {  // "0-31,64-95"
+    char* e;
+    long a = strtol(p, &e, 10);
+    if (e == p) break;
+    long b = a;
+    if (*e == '-') b = strtol(e + 1, &e, 10);
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET((int)c, &want);
+    p = (*e == ',') ? e + 1 : e;
+    if (*e != ',') break;
+  }
+  if (sched_getaffinity(0, sizeof have, &have) != 0) return -1;
+  cpu_set_t both;
+  CPU_AND(&both, &want, &have);
+  if (CPU_COUNT(&both) == 0) return -1;  // the container's CPU set does not reach that node
+  if (sched_setaffinity(0, sizeof both, &both) != 0) return -1;
+  return node;
+}
+
+static int cut_device_impl(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, const uint64_t* d_doc_off, uint64_t ndocs, int use_hmm,
+                           const PipeOut& po, void* cuda_stream) {
+  if (!tk || !d_doc_off || !po.d_n_tokens || (nbytes && !d_text)) return fail(JB_EINVAL, "null argument");
+  if (nbytes >= (1ull << 31)) return fail(JB_ELIMIT, "the device entry points handle < 2 GiB per call");
   CUDA_TRY(cudaSetDevice(tk->device));
   std::lock_guard<std::mutex> g(tk->dev_mu);
   WsSlot& sl = tk->dev_ws;
@@ -698,12 +994,35 @@ int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, cons
   int rc = workspace_reserve(ws, nbytes, ndocs, tk->w_per_slot, false);
   if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
   ws.seg_max_runes = tk->seg_max_runes;
-  rc = run_pipeline(tk->T, ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, d_start, d_end, cap_tokens,
-                    d_doc_tok_off, 0, d_n_tokens, st, tk->path);
+  rc = run_pipeline(tk->T, ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, po, st, tk->path);
   cudaEventRecord(sl.ev, st);
   tk->dev_busy = true;
   if (rc != JB_OK) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   return JB_OK;
+}
+
+int jb_cut_device(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, const uint64_t* d_doc_off, uint64_t ndocs, int use_hmm,
+                  uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens, uint64_t* d_doc_tok_off, uint64_t* d_n_tokens,
+                  void* cuda_stream) {
+  PipeOut po;
+  po.d_start = d_start;
+  po.d_end = d_end;
+  po.cap_tokens = cap_tokens;
+  po.d_doc_tok_off = d_doc_tok_off;
+  po.d_n_tokens = d_n_tokens;
+  return cut_device_impl(tk, d_text, nbytes, d_doc_off, ndocs, use_hmm, po, cuda_stream);
+}
+
+int jb_cut_device_bits(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes, const uint64_t* d_doc_off, uint64_t ndocs, int use_hmm,
+                       uint32_t* d_start_bits, uint32_t* d_end_bits, uint64_t* d_doc_tok_off, uint64_t* d_n_tokens, void* cuda_stream) {
+  if (!d_start_bits || !d_end_bits) return fail(JB_EINVAL, "null argument");
+  PipeOut po;
+  po.d_s_bits = d_start_bits;
+  po.d_e_bits = d_end_bits;
+  po.bits_only = true;
+  po.d_doc_tok_off = d_doc_tok_off;
+  po.d_n_tokens = d_n_tokens;
+  return cut_device_impl(tk, d_text, nbytes, d_doc_off, ndocs, use_hmm, po, cuda_stream);
 }
 
 int jb_set_general_only(jb_tokenizer* tk, int on) {
@@ -776,6 +1095,9 @@ int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, u
   CUDA_TRY(cudaMemcpy(ws.text, han_text, nbytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(ws.doc_off64, off, 16, cudaMemcpyHostToDevice));
   uint64_t o = 0;
+  PipeOut dbg_out;
+  dbg_out.d_doc_tok_off = ws.out_doc_tok;
+  dbg_out.d_n_tokens = ws.out_ntok;
   if (tk->path != PATH_GENERAL) {
     // streaming path (k_route, or k_seg with PATH_SEG): per rune, index = lead byte / 3.
     // Only for text whose runes all have 3 bytes (a 4-byte rune sends its block to k_wide, which records nothing).
@@ -786,7 +1108,7 @@ int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, u
     CUDA_TRY(cudaMalloc(&ws.dbg_R, (nr + 64) * 8));
     CUDA_TRY(cudaMalloc(&ws.dbg_D, nr + 64));
     CUDA_TRY(cudaMemset(ws.dbg_D, 0, nr + 64));
-    rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, nullptr, nullptr, 0, ws.out_doc_tok, 0, ws.out_ntok, 0, tk->path);
+    rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, dbg_out, 0, tk->path);
     CUDA_TRY(cudaDeviceSynchronize());
     std::vector<double> R(nr);
     std::vector<uint8_t> D(nr);
@@ -807,7 +1129,7 @@ int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, u
   }
   uint64_t nslots = (ws.cap_bytes / kTileBytes + 2) * kTileSlots + 64;
   if (!ws.dbg_proba) CUDA_TRY(cudaMalloc(&ws.dbg_proba, nslots * 8));
-  rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, nullptr, nullptr, 0, ws.out_doc_tok, 0, ws.out_ntok, 0, PATH_GENERAL);
+  rc = run_pipeline(tk->T, ws, ws.text, (uint32_t)nbytes, ws.doc_off64, 1, false, dbg_out, 0, PATH_GENERAL);
   CUDA_TRY(cudaDeviceSynchronize());
   // read back records + probabilities and translate slots to rune indexes
   uint64_t ns = (nbytes + 2) / 3 + 2;

@@ -65,11 +65,11 @@ __device__ __forceinline__ uint32_t d_decode(const uint8_t* b, int len) {
 __device__ __forceinline__ uint32_t d_slot(uint32_t p) { return (p + 2u) / 3u; }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_docstart(const uint64_t* __restrict__ doc_off, uint64_t ndocs, uint32_t n, uint32_t* __restrict__ doc_off32,
+__global__ void k_docstart(const uint64_t* __restrict__ doc_off, uint64_t ndocs, uint32_t n, uint32_t pos0, uint32_t* __restrict__ doc_off32,
                            uint32_t* __restrict__ ds_bits, uint32_t* __restrict__ tile_first_doc) {
   uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (d > ndocs) return;
-  uint64_t base = doc_off[0];
+  uint64_t base = doc_off[0] - pos0;  // (as if pos0 bytes came before the first document; wraps harmlessly)
   uint64_t p64 = doc_off[d] - base;
   uint32_t p = p64 > n ? n : (uint32_t)p64;
   doc_off32[d] = p;
@@ -1141,6 +1141,22 @@ __global__ void __launch_bounds__(kRankWords) k_rank_scatter(const uint32_t* __r
   }
 }
 
+// doc_tok_off without the scatter (bitmap results): one warp per document, rank of its first byte among the token starts
+__global__ void __launch_bounds__(256) k_doc_tok(const uint32_t* __restrict__ s_bits, const uint32_t* __restrict__ tile_base,
+                                                 const uint32_t* __restrict__ doc_off32, uint64_t ndocs, uint32_t n,
+                                                 uint64_t* __restrict__ doc_tok, uint64_t tok_base) {
+  const uint64_t d = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (d >= ndocs) return;
+  const uint32_t p = doc_off32[d];
+  if (p >= n) return;  // (documents at the end of the text: k_rank_scan)
+  const uint32_t tile = p / (uint32_t)kRankBytes, w0 = tile * (uint32_t)kRankWords, w1 = p >> 5;
+  uint32_t c = 0;
+  for (uint32_t w = w0 + lane; w < w1; w += 32) c += __popc(__ldg(s_bits + w));
+  c = __reduce_add_sync(FULL, c);
+  if (lane == 0) doc_tok[d] = tok_base + tile_base[2 * tile] + c + __popc(__ldg(s_bits + w1) & ((1u << (p & 31)) - 1u));
+}
+
 // ------------------------------------------------------------------------------------------
 // Helpers around the streaming fast path (jb_stream.cu)
 // ------------------------------------------------------------------------------------------
@@ -1319,10 +1335,24 @@ static int g_num_sms = 0;
 
 static bool g_attr_done = false;
 
-int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t n, const uint64_t* d_doc_off, uint64_t ndocs,
-                 bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens, uint64_t* d_doc_tok_off, uint64_t tok_base,
-                 uint64_t* d_n_tokens, cudaStream_t st, int path) {
+int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uint32_t n, const uint64_t* d_doc_off, uint64_t ndocs,
+                 bool use_hmm, const PipeOut& out, cudaStream_t st, int path) {
   const bool force_general = path == PATH_GENERAL;
+  // the caller's bitmaps stand in for the workspace's (a shallow copy of the pointer set: nothing is owned twice)
+  Workspace wsv;
+  Workspace* wsp = &ws_in;
+  if (out.d_s_bits && out.d_e_bits) {
+    wsv = ws_in;
+    wsv.s_bits = out.d_s_bits;
+    wsv.e_bits = out.d_e_bits;
+    wsp = &wsv;
+  }
+  Workspace& ws = *wsp;
+  uint32_t* const d_start = out.d_start;
+  uint32_t* const d_end = out.d_end;
+  uint64_t* const d_doc_tok_off = out.d_doc_tok_off;
+  uint64_t* const d_n_tokens = out.d_n_tokens;
+  const uint64_t tok_base = out.tok_base, cap_tokens = out.cap_tokens;
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1347,7 +1377,7 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
   cudaMemsetAsync(ws.ds_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.s_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.e_bits, 0, ((uint64_t)nwords + 4) * 4, st);
-  JB_LAUNCH(k_docstart, (unsigned)((ndocs + 1 + 255) / 256), 256, 0, st, d_doc_off, ndocs, n, ws.doc_off32, ws.ds_bits, ws.tile_first_doc);
+  JB_LAUNCH(k_docstart, (unsigned)((ndocs + 1 + 255) / 256), 256, 0, st, d_doc_off, ndocs, n, out.pos0, ws.doc_off32, ws.ds_bits, ws.tile_first_doc);
   PROF(1);
   if (n > 0) {
     const unsigned pgrid = (unsigned)g_num_sms * 8;
@@ -1531,18 +1561,31 @@ int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32
   JB_LAUNCH(k_rank_scan, 1, 1024, 0, st, ws.rank_cnt, n ? nrt : 0u, ws.counters, d_n_tokens, ws.doc_off32, ndocs, n, d_doc_tok_off,
             tok_base);
   PROF(7);
-  if (d_start && d_end) return run_scatter(ws, n, ndocs, d_start, d_end, cap_tokens, d_doc_tok_off, tok_base, st);
-  PROF(8);
-  if (ws.prof) ws.prof_pending = true;
-  return cudaGetLastError() == cudaSuccess ? JB_OK : JB_ECUDA;
+  int rc = JB_OK;
+  if (d_start && d_end) {
+    rc = run_scatter(ws, n, ndocs, d_start, d_end, cap_tokens, d_doc_tok_off, tok_base, st);
+  } else {
+    if (out.bits_only && d_doc_tok_off && n > 0 && ndocs > 0)
+      JB_LAUNCH(k_doc_tok, (unsigned)((ndocs * 32 + 255) / 256), 256, 0, st, ws.s_bits, ws.rank_cnt, ws.doc_off32, ndocs, n, d_doc_tok_off, tok_base);
+    PROF(8);
+    if (ws.prof) ws.prof_pending = true;
+    rc = cudaGetLastError() == cudaSuccess ? JB_OK : JB_ECUDA;
+  }
+  if (wsp == &wsv) {  // event / stream handles created during this call belong to the real workspace
+    wsv.s_bits = ws_in.s_bits;
+    wsv.e_bits = ws_in.e_bits;
+    ws_in = wsv;
+    wsv = Workspace();
+  }
+  return rc;
 }
 
 int run_scatter(Workspace& ws, uint32_t n, uint64_t ndocs, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
-                uint64_t* d_doc_tok_off, uint64_t tok_base, cudaStream_t st) {
+                uint64_t* d_doc_tok_off, uint64_t tok_base, cudaStream_t st, const uint32_t* d_s_bits, const uint32_t* d_e_bits) {
   const uint32_t nwords = (n + 31) / 32;
   const uint32_t nrt = (n + kRankBytes - 1) / kRankBytes;
   if (n > 0)
-    JB_LAUNCH(k_rank_scatter, nrt, kRankWords, 0, st, ws.s_bits, ws.e_bits, ws.ds_bits, nwords, n, ws.rank_cnt, ws.doc_off32, ws.tile_first_doc, ndocs,
+    JB_LAUNCH(k_rank_scatter, nrt, kRankWords, 0, st, d_s_bits ? d_s_bits : ws.s_bits, d_e_bits ? d_e_bits : ws.e_bits, ws.ds_bits, nwords, n, ws.rank_cnt, ws.doc_off32, ws.tile_first_doc, ndocs,
               d_start, d_end, cap_tokens, d_doc_tok_off, tok_base);
   PROF(8);
   if (ws.prof) ws.prof_pending = true;

@@ -93,23 +93,35 @@ struct Workspace {
 int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_per_slot, bool host_staging);
 void workspace_free(Workspace& ws);
 
+// Where a batch's result goes (all device pointers).
+struct PipeOut {
+  uint32_t* d_start = nullptr;  // token (start,end), doc-relative, up to cap_tokens (both NULL: count only; run_scatter later)
+  uint32_t* d_end = nullptr;
+  uint64_t cap_tokens = 0;
+  uint64_t* d_doc_tok_off = nullptr;  // [ndocs+1]: tok_base + rank of each document's first token
+  uint64_t tok_base = 0;
+  uint64_t* d_n_tokens = nullptr;     // [0] token count of the batch, [1] status word
+  // BITMAP result: bit p of d_s_bits / d_e_bits = a token starts at / ends with byte p of the batch.  When given, these
+  // buffers ((nbytes / 32 + 8) words each) are the pipeline's working bitmaps instead of the workspace's.
+  uint32_t* d_s_bits = nullptr;
+  uint32_t* d_e_bits = nullptr;
+  bool bits_only = false;  // no (start,end) arrays at all: the bitmaps + doc_tok_off are the result (k_rank_scatter is not run)
+  uint32_t pos0 = 0;       // the first document starts at byte pos0 (< 32) of d_text; bytes before it must be spaces
+};
+
 // Enqueue the whole Cut pipeline for one batch on `stream`.
-//   d_text[nbytes], d_doc_off[ndocs+1] (uint64, absolute; doc_off[0] is subtracted) on device.
-//   Token (start,end) are written doc-relative into d_start/d_end (up to cap_tokens),
-//   d_doc_tok_off[ndocs+1] gets tok_base + rank, d_n_tokens[0] the batch's token count and
-//   d_n_tokens[1] the status word.
+//   d_text[nbytes], d_doc_off[ndocs+1] (uint64, absolute; doc_off[0] is subtracted, out.pos0 added) on device.
 //   path: PATH_DEFAULT k_scan -> k_route -> k_emit (lane per block); PATH_GENERAL skip the fast path and run the general
 //   kernels on everything; PATH_SEG k_scan -> k_seg (CTA-cooperative, shared-memory candidates; k_route / k_emit only for
 //   the blocks it leaves).
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_doc_off,
-                 uint64_t ndocs, bool use_hmm, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
-                 uint64_t* d_doc_tok_off, uint64_t tok_base, uint64_t* d_n_tokens, cudaStream_t stream,
-                 int path = 0);
+                 uint64_t ndocs, bool use_hmm, const PipeOut& out, cudaStream_t stream, int path = 0);
 enum { PATH_DEFAULT = 0, PATH_GENERAL = 1, PATH_SEG = 2 };
 
 // Second phase when d_start/d_end were NULL in run_pipeline (count first, then scatter).
 int run_scatter(Workspace& ws, uint32_t nbytes, uint64_t ndocs, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,
-                uint64_t* d_doc_tok_off, uint64_t tok_base, cudaStream_t stream);
+                uint64_t* d_doc_tok_off, uint64_t tok_base, cudaStream_t stream, const uint32_t* d_s_bits = nullptr,
+                const uint32_t* d_e_bits = nullptr);
 
 int debug_lookup(const JbTables& T, const uint32_t* runes_host, int L, int* kind, double* w);
 

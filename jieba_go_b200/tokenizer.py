@@ -156,6 +156,49 @@ class Tokenizer:
             self._L.jb_result_free(r)
         return st, en, dto
 
+    def cut_batch_bits(self, text, doc_off, use_hmm: bool, others=()):
+        """Batched Cut with the BITMAP result (jb_cut_batch_bits): 2 bits per input byte come back instead of 8 bytes
+        per token.  `others`: more Tokenizers on other devices -- the batch is then sharded over all of them
+        (jb_cut_batch_multi).  -> CutBits (views of pinned memory; .expand() gives the arrays of cut_batch)."""
+        if isinstance(text, (bytes, bytearray)):
+            tarr = np.frombuffer(text, dtype=np.uint8)
+        else:
+            tarr = np.ascontiguousarray(text, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        nd = len(doc_off) - 1
+        r = C.c_void_p()
+        tks = [self] + list(others)
+        hs = (C.c_void_p * len(tks))(*[t._h for t in tks])
+        with self._lock:
+            check(self._L.jb_cut_batch_multi(hs, len(tks), tarr.ctypes.data if tarr.size else None, doc_off.ctypes.data, nd,
+                                             int(bool(use_hmm)), C.byref(r)), "jb_cut_batch_multi")
+        return CutBits(self._L, r, nd)
+
+    def cut_many(self, texts, use_hmm: bool):
+        """CutBatch(texts []string, hmm) [][]string: many strings in ONE device batch (the way a caller with short
+        strings reaches throughput; one Cut per string pays the launch latency every time)."""
+        bs = [t.encode("utf-8") if isinstance(t, str) else bytes(t) for t in texts]
+        off = np.zeros(len(bs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(b) for b in bs])
+        with self.cut_batch_bits(b"".join(bs), off, use_hmm) as r:
+            st, en = r.expand()
+            dto = r.doc_tok_off.copy()
+        out = []
+        for i, b in enumerate(bs):
+            lo, hi = int(dto[i]), int(dto[i + 1])
+            out.append(["\ufffd" if (e - s == 1 and b[s] >= 0x80) else b[s:e].decode("utf-8", errors="replace")
+                        for s, e in zip(st[lo:hi].tolist(), en[lo:hi].tolist())])
+        return out
+
+    def cut_device_bits(self, d_text, d_doc_off, use_hmm: bool, d_start_bits, d_end_bits, d_doc_tok_off, d_n_tokens, stream=None):
+        """jb_cut_device_bits on torch tensors: the bitmaps (int32, numel >= nbytes / 32 + 8) are the result."""
+        sp = stream.cuda_stream if stream is not None else None
+        nd = d_doc_off.numel() - 1
+        check(self._L.jb_cut_device_bits(self._h, d_text.data_ptr(), d_text.numel(), d_doc_off.data_ptr(), nd, int(bool(use_hmm)),
+                                         d_start_bits.data_ptr(), d_end_bits.data_ptr(),
+                                         d_doc_tok_off.data_ptr() if d_doc_tok_off is not None else None, d_n_tokens.data_ptr(), sp),
+              "jb_cut_device_bits")
+
     def cut_offsets(self, text, use_hmm: bool):
         b = text.encode("utf-8") if isinstance(text, str) else bytes(text)
         st, en, _ = self.cut_batch(b, np.array([0, len(b)], dtype=np.uint64), use_hmm)
@@ -259,6 +302,49 @@ class CutResult:
     def close(self):
         if self._r:
             self.start = self.end = self.doc_tok_off = None
+            self._L.jb_result_free(self._r)
+            self._r = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CutBits:
+    """Zero-copy view of a bitmap jb_result (library-owned pinned memory) -- valid until close()."""
+
+    def __init__(self, L, handle, ndocs):
+        self._L = L
+        self._r = handle
+        self.n_tokens = L.jb_result_num_tokens(handle)
+        self.n_bytes = L.jb_result_num_bytes(handle)
+        nw = (self.n_bytes + 31) // 32
+        if nw:
+            self.start_bits = np.ctypeslib.as_array(L.jb_result_start_bits(handle), shape=(nw,))
+            self.end_bits = np.ctypeslib.as_array(L.jb_result_end_bits(handle), shape=(nw,))
+        else:
+            self.start_bits = np.zeros(0, np.uint32)
+            self.end_bits = np.zeros(0, np.uint32)
+        self.doc_tok_off = np.ctypeslib.as_array(L.jb_result_doc_tok_off(handle), shape=(ndocs + 1,))
+
+    def expand(self, nthreads=8):
+        """-> (start uint32[], end uint32[]) as jb_cut_batch returns them (jb_result_expand, host threads)."""
+        st = np.empty(self.n_tokens, np.uint32)
+        en = np.empty(self.n_tokens, np.uint32)
+        check(self._L.jb_result_expand(self._r, st.ctypes.data, en.ctypes.data, nthreads), "jb_result_expand")
+        return st, en
+
+    def close(self):
+        if self._r:
+            self.start_bits = self.end_bits = self.doc_tok_off = None
             self._L.jb_result_free(self._r)
             self._r = None
 

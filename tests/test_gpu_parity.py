@@ -515,3 +515,108 @@ def test_device_api_two_streams(medium_pair):
         assert np.array_equal(d_start[:len(os_)].cpu().numpy().astype(np.uint32), os_)
         assert np.array_equal(d_end[:len(os_)].cpu().numpy().astype(np.uint32), oe)
         assert np.array_equal(d_dto.cpu().numpy().astype(np.uint64), od)
+
+
+# ---- the bitmap result format, pageable input, many short strings ----------------------------------------------
+def _bits_equal_arrays(tk, ora, t, off, hmm, nthreads=4):
+    want = ora.cut_batch(t, off, hmm, 8)
+    with tk.cut_batch_bits(t, off, hmm) as r:
+        assert r.n_tokens == len(want[0])
+        assert np.array_equal(r.doc_tok_off, want[3])
+        # the bitmaps themselves: popcounts, and every start / end bit where the oracle says
+        abs_s = np.repeat(off[:-1], np.diff(want[3]).astype(np.int64)) + want[0]
+        abs_e = np.repeat(off[:-1], np.diff(want[3]).astype(np.int64)) + want[1] - 1
+        sb = np.unpackbits(r.start_bits.view(np.uint8), bitorder="little")
+        eb = np.unpackbits(r.end_bits.view(np.uint8), bitorder="little")
+        assert sb.sum() == len(want[0]) and eb.sum() == len(want[0])
+        assert np.array_equal(np.nonzero(sb)[0].astype(np.uint64), abs_s - off[0])
+        assert np.array_equal(np.nonzero(eb)[0].astype(np.uint64), abs_e - off[0])
+        for nt in (1, nthreads):
+            st, en = r.expand(nt)
+            assert np.array_equal(st, want[0]) and np.array_equal(en, want[1])
+
+
+@pytest.mark.parametrize("hmm", [False, True])
+def test_bitmap_result_format(synth_pair, hmm):
+    sd, emit, _, ora = synth_pair
+    tk = _gpu_tokenizer(sd, emit, 1, max_batch_bytes=50_000)   # many sub-batches starting at every bit offset of a word
+    text, doc_off = synth.make_corpus(sd, "oov", 600_000, synth.SEED_BASE + 61)
+    t = text.numpy()
+    rng = np.random.default_rng(6)
+    cuts = np.unique(np.concatenate([[0, t.size], rng.integers(0, t.size, 300)])).astype(np.uint64)
+    off = np.concatenate([cuts[:40], cuts[39:40], cuts[40:]])   # an empty document too
+    _bits_equal_arrays(tk, ora, t, off, hmm)
+    _bits_equal_arrays(tk, ora, t, off[5:-7], hmm)             # doc_off[0] != 0: bit 0 = first byte of the first document
+    rng2 = np.random.default_rng(7)
+    docs = fuzz_docs(sd, rng2, n_docs=300, max_len=60) + [b"", b"x", b""]
+    ft, foff = pack_docs(docs)
+    _bits_equal_arrays(tk, ora, ft, foff, hmm)
+    e = np.zeros(1, np.uint64)
+    with tk.cut_batch_bits(b"", e, hmm) as r:                   # no documents at all
+        assert r.n_tokens == 0 and r.doc_tok_off.tolist() == [0]
+
+
+def test_bitmap_result_two_tokenizers_one_device(synth_pair):
+    """jb_cut_batch_multi with two tokenizers (here both on device 0; one per GPU on a multi-GPU box): two host threads,
+    two pipelines, one shared bitmap result."""
+    sd, emit, tk, ora = synth_pair
+    tk2 = _gpu_tokenizer(sd, emit)
+    tk3 = _gpu_tokenizer(sd, emit)
+    text, doc_off = synth.make_corpus(sd, "freq", 1_500_000, synth.SEED_BASE + 62)
+    t, off = text.numpy(), doc_off.numpy().astype(np.uint64)
+    want = ora.cut_batch(t, off, True, 8)
+    with tk.cut_batch_bits(t, off, True, others=[tk2, tk3]) as r:
+        st, en = r.expand(3)
+        assert np.array_equal(r.doc_tok_off, want[3]) and np.array_equal(st, want[0]) and np.array_equal(en, want[1])
+
+
+def test_device_bits_api(medium_pair):
+    import torch
+    sd, emit, tk, ora = medium_pair
+    text, doc_off = synth.make_corpus(sd, "oov", 1_000_000, synth.SEED_BASE + 71)
+    t, off = text.numpy(), doc_off.numpy().astype(np.uint64)
+    os_, oe, _, od = ora.cut_batch(t, off, True, 8)
+    dt, ddo = text.cuda(), doc_off.cuda()
+    nw = t.size // 32 + 8
+    sb = torch.full((nw,), -1, dtype=torch.int32, device="cuda")   # (garbage in: the call clears them)
+    eb = torch.full((nw,), -1, dtype=torch.int32, device="cuda")
+    d_dto = torch.zeros(off.size, dtype=torch.int64, device="cuda")
+    d_nt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    tk.cut_device_bits(dt, ddo, True, sb, eb, d_dto, d_nt)
+    torch.cuda.synchronize()
+    assert d_nt.tolist() == [len(os_), 0]
+    assert np.array_equal(d_dto.cpu().numpy().astype(np.uint64), od)
+    s_pos = np.nonzero(np.unpackbits(sb.cpu().numpy().view(np.uint8), bitorder="little")[: t.size])[0]
+    e_pos = np.nonzero(np.unpackbits(eb.cpu().numpy().view(np.uint8), bitorder="little")[: t.size])[0]
+    base = np.repeat(off[:-1], np.diff(od).astype(np.int64))
+    assert np.array_equal(s_pos.astype(np.uint64), base + os_) and np.array_equal(e_pos.astype(np.uint64), base + oe - 1)
+
+
+def test_pageable_and_pinned_input_agree(medium_pair):
+    import torch
+    sd, emit, tk, ora = medium_pair
+    text, doc_off = synth.make_corpus(sd, "oov", 40_000_000, synth.SEED_BASE + 72)   # two 16 MiB+ sub-batches
+    off = doc_off.numpy().astype(np.uint64)
+    pinned = text.pin_memory()
+    pageable = np.array(text.numpy(), copy=True)
+    a = tk.cut_batch(pinned.numpy(), off, True)
+    b = tk.cut_batch(pageable, off, True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    _assert_same(b, ora.cut_batch(pageable, off, True, 16), pageable, off)
+
+
+def test_ten_thousand_short_strings_in_one_batch(synth_pair):
+    """The batch call a Go caller with many short strings uses (CutBatch in go/tokenizer.go): 10k strings, one device batch."""
+    sd, emit, tk, ora = synth_pair
+    rng = np.random.default_rng(8)
+    words = [w.decode() for w in sd.words]
+    texts = []
+    for i in range(10_000):
+        k = int(rng.integers(0, 12))
+        s = "".join(words[int(j)] if rng.random() < 0.8 else ["，", " a1 ", "。", "龥"][int(rng.integers(0, 4))] for j in rng.integers(0, len(words), k))
+        texts.append(s)
+    got = tk.cut_many(texts, True)
+    for i in rng.integers(0, len(texts), 400).tolist() + [0, len(texts) - 1]:
+        assert got[i] == ora.cut_strings(texts[i], True), texts[i]
+    assert sum(len(g) for g in got) == sum(len(ora.cut_strings(s, True)) for s in texts[:2000]) + sum(len(g) for g in got[2000:])
