@@ -11,8 +11,16 @@ batch of the same size (documents shard with no data-path collective): weak scal
 
 `value`   device-resident input -> device-resident (start,end) arrays via jb_cut_device, CUDA events
           on the launching stream, max over ranks.
-`e2e`     the same batch through jb_cut_batch with HOST buffers: pinned text H2D, pipeline, token
-          arrays D2H -- everything inside the timed region.
+`e2e`     the same batch through the public host-memory call with HOST buffers, everything inside the
+          timed region: pinned text H2D, pipeline, result D2H, and a read of the result on the host.
+          The call is jb_cut_batch_bits (result = token start/end bitmaps + per-document token offsets:
+          2 bits per input byte come back instead of 8 bytes per token).  `e2e_arrays` is the same through
+          jb_cut_batch ((start,end) uint32 arrays), `e2e_pageable` is jb_cut_batch_bits on PAGEABLE text
+          (what a Go string is): the library stages it through pinned buffers with host threads.
+`config5` (every N) BASELINE config 5 as stated: ONE deterministic 16e9-byte OOV corpus (16 segments of 1e9
+          bytes, seed = segment index), HMM on, documents sharded over the N ranks (16/N segments each), device-
+          resident rate + e2e + a per-rank oracle parity sample + token count / checksum reduced over ranks
+          (identical for every N).
 `roofline` algorithmic bytes A = B_in + 8*T_out / duration of the dominant kernel
           (per-kernel CUDA events recorded by the library, jb_profile_*), against the measured HBM
           copy peak in MEASURED_PEAKS.json.  `pipeline_frac` is A / all kernels of the step.
@@ -136,6 +144,94 @@ def run_cpu_baseline(otk, co, text_np, off_np, hmm, seconds=12.0):
     return len(st) / dt / 1e6, cores, st, so, res
 
 
+def run_config5(args, tk, L, sd, emit, dev, rank, world, barrier, stream):
+    """BASELINE config 5: one deterministic corpus of 16 segments (seed = segment index, so it is the same corpus for
+    every N), HMM on, documents sharded contiguously: rank r owns segments [16 r / N, 16 (r + 1) / N).  Each segment
+    is one < 2 GiB device call.  Returns the dict for the bench line on rank 0 (None elsewhere)."""
+    import torch
+    from jieba_go_b200 import synth
+    from jieba_go_b200.dist import reduce_max_sum
+    nseg = 16
+    seg_bytes = args.config5_bytes // nseg
+    mine = list(range(nseg * rank // world, nseg * (rank + 1) // world))
+    segs = [synth.make_corpus(sd, "oov", seg_bytes, synth.SEED_BASE + 5000 + i, device=dev) for i in mine]
+    cap = max(t.numel() for t, _ in segs) // 3 + 4096
+    d_start = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_end = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_dto = torch.empty(max(o.numel() for _, o in segs), dtype=torch.int64, device=dev)
+    d_nt = torch.zeros(2, dtype=torch.int64, device=dev)
+    steps, warm = max(1, min(args.steps, 3)), 1
+    n_tok, chk = 0, 0
+
+    def one_pass(check):
+        nonlocal n_tok, chk
+        n_tok, chk = 0, 0
+        for t, o in segs:
+            tk.cut_device(t, o, True, d_start, d_end, d_dto, d_nt, stream=stream)
+            if check:
+                stream.synchronize()
+                n, status = d_nt.tolist()
+                assert status == 0 and n <= cap
+                n_tok += n
+                # order-independent checksum of the (start, end) pairs: the same for every sharding of the corpus
+                chk = (chk + int(((d_start[:n].long() * 1_000_003 + d_end[:n].long()) % 2_147_483_629).sum().item())) % (1 << 61)
+
+    with torch.cuda.stream(stream):
+        for _ in range(warm):
+            one_pass(False)
+    stream.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            one_pass(False)
+        ev1.record(stream)
+    stream.synchronize()
+    barrier()
+    t_ms = ev0.elapsed_time(ev1) / steps
+    with torch.cuda.stream(stream):
+        one_pass(True)
+    my_bytes = sum(t.numel() for t, _ in segs)
+    # e2e: every segment through jb_cut_batch_bits from ONE pinned host buffer (filled outside the timed region)
+    e_dt = 0.0
+    if not args.no_e2e:
+        h_buf = torch.empty(max(t.numel() for t, _ in segs), dtype=torch.uint8).pin_memory()
+        for it in range(2):
+            e_dt = 0.0
+            for t, o in segs:
+                h_buf[: t.numel()].copy_(t)
+                torch.cuda.synchronize(dev)
+                h_off = o.cpu().numpy().astype(np.uint64)
+                t0 = time.perf_counter()
+                with tk.cut_batch_bits(h_buf[: t.numel()].numpy(), h_off, True) as r:
+                    nt = r.n_tokens + int(r.doc_tok_off[-1]) * 0
+                e_dt += time.perf_counter() - t0
+        del h_buf
+    # parity sample on every rank: the first ~24 MB of its first segment against the oracle
+    same = None
+    if not args.no_cpu:
+        co, otk = build_oracle(sd, emit)
+        t_np = segs[0][0][:30_000_000].cpu().numpy()
+        o_np = segs[0][1].cpu().numpy().astype(np.uint64)
+        st, so = cpu_sample(t_np, o_np, 24_000_000)
+        res = otk.cut_batch(st, so, True, co.num_procs())
+        g = tk.cut_batch(st, so, True)
+        same = bool(np.array_equal(g[0], res[0]) and np.array_equal(g[1], res[1]) and np.array_equal(g[2], res[3]))
+    (t_max, e_max), (tot_bytes, tot_tok, tot_chk, n_same) = reduce_max_sum(
+        [t_ms, e_dt], [float(my_bytes), float(n_tok), float(chk % (1 << 40)), float(1 if same else 0)], device=dev)
+    del segs
+    if rank != 0:
+        return None
+    return {"workload": "config5: ONE %d-byte OOV corpus (16 seeded segments), HMM on, documents sharded over %d GPU(s), %d segment(s) per GPU, one < 2 GiB device call per segment" % (
+                int(tot_bytes), world, nseg // world),
+            "value": tot_bytes / (t_max * 1e-3) / 1e6, "unit": "MB/s", "ms_per_pass": t_max,
+            "e2e": (tot_bytes / e_max / 1e6) if e_max else None, "e2e_ms_per_pass": e_max * 1e3 if e_max else None,
+            "bytes": int(tot_bytes), "tokens": int(tot_tok), "checksum_mod_2p40_summed": int(tot_chk),
+            "parity": None if same is None else ("bit-exact on every rank's 24 MB sample" if int(n_same) == world else "MISMATCH on %d rank(s)" % (world - int(n_same))),
+            "steps": steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,6 +243,8 @@ def main():
     ap.add_argument("--dict-words", type=int, default=349_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--config5-bytes", type=int, default=16_000_000_000, help="total bytes of the config-5 corpus (16 segments)")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: whatever libraries print there (NCCL's version banner, ...) is sent to
     # stderr by pointing fd 1 at fd 2 for the run; the JSON line is written to the saved descriptor at the end
@@ -175,24 +273,28 @@ def main():
         emit = synth.make_emit(sd)
         co, otk = build_oracle(sd, emit)
         cores = co.num_procs()
-        sample_bytes = min(args.bytes, 6_000_000 * cores)  # ~1-2 s of all-core work per step
-        text, doc_off = synth.make_corpus(sd, cfg["kind"], sample_bytes, synth.SEED_BASE + args.config, device="cpu")
+        # the same workload as the GPU arm: the whole --bytes batch every step (about 5 s of all-core work per GB)
+        text, doc_off = synth.make_corpus(sd, cfg["kind"], args.bytes, synth.SEED_BASE + args.config, device="cpu")
         t = text.numpy()
         off = doc_off.numpy().astype(np.uint64)
+        res = None
         for _ in range(args.warmup):
-            otk.cut_batch(t, off, cfg["hmm"], cores)
+            res = otk.cut_batch(t, off, cfg["hmm"], cores)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            otk.cut_batch(t, off, cfg["hmm"], cores)
+            res = otk.cut_batch(t, off, cfg["hmm"], cores)
         dt = (time.perf_counter() - t0) / max(1, args.steps)
         v = t.size / dt / 1e6
+        n_tok_ref = int(len(res[0])) if res is not None else None
         line = {
             "impl": "reference", "metric": "UTF-8 MB/s segmented", "value": v, "unit": "MB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"], "bytes_per_step": int(t.size), "hmm": cfg["hmm"], "dict_words": args.dict_words},
+            "config": {"workload": cfg["name"], "bytes_per_gpu_per_step": int(t.size), "docs_per_gpu": int(off.size - 1),
+                       "tokens_per_gpu": n_tok_ref, "hmm": cfg["hmm"], "dict_words": args.dict_words,
+                       "l2": "n/a (CPU)", "sharding": "documents over host threads"},
             "cpu_baseline": {"value": v, "unit": "MB/s", "cores": cores, "kind": "port",
-                             "sample": "%d B of the workload per step, C restatement of jieba-go (not Go), %d threads" % (t.size, cores)},
+                             "sample": "the whole batch (%d B) per step, C restatement of jieba-go (not Go; no Go toolchain in the image), %d threads" % (t.size, cores)},
             "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -266,32 +368,61 @@ def main():
     L.jb_profile_enable(tk.handle, 0)
     kern_ms = {L.jb_profile_kernel_name(i).decode(): ms[i] / max(1, nsteps.value) for i in range(len(ms))}
 
-    # ---- e2e: host buffers in, host arrays out, copies inside the timed region -------------------
+    # ---- e2e: host buffers in, result on the host, copies inside the timed region ----------------------
+    L.jb_bind_thread_to_device(local_rank)  # pinned buffers and the driving thread on the GPU's NUMA node (best effort)
     e2e = None
+    e2e_extra = {}
     if not args.no_e2e:
         h_text = text.cpu().pin_memory()
         h_off = doc_off.cpu().numpy().astype(np.uint64)
         h_np = h_text.numpy()
         e_steps = max(2, min(args.steps, 3))
-        for _ in range(2):  # warm-up (workspaces of both pipeline slots + pinned result buffers)
-            tk.cut_batch_view(h_np, h_off, hmm).close()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            # the call a user makes: host text in, host (start,end) arrays out (zero-copy views of the
-            # library's pinned result, as the Go shim would slice them); the D2H read is inside
+
+        def time_e2e(call, warm=2):
+            for _ in range(warm):  # warm-up (workspaces of the pipeline slots + pinned result buffers)
+                call()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                chk = call()
+            torch.cuda.synchronize(dev)
+            return (time.perf_counter() - t0) / e_steps, chk
+
+        def call_bits(src):
+            # the call a user makes: host text in, token bitmaps + per-document offsets out (zero-copy views of the
+            # library's pinned result, as the Go shim walks them); the result is READ here: the last document's
+            # tokens are expanded from the bits
+            with tk.cut_batch_bits(src, h_off, hmm) as r:
+                lo = int(h_off[-2] - h_off[0])
+                last = int(np.unpackbits(r.start_bits[lo // 32:].view(np.uint8), bitorder="little").sum()) if r.n_bytes else 0
+                return r.n_tokens, int(r.doc_tok_off[-1]), last
+
+        def call_arrays():
             with tk.cut_batch_view(h_np, h_off, hmm) as r:
-                e_ntok = r.n_tokens
-                e_last = int(r.end[-1]) if e_ntok else 0
-        torch.cuda.synchronize(dev)
-        e_dt = (time.perf_counter() - t0) / e_steps
-        assert e_ntok == n_tok
-        e2e = (e_dt, nbytes + 8 * (ndocs + 1), 8 * n_tok + 8 * (ndocs + 1))
-        del h_text
+                return r.n_tokens, int(r.end[-1]) if r.n_tokens else 0
+
+        e_dt, chk = time_e2e(lambda: call_bits(h_np))
+        assert chk[0] == n_tok and chk[1] == n_tok
+        e2e = (e_dt, nbytes + 8 * (ndocs + 1), 2 * 4 * ((nbytes + 31) // 32) + 8 * (ndocs + 1))
+        a_dt, chk = time_e2e(call_arrays, warm=1)
+        assert chk[0] == n_tok
+        e2e_extra["e2e_arrays"] = (a_dt, nbytes + 8 * (ndocs + 1), 8 * n_tok + 8 * (ndocs + 1))
+        pageable = np.array(h_np, copy=True)  # ordinary (pageable) host memory, like a Go string
+        p_dt, chk = time_e2e(lambda: call_bits(pageable), warm=1)
+        assert chk[0] == n_tok
+        e2e_extra["e2e_pageable"] = (p_dt, nbytes + 8 * (ndocs + 1), e2e[2])
+        del h_text, pageable
+
+    # ---- config 5 as stated: one 16e9-byte corpus, documents sharded over the ranks -----------------------
+    c5 = None
+    if not args.no_config5 and world in (1, 2, 4, 8, 16):
+        c5 = run_config5(args, tk, L, sd, emit, dev, rank, world, barrier, stream)
 
     # ---- reductions over ranks (max time, total bytes) ---------------------------------------------
     from jieba_go_b200.dist import reduce_max_sum
-    (t_ms_max, e_dt_max), (tot_bytes, tot_tok) = reduce_max_sum([t_ms, e2e[0] if e2e else 0.0], [float(nbytes), float(n_tok)], device=dev)
+    ex = [e2e_extra[k][0] if k in e2e_extra else 0.0 for k in ("e2e_arrays", "e2e_pageable")]
+    (t_ms_max, e_dt_max, a_dt_max, p_dt_max), (tot_bytes, tot_tok) = reduce_max_sum(
+        [t_ms, e2e[0] if e2e else 0.0] + ex, [float(nbytes), float(n_tok)], device=dev)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -302,16 +433,19 @@ def main():
         t_k = sum(kern_ms.values())
         # DRAM traffic of the dominant kernel per launch: from the committed `ncu --set full` capture of the same
         # workload (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), else null
-        traffic = None
+        traffic, capture = None, {}
         try:
             for rec in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))):
                 if dom.startswith(rec["kernel"]) and rec["config"] == args.config and abs(rec["input_bytes"] - nbytes) <= 0.01 * nbytes:
                     traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
+                    capture = {k: rec[k] for k in ("capture", "l2_hit_rate_pct", "l1_hit_rate_pct", "lts_throughput_pct") if k in rec}
         except Exception:
             pass
         roof = {
             "bound": "hbm", "kernel": dom, "achieved": A / (kern_ms[dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": A / (kern_ms[dom] * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+            "frac": A / (kern_ms[dom] * 1e-3) / 1e9 / peak, "traffic": traffic,
+            "traffic_source": "committed ncu --set full capture of this workload (not measured in this run)" if traffic else None,
+            "ncu": capture, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": A,
             "pipeline_achieved": A / (t_k * 1e-3) / 1e9, "pipeline_frac": A / (t_k * 1e-3) / 1e9 / peak,
             "kernel_ms": {k: round(v, 4) for k, v in kern_ms.items()},
@@ -327,7 +461,15 @@ def main():
         }
         if e2e:
             line["e2e"] = {"value": tot_bytes / e_dt_max / 1e6, "unit": "MB/s", "h2d_bytes_per_step": int(e2e[1]),
-                           "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": e_dt_max * 1e3}
+                           "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": e_dt_max * 1e3,
+                           "call": "jb_cut_batch_bits: pinned host text in, token start/end bitmaps + doc_tok_off out"}
+            for k, dtm, what in (("e2e_arrays", a_dt_max, "jb_cut_batch: (start,end) uint32 arrays out"),
+                                 ("e2e_pageable", p_dt_max, "jb_cut_batch_bits on pageable host text (staged through pinned buffers)")):
+                if k in e2e_extra:
+                    line[k] = {"value": tot_bytes / dtm / 1e6, "unit": "MB/s", "h2d_bytes_per_step": int(e2e_extra[k][1]),
+                               "d2h_bytes_per_step": int(e2e_extra[k][2]), "ms_per_step": dtm * 1e3, "call": what}
+        if c5:
+            line["config5"] = c5
         if not args.no_cpu:
             co, otk = build_oracle(sd, emit)
             t_np = text.cpu().numpy()
