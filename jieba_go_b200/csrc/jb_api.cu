@@ -50,8 +50,28 @@ struct WsSlot {
   uint64_t h_text_cap = 0;
 };
 
+// Small calls (Cut of one sentence): the whole pipeline of a fixed-size batch captured ONCE as a CUDA graph; its results
+// land in mapped pinned host memory, so a call is: fill the staging buffers, one graph launch, one synchronise.
+constexpr uint32_t kSmallBytes = 8192;  // text capacity of the small path
+constexpr uint32_t kSmallDocs = 256;    // documents per small call (the slot after the last real one holds the padding)
+struct SmallPath {
+  std::mutex mu;  // one small call at a time per tokenizer (others take the ordinary path)
+  bool failed = false;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};  // HMM off / on
+  int path_of[2] = {-1, -1};
+  Workspace ws;
+  uint8_t* h_text = nullptr;     // pinned staging
+  uint64_t* h_doc = nullptr;
+  uint32_t* h_start = nullptr;   // mapped pinned: written by the kernels
+  uint32_t* h_end = nullptr;
+  uint64_t* h_doc_tok = nullptr;
+  uint64_t* h_cnt = nullptr;
+};
+
 struct jb_tokenizer {
   int device = 0;
+  SmallPath small;
   JbTables T;
   std::vector<void*> dev_allocs;
   void* table_base = nullptr;
@@ -71,6 +91,7 @@ struct jb_tokenizer {
 };
 
 struct jb_result {
+  bool heap = false;  // small results: plain malloc instead of the pinned pool
   uint64_t n_tokens = 0, ndocs = 0, nbytes = 0;
   // (start, end) arrays (jb_cut, jb_cut_batch)
   uint32_t* start = nullptr;
@@ -396,6 +417,7 @@ int jb_tokenizer_create_from_gob(const char* gob_path, int64_t size, const char*
   return rc;
 }
 
+static void small_destroy(SmallPath& sp);
 static void free_slot(WsSlot* s) {
   workspace_free(s->ws);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -413,6 +435,7 @@ void jb_tokenizer_destroy(jb_tokenizer* tk) {
     delete s;
   }
   free_slot(&tk->dev_ws);
+  small_destroy(tk->small);
   for (void* p : tk->dev_allocs) cudaFree(p);
   delete tk;
 }
@@ -433,6 +456,13 @@ const uint32_t* jb_result_end_bits(const jb_result* r) { return r->ebits; }
 uint64_t jb_result_num_bytes(const jb_result* r) { return r->nbytes; }
 void jb_result_free(jb_result* r) {
   if (!r) return;
+  if (r->heap) {
+    free(r->start);
+    free(r->end);
+    free(r->doc_tok);
+    delete r;
+    return;
+  }
   pin_free(r->start, r->start_bytes);
   pin_free(r->end, r->end_bytes);
   pin_free(r->sbits, r->sbits_bytes);
@@ -832,9 +862,130 @@ static int check_batch_args(jb_tokenizer* tk, const uint8_t* text, const uint64_
   return JB_OK;
 }
 
+static void small_destroy(SmallPath& sp) {
+  for (auto& e : sp.exec)
+    if (e) cudaGraphExecDestroy(e);
+  sp.exec[0] = sp.exec[1] = nullptr;
+  workspace_free(sp.ws);
+  if (sp.stream) cudaStreamDestroy(sp.stream);
+  sp.stream = nullptr;
+  void* hp[] = {sp.h_text, sp.h_doc, sp.h_start, sp.h_end, sp.h_doc_tok, sp.h_cnt};
+  for (void* p : hp)
+    if (p) cudaFreeHost(p);
+  sp.h_text = nullptr;
+  sp.h_doc = nullptr;
+  sp.h_start = sp.h_end = nullptr;
+  sp.h_doc_tok = sp.h_cnt = nullptr;
+}
+
+// (sp.mu held)  Buffers + one captured graph per HMM flag.  Returns false when anything fails: the caller then
+// takes the ordinary path, which reports the error if it is a real one.
+static bool small_prepare(jb_tokenizer* tk, int hmm) {
+  SmallPath& sp = tk->small;
+  if (sp.failed) return false;
+  if (sp.exec[hmm] && sp.path_of[hmm] == tk->path) return true;
+  auto bad = [&]() {
+    cudaGetLastError();
+    sp.failed = true;
+    return false;
+  };
+  if (!sp.stream) {
+    if (cudaStreamCreateWithFlags(&sp.stream, cudaStreamNonBlocking) != cudaSuccess) return bad();
+    const unsigned fl = cudaHostAllocMapped;
+    if (cudaHostAlloc(&sp.h_text, kSmallBytes + 64, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc(&sp.h_doc, (kSmallDocs + 1) * 8, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc(&sp.h_start, (kSmallBytes + 64) * 4, fl) != cudaSuccess || cudaHostAlloc(&sp.h_end, (kSmallBytes + 64) * 4, fl) != cudaSuccess ||
+        cudaHostAlloc(&sp.h_doc_tok, (kSmallDocs + 1) * 8, fl) != cudaSuccess || cudaHostAlloc(&sp.h_cnt, 16, fl) != cudaSuccess)
+      return bad();
+    if (workspace_reserve(sp.ws, kSmallBytes, kSmallDocs, tk->w_per_slot, true) != JB_OK) return bad();
+    memset(sp.h_text, ' ', kSmallBytes + 64);
+    for (uint32_t d = 0; d <= kSmallDocs; d++) sp.h_doc[d] = kSmallBytes;
+  }
+  sp.ws.seg_max_runes = tk->seg_max_runes;
+  void *d_start = nullptr, *d_end = nullptr, *d_doc_tok = nullptr, *d_cnt = nullptr;
+  if (cudaHostGetDevicePointer(&d_start, sp.h_start, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_end, sp.h_end, 0) != cudaSuccess ||
+      cudaHostGetDevicePointer(&d_doc_tok, sp.h_doc_tok, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_cnt, sp.h_cnt, 0) != cudaSuccess)
+    return bad();
+  PipeOut po;
+  po.d_start = (uint32_t*)d_start;
+  po.d_end = (uint32_t*)d_end;
+  po.cap_tokens = kSmallBytes + 64;
+  // at this size no list of the streaming path can overflow (blocks <= bytes / 4 < blocks_cap; deferred tokens and wide
+  // blocks <= bytes <= their capacities, see workspace_reserve): the general kernels stay out of the graph
+  po.no_general = true;
+  po.d_doc_tok_off = (uint64_t*)d_doc_tok;
+  po.d_n_tokens = (uint64_t*)d_cnt;
+  auto enqueue = [&]() -> bool {
+    if (cudaMemcpyAsync(sp.ws.text, sp.h_text, kSmallBytes, cudaMemcpyHostToDevice, sp.stream) != cudaSuccess) return false;
+    if (cudaMemcpyAsync(sp.ws.doc_off64, sp.h_doc, (kSmallDocs + 1) * 8, cudaMemcpyHostToDevice, sp.stream) != cudaSuccess) return false;
+    return run_pipeline(tk->T, sp.ws, sp.ws.text, kSmallBytes, sp.ws.doc_off64, kSmallDocs, hmm != 0, po, sp.stream, tk->path) == JB_OK;
+  };
+  // once outside a capture: lazily created streams / events / function attributes of the pipeline exist afterwards
+  if (!enqueue() || cudaStreamSynchronize(sp.stream) != cudaSuccess) return bad();
+  if (sp.exec[hmm]) {
+    cudaGraphExecDestroy(sp.exec[hmm]);
+    sp.exec[hmm] = nullptr;
+  }
+  cudaGraph_t g = nullptr;
+  if (cudaStreamBeginCapture(sp.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return bad();
+  const bool ok = enqueue();
+  if (cudaStreamEndCapture(sp.stream, &g) != cudaSuccess || !ok || !g) {
+    if (g) cudaGraphDestroy(g);
+    return bad();
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&sp.exec[hmm], g, 0);
+  cudaGraphDestroy(g);
+  if (ie != cudaSuccess) return bad();
+  sp.path_of[hmm] = tk->path;
+  return true;
+}
+
+// Returns 1 when the small path produced *out, 0 when the call must take the ordinary path.
+static int cut_small(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm, jb_result** out) {
+  static const bool disabled = getenv("JB_NO_SMALL") != nullptr;
+  const uint64_t nbytes = ndocs ? doc_off[ndocs] - doc_off[0] : 0;
+  if (disabled || ndocs == 0 || ndocs >= kSmallDocs || nbytes > kSmallBytes - 32) return 0;
+  SmallPath& sp = tk->small;
+  std::unique_lock<std::mutex> lk(sp.mu, std::try_to_lock);
+  if (!lk.owns_lock()) return 0;
+  if (cudaSetDevice(tk->device) != cudaSuccess) return 0;
+  const int hmm = use_hmm ? 1 : 0;
+  if (!small_prepare(tk, hmm)) return 0;
+  // the real documents, then one document that holds the padding (spaces: no tokens), then empty ones
+  if (nbytes) memcpy(sp.h_text, text + doc_off[0], nbytes);
+  for (uint64_t d = 0; d <= ndocs; d++) sp.h_doc[d] = doc_off[d] - doc_off[0];
+  bool ok = cudaGraphLaunch(sp.exec[hmm], sp.stream) == cudaSuccess && cudaStreamSynchronize(sp.stream) == cudaSuccess;
+  // leave the staging buffers as the capture expects them for the next call
+  if (nbytes) memset(sp.h_text, ' ', nbytes);
+  for (uint64_t d = 0; d <= ndocs; d++) sp.h_doc[d] = kSmallBytes;
+  if (!ok || sp.h_cnt[1] != 0) {
+    cudaGetLastError();
+    return 0;
+  }
+  const uint64_t nt = sp.h_cnt[0];
+  jb_result* res = new jb_result();
+  res->heap = true;
+  res->ndocs = ndocs;
+  res->nbytes = nbytes;
+  res->n_tokens = nt;
+  res->start = (uint32_t*)malloc((nt + 1) * 4);
+  res->end = (uint32_t*)malloc((nt + 1) * 4);
+  res->doc_tok = (uint64_t*)malloc((ndocs + 1) * 8);
+  if (!res->start || !res->end || !res->doc_tok) {
+    jb_result_free(res);
+    return 0;
+  }
+  memcpy(res->start, sp.h_start, nt * 4);
+  memcpy(res->end, sp.h_end, nt * 4);
+  memcpy(res->doc_tok, sp.h_doc_tok, (ndocs + 1) * 8);
+  *out = res;
+  return 1;
+}
+
 int jb_cut_batch(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t ndocs, int use_hmm, jb_result** out) {
   int rc = check_batch_args(tk, text, doc_off, ndocs, out);
   if (rc != JB_OK) return rc;
+  if (cut_small(tk, text, doc_off, ndocs, use_hmm, out)) return JB_OK;
   jb_result* res = new jb_result();
   res->ndocs = ndocs;
   res->nbytes = ndocs ? doc_off[ndocs] - doc_off[0] : 0;

@@ -1278,6 +1278,7 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ok = ok && dalloc(ws.ends, ntiles * kTileSlots + 8) && dalloc(ws.walks, ntiles * kTileSlots + 8);
     ok = ok && dalloc(ws.tile_sum, ntiles + 8) && dalloc(ws.tile_ctx, ntiles + 8);
     ws.deferred_cap = (uint32_t)(cap / 64 + 4096);
+    if (cap <= 65536) ws.deferred_cap = (uint32_t)cap + 64;  // (one gated token per byte at most: cannot overflow)
     ok = ok && dalloc(ws.deferred, (uint64_t)ws.deferred_cap);
     ws.wide_cap = (uint32_t)(cap / 256 + 4096);
     ok = ok && dalloc(ws.wide_list, (uint64_t)ws.wide_cap);
@@ -1534,7 +1535,7 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       g_launches.fetch_add(1);
       if (forked) cudaStreamWaitEvent(st, ws.ev_join, 0);
       PROF(4);
-      JB_LAUNCH(k_fallback_reset, (unsigned)g_num_sms * 4, 256, 0, st, ws.counters, ws.s_bits, ws.e_bits, nwords + 4);
+      if (!out.no_general) JB_LAUNCH(k_fallback_reset, (unsigned)g_num_sms * 4, 256, 0, st, ws.counters, ws.s_bits, ws.e_bits, nwords + 4);
     } else {
       PROF(2);
       PROF(3);
@@ -1547,11 +1548,13 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
     wa.count_idx = C_N_ENDS;
     wa.cursor_idx = C_CUR_WALK;
     wa.require_flag = force_general ? 0 : 1;
-    JB_LAUNCH(k_split<true>, sgrid, kSplitThreads, sizeof(SplitSmem), st, T, sa);
-    JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles, ws.counters, force_general ? 0 : 1);
-    JB_LAUNCH(k_split<false>, sgrid, kSplitThreads, sizeof(SplitSmem), st, T, sa);
-    launch_dp();
-    launch_walk();
+    if (force_general || !out.no_general) {
+      JB_LAUNCH(k_split<true>, sgrid, kSplitThreads, sizeof(SplitSmem), st, T, sa);
+      JB_LAUNCH(k_tile_scan, 1, 1024, 0, st, ws.tile_sum, ws.tile_ctx, ntiles, ws.counters, force_general ? 0 : 1);
+      JB_LAUNCH(k_split<false>, sgrid, kSplitThreads, sizeof(SplitSmem), st, T, sa);
+      launch_dp();
+      launch_walk();
+    }
     PROF(5);
     JB_LAUNCH(k_rank_count, nrt, kRankWords, 0, st, ws.s_bits, ws.e_bits, nwords, ws.rank_cnt);
   } else {

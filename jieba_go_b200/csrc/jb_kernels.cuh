@@ -107,6 +107,8 @@ struct PipeOut {
   uint32_t* d_e_bits = nullptr;
   bool bits_only = false;  // no (start,end) arrays at all: the bitmaps + doc_tok_off are the result (k_rank_scatter is not run)
   uint32_t pos0 = 0;       // the first document starts at byte pos0 (< 32) of d_text; bytes before it must be spaces
+  bool no_general = false; // the caller guarantees that no list of the streaming path can overflow (small fixed-size
+                           // batches with lists sized for the worst case): the flag-gated general kernels are not enqueued
 };
 
 // Enqueue the whole Cut pipeline for one batch on `stream`.
