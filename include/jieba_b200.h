@@ -214,9 +214,10 @@ int jb_cut_device_bits(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes,
 int jb_set_candidates_per_slot(jb_tokenizer* tk, double per_slot);
 /* 1: bypass the streaming fast path and run the general kernels on every block (testing) */
 int jb_set_general_only(jb_tokenizer* tk, int on);
-/* Kernel path of the Han blocks (testing / A-B measurements): 0 default (k_scan -> k_route -> k_emit, one lane per
- * block), 1 general kernels only, 2 k_scan -> k_seg (CTA-cooperative: position-parallel dictionary probes into shared
- * memory, then one lane per block; k_route + k_emit only for blocks longer than 1024 runes) */
+/* Kernel path of the Han blocks (testing / A-B measurements): 0 default, 1 general kernels only, 2 k_scan -> k_seg
+ * (CTA-cooperative: position-parallel dictionary probes into shared memory, then one lane per block; the lane-per-block
+ * kernels only for blocks longer than 1024 runes), 3 k_scan -> k_route -> k_emit (one lane per block, one position per
+ * iteration), 4 the same with k_route2 (four positions per iteration).  The default is 3 or 4. */
 int jb_set_path(jb_tokenizer* tk, int path);
 /* Test knob for path 2: Han blocks longer than max_runes (<= 1024; 0 = default) are left to k_route / k_emit by k_seg */
 int jb_set_seg_max_runes(jb_tokenizer* tk, uint32_t max_runes);

@@ -358,6 +358,11 @@ int jb_tokenizer_create(const jb_dict_desc* dict, const jb_hmm_desc* hmm, const 
   if (rc == JB_OK) rc = arena_put(tk, o_emit, img.emit, &T.emit);
   if (rc == JB_OK) rc = arena_put(tk, o_er, img.emit_supp_rune, &T.emit_supp_rune);
   if (rc == JB_OK) rc = arena_put(tk, o_es, img.emit_supp, &T.emit_supp);
+  if (getenv("JB_L2WIN") && (atoi(getenv("JB_L2WIN")) == 1 || atoi(getenv("JB_L2WIN")) == 3)) {  // (experiment: persisting window needs the carve-out)
+    int maxp = 0;
+    cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxp, off + (8u << 20)));
+  }
   if (rc != JB_OK) {
     jb_tokenizer_destroy(tk);
     return rc;
@@ -681,6 +686,10 @@ static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
     if (r != JB_OK) return fail(r, "device workspace allocation failed");
     Workspace& ws = sl->ws;
     ws.seg_max_runes = tk->seg_max_runes;
+  ws.l2_base = tk->table_base;
+  ws.l2_bytes = tk->table_bytes;
+    ws.l2_base = tk->table_base;
+    ws.l2_bytes = tk->table_bytes;
     if (!bits) {
       const uint64_t want = c.nb / 4 + 4096;
       if (ws.out_cap < want) {
@@ -902,6 +911,8 @@ static bool small_prepare(jb_tokenizer* tk, int hmm) {
     for (uint32_t d = 0; d <= kSmallDocs; d++) sp.h_doc[d] = kSmallBytes;
   }
   sp.ws.seg_max_runes = tk->seg_max_runes;
+  sp.ws.l2_base = tk->table_base;
+  sp.ws.l2_bytes = tk->table_bytes;
   void *d_start = nullptr, *d_end = nullptr, *d_doc_tok = nullptr, *d_cnt = nullptr;
   if (cudaHostGetDevicePointer(&d_start, sp.h_start, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_end, sp.h_end, 0) != cudaSuccess ||
       cudaHostGetDevicePointer(&d_doc_tok, sp.h_doc_tok, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_cnt, sp.h_cnt, 0) != cudaSuccess)
@@ -1145,6 +1156,8 @@ static int cut_device_impl(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nby
   int rc = workspace_reserve(ws, nbytes, ndocs, tk->w_per_slot, false);
   if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
   ws.seg_max_runes = tk->seg_max_runes;
+  ws.l2_base = tk->table_base;
+  ws.l2_bytes = tk->table_bytes;
   rc = run_pipeline(tk->T, ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, po, st, tk->path);
   cudaEventRecord(sl.ev, st);
   tk->dev_busy = true;
@@ -1182,7 +1195,7 @@ int jb_set_general_only(jb_tokenizer* tk, int on) {
   return JB_OK;
 }
 int jb_set_path(jb_tokenizer* tk, int path) {
-  if (!tk || path < PATH_DEFAULT || path > PATH_SEG) return fail(JB_EINVAL, "path must be 0 (default), 1 (general) or 2 (seg)");
+  if (!tk || path < PATH_DEFAULT || path > PATH_ROUTE2) return fail(JB_EINVAL, "path must be 0 (default), 1 (general), 2 (seg), 3 (k_route) or 4 (k_route2)");
   tk->path = path;
   return JB_OK;
 }
@@ -1242,6 +1255,8 @@ int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, u
   if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
   Workspace& ws = s.ws;
   ws.seg_max_runes = tk->seg_max_runes;
+  ws.l2_base = tk->table_base;
+  ws.l2_bytes = tk->table_bytes;
   uint64_t off[2] = {0, nbytes};
   CUDA_TRY(cudaMemcpy(ws.text, han_text, nbytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(ws.doc_off64, off, 16, cudaMemcpyHostToDevice));

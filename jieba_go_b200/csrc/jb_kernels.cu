@@ -1374,6 +1374,16 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       if (!ws.ev[i]) cudaEventCreate(&ws.ev[i]);
   }
   PROF(0);
+  if (getenv("JB_L2WIN") && atoi(getenv("JB_L2WIN")) == 3 && ws.l2_base) {  // EXPERIMENT: round 1's stream-wide persisting window
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.base_ptr = const_cast<void*>(ws.l2_base);
+    av.accessPolicyWindow.num_bytes = ws.l2_bytes;
+    av.accessPolicyWindow.hitRatio = 1.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
   cudaMemsetAsync(ws.counters, 0, C_NUM * sizeof(uint32_t), st);
   cudaMemsetAsync(ws.ds_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.s_bits, 0, ((uint64_t)nwords + 4) * 4, st);
@@ -1496,12 +1506,17 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       ra.count_idx = legacy ? C_N_BLK : C_N_LONG;
       ra.dbg_R = ws.dbg_R;
       ra.dbg_D = ws.dbg_D;
+      {
+        static const int env_route = getenv("JB_ROUTE") ? atoi(getenv("JB_ROUTE")) : 0;  // A/B measurements: 1 k_route, 2 k_route2
+        ra.chunked = path == PATH_ROUTE2 || (path != PATH_ROUTE1 && env_route != 1 && (env_route == 2 || kDefaultChunkedRoute));
+      }
       ra.counters = ws.counters;
       ra.path = ws.path;
       ra.wide_list = ws.wide_list;
       ra.wide_cap = ws.wide_cap;
       ra.min_chunk = 16;  // measured on 10k-rune blocks: fuller warps beat more warps (instruction issue is per warp)
-      launch_route(T, ra, g_num_sms, st);
+      const TableWindow tw{ws.l2_base, ws.l2_bytes};
+      launch_route(T, ra, g_num_sms, st, tw);
       g_launches.fetch_add(1);
       {
         WideArgs wa2;
@@ -1531,7 +1546,7 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       ea.s_bits = ws.s_bits;
       ea.e_bits = ws.e_bits;
       ea.min_chunk = 1;
-      launch_emit(T, ea, use_hmm, g_num_sms, st);
+      launch_emit(T, ea, use_hmm, g_num_sms, st, tw);
       g_launches.fetch_add(1);
       if (forked) cudaStreamWaitEvent(st, ws.ev_join, 0);
       PROF(4);

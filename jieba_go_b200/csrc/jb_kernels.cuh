@@ -49,6 +49,9 @@ struct Workspace {
   // side stream for the tile-summary scan (forked after k_scan, joined before the ranking)
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // the dictionary tables (one allocation): kernels that probe them are launched with an L2 access-policy window
+  const void* l2_base = nullptr;
+  size_t l2_bytes = 0;
   // capacity
   uint64_t cap_bytes = 0;
   uint32_t w_per_tile = 0;  // candidate weights reserved per tile
@@ -118,7 +121,7 @@ struct PipeOut {
 //   the blocks it leaves).
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_doc_off,
                  uint64_t ndocs, bool use_hmm, const PipeOut& out, cudaStream_t stream, int path = 0);
-enum { PATH_DEFAULT = 0, PATH_GENERAL = 1, PATH_SEG = 2 };
+enum { PATH_DEFAULT = 0, PATH_GENERAL = 1, PATH_SEG = 2, PATH_ROUTE1 = 3, PATH_ROUTE2 = 4 };
 
 // Second phase when d_start/d_end were NULL in run_pipeline (count first, then scatter).
 int run_scatter(Workspace& ws, uint32_t nbytes, uint64_t ndocs, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,

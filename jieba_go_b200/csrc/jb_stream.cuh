@@ -53,6 +53,7 @@ struct RouteArgs {
   uint32_t min_chunk;     // blocks a warp takes from the queue at least (few long blocks: lanes per warp vs warps per SM)
   double* dbg_R;          // optional (jb_debug_route): selected route value / word length per rune, index = lead byte / 3
   uint8_t* dbg_D;
+  bool chunked;           // k_route2 (four positions per iteration) instead of k_route
 };
 
 // k_seg: the Han blocks of k_scan's list, a few dozen at a time per CTA, entirely in shared memory
@@ -101,13 +102,19 @@ struct WideArgs {
   uint32_t* e_bits;
 };
 
+constexpr bool kDefaultChunkedRoute = false;  // which of k_route / k_route2 the default path uses
 constexpr uint32_t kSgMaxRunes = 1024;  // Han blocks up to this many runes are cut by k_seg
 
 int launch_seg(const JbTables& T, const SegArgs& A, bool hmm, int num_sms, cudaStream_t st);
 int launch_wide(const JbTables& T, const WideArgs& A, bool hmm, int num_sms, cudaStream_t st);
 int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st);
-int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st);
-int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st);
+// tables: the window of device memory that holds the dictionary tables (see launch_cfg in jb_stream.cu)
+struct TableWindow {
+  const void* base;
+  size_t bytes;
+};
+int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st, TableWindow tw);
+int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st, TableWindow tw);
 inline uint32_t scan_tiles(uint32_t n) { return (n + kScTileBytes - 1) / kScTileBytes; }
 
 #if defined(__CUDACC__)

@@ -14,8 +14,8 @@ pytestmark = pytest.mark.gpu
 
 # default streaming path (k_scan/k_route/k_emit) / k_seg (CTA-cooperative) / the same with blocks over 12 runes handed to
 # k_route + k_emit / general kernels only
-PATHS = ["stream", "seg", "seg12", "general"]
-_PATH_ARGS = {"stream": (0, 0), "seg": (2, 0), "seg12": (2, 12), "general": (1, 0)}
+PATHS = ["stream", "route1", "route2", "seg", "seg12", "general"]
+_PATH_ARGS = {"stream": (0, 0), "route1": (3, 0), "route2": (4, 0), "seg": (2, 0), "seg12": (2, 12), "general": (1, 0)}
 
 
 def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="stream", **kw):
