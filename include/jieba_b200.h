@@ -144,6 +144,17 @@ int jb_tokenizer_create_from_files(const char* dict_path, int dict_mode, const c
 /* NewJiebaTokenizer() T:69-75: prefix_dictionary.gob (size 60,101,967, T:454) + prob_emit.json */
 int jb_tokenizer_create_from_gob(const char* gob_path, int64_t size, const char* emit_json_path,
                                  const jb_options* opt, jb_tokenizer** out);
+/*
+ * The same two constructors with a CACHED TABLE IMAGE -- what prefix_dictionary.gob is to dict.txt in the reference
+ * (T:439-458: a pre-built form of the parsed dictionary), taken one step further: the device tables themselves.
+ * dict_kind = JB_DICT_FILE_MODE / JB_DICT_PREFIX_MODE (dict.txt) or JB_DICT_GOB (then gob_size = pd.size, T:454).
+ * image_path: written on the first call, read back afterwards; it is keyed by the SHA-256 of both files' bytes, the
+ * kind / size, the Unicode version and the format version, so a stale or damaged image is rebuilt, never used.
+ * *from_cache (optional) = 1 when the image was used.  math.Log values are the library's (jb_go_log).
+ */
+#define JB_DICT_GOB 2
+int jb_tokenizer_create_cached(const char* dict_path, int dict_kind, int64_t gob_size, const char* emit_json_path,
+                               const jb_options* opt, const char* image_path, int* from_cache, jb_tokenizer** out);
 void jb_tokenizer_destroy(jb_tokenizer* tk);
 
 /* ---- Cut ------------------------------------------------------------------------------ */
@@ -214,13 +225,6 @@ int jb_cut_device_bits(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes,
 int jb_set_candidates_per_slot(jb_tokenizer* tk, double per_slot);
 /* 1: bypass the streaming fast path and run the general kernels on every block (testing) */
 int jb_set_general_only(jb_tokenizer* tk, int on);
-/* Kernel path of the Han blocks (testing / A-B measurements): 0 default, 1 general kernels only, 2 k_scan -> k_seg
- * (CTA-cooperative: position-parallel dictionary probes into shared memory, then one lane per block; the lane-per-block
- * kernels only for blocks longer than 1024 runes), 3 k_scan -> k_route -> k_emit (one lane per block, one position per
- * iteration), 4 the same with k_route2 (four positions per iteration).  The default is 3 or 4. */
-int jb_set_path(jb_tokenizer* tk, int path);
-/* Test knob for path 2: Han blocks longer than max_runes (<= 1024; 0 = default) are left to k_route / k_emit by k_seg */
-int jb_set_seg_max_runes(jb_tokenizer* tk, uint32_t max_runes);
 
 /* ---- introspection (tests / bench) ------------------------------------------------------ */
 uint64_t jb_kernel_launch_count(void); /* kernels launched by this library in this process */
@@ -237,6 +241,8 @@ int jb_profile_read(jb_tokenizer* tk, double* ms_total, uint64_t* steps, int res
 /* Debug: per-rune route values R[i] = (end, proba) of one Han block (maxIndexProba of dagProba[i]) */
 int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, uint32_t* best_end,
                    double* best_proba, uint64_t cap);
+/* the SHA-256 that keys the cached table image (tests compare it with a reference implementation) */
+void jb_debug_sha256(const uint8_t* data, uint64_t len, uint8_t out[32]);
 /* dictionary probe through the device tables: returns 0 missing, 1 present with freq 0, 2 present freq>0
  * (weight = log(freq) - log(size) stored in *w) */
 int jb_debug_lookup(jb_tokenizer* tk, const uint8_t* key, uint64_t len, double* w);

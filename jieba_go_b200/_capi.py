@@ -54,6 +54,7 @@ SYMBOLS = {
     "jb_tokenizer_create": (C.c_int, [C.POINTER(DictDesc), C.POINTER(HmmDesc), C.POINTER(Options), _PP]),
     "jb_tokenizer_create_from_files": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(Options), _PP]),
     "jb_tokenizer_create_from_gob": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.POINTER(Options), _PP]),
+    "jb_tokenizer_create_cached": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, C.c_char_p, C.POINTER(Options), C.c_char_p, C.POINTER(C.c_int), _PP]),
     "jb_tokenizer_destroy": (None, [_P]),
     "jb_cut": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _PP]),
     "jb_cut_batch": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int, _PP]),
@@ -73,14 +74,13 @@ SYMBOLS = {
     "jb_cut_device": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, _P, _P, C.c_uint64, _P, _P, _P]),
     "jb_set_candidates_per_slot": (C.c_int, [_P, C.c_double]),
     "jb_set_general_only": (C.c_int, [_P, C.c_int]),
-    "jb_set_path": (C.c_int, [_P, C.c_int]),
-    "jb_set_seg_max_runes": (C.c_int, [_P, C.c_uint32]),
     "jb_kernel_launch_count": (C.c_uint64, []),
     "jb_profile_enable": (C.c_int, [_P, C.c_int]),
     "jb_profile_num_kernels": (C.c_int, []),
     "jb_profile_kernel_name": (C.c_char_p, [C.c_int]),
     "jb_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "jb_debug_route": (C.c_int, [_P, C.c_char_p, C.c_uint64, _P, _P, C.c_uint64]),
+    "jb_debug_sha256": (None, [C.c_char_p, C.c_uint64, C.c_char_p]),
     "jb_debug_lookup": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.POINTER(C.c_double)]),
 }
 

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjieba_b200.so")
-SOURCES = ["jb_kernels.cu", "jb_stream.cu", "jb_seg.cu", "jb_api.cu", "jb_host.cpp"]
+SOURCES = ["jb_kernels.cu", "jb_stream.cu", "jb_api.cu", "jb_host.cpp"]
 HEADERS = ["jb_common.h", "jb_host.h", "jb_kernels.cuh", "jb_stream.cuh", os.path.join("..", "..", "include", "jieba_b200.h")]
 
 NVCC_FLAGS = [

@@ -78,8 +78,7 @@ struct jb_tokenizer {
   size_t table_bytes = 0;
   uint64_t max_batch = 128ull << 20;
   double w_per_slot = 3.0;
-  int path = PATH_DEFAULT;  // PATH_GENERAL / PATH_SEG: tests and A/B measurements
-  uint32_t seg_max_runes = 0;
+  int path = PATH_DEFAULT;  // PATH_GENERAL: tests
   std::mutex mu;
   std::vector<WsSlot*> free_ws;
   // jb_cut_device: ONE workspace per tokenizer.  Calls are serialised ON THE DEVICE: every call records dev_ws.ev at
@@ -190,6 +189,11 @@ const char* jb_last_error(void) { return g_err.c_str(); }
 void jb_hmm_defaults(jb_hmm_desc* h) { hmm_defaults(h); }
 double jb_go_log(double x) { return go_log(x); }
 uint64_t jb_kernel_launch_count(void) { return kernel_launch_count(); }
+void jb_debug_sha256(const uint8_t* data, uint64_t len, uint8_t out[32]) {
+  Sha256 sh;
+  sh.update(data, len);
+  sh.finish(out);
+}
 uint64_t jb_host_pool_limit(uint64_t max_bytes) {
   uint64_t held;
   {
@@ -323,8 +327,19 @@ void jb_emit_buf_fill(const jb_emit_buf* e, jb_hmm_desc* hmm) {
 void jb_emit_buf_free(jb_emit_buf* e) { delete e; }
 
 // ---- tokenizer ------------------------------------------------------------------------------
+static int create_from_image(const TableImage& img, const jb_options* opt, jb_tokenizer** out);
+
 int jb_tokenizer_create(const jb_dict_desc* dict, const jb_hmm_desc* hmm, const jb_options* opt, jb_tokenizer** out) {
   if (!dict || !hmm || !out) return fail(JB_EINVAL, "null argument");
+  TableImage img;
+  std::string err;
+  int rc = build_tables(dict, hmm, opt ? opt->unicode_version : 15, img, err);
+  if (rc != JB_OK) return fail(rc, err);
+  return create_from_image(img, opt, out);
+}
+
+// the device half of tokenizer creation: one allocation for all tables, upload, parameter block
+static int create_from_image(const TableImage& img, const jb_options* opt, jb_tokenizer** out) {
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -333,10 +348,7 @@ int jb_tokenizer_create(const jb_dict_desc* dict, const jb_hmm_desc* hmm, const 
   if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
   if (dev >= ndev) return fail(JB_EINVAL, "device ordinal out of range");
   CUDA_TRY(cudaSetDevice(dev));
-  TableImage img;
-  std::string err;
-  int rc = build_tables(dict, hmm, opt ? opt->unicode_version : 15, img, err);
-  if (rc != JB_OK) return fail(rc, err);
+  int rc = JB_OK;
   jb_tokenizer* tk = new jb_tokenizer();
   tk->device = dev;
   if (opt && opt->max_batch_bytes) tk->max_batch = opt->max_batch_bytes;
@@ -358,11 +370,6 @@ int jb_tokenizer_create(const jb_dict_desc* dict, const jb_hmm_desc* hmm, const 
   if (rc == JB_OK) rc = arena_put(tk, o_emit, img.emit, &T.emit);
   if (rc == JB_OK) rc = arena_put(tk, o_er, img.emit_supp_rune, &T.emit_supp_rune);
   if (rc == JB_OK) rc = arena_put(tk, o_es, img.emit_supp, &T.emit_supp);
-  if (getenv("JB_L2WIN") && (atoi(getenv("JB_L2WIN")) == 1 || atoi(getenv("JB_L2WIN")) == 3)) {  // (experiment: persisting window needs the carve-out)
-    int maxp = 0;
-    cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
-    if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxp, off + (8u << 20)));
-  }
   if (rc != JB_OK) {
     jb_tokenizer_destroy(tk);
     return rc;
@@ -397,6 +404,62 @@ static int create_from_bufs(jb_dict_buf* db, const char* emit_json_path, const j
   rc = jb_tokenizer_create(&dd, &hd, opt, out);
   jb_emit_buf_free(eb);
   return rc;
+}
+
+// NewTokenizer / NewJiebaTokenizer with a cached table image next to the data: the first call parses the files, builds
+// the tables and writes the image; later calls with the same bytes in the files only read it back (its key is the
+// SHA-256 of both files, the loader's mode / size literal, the Unicode version and the image format).
+int jb_tokenizer_create_cached(const char* dict_path, int dict_kind, int64_t gob_size, const char* emit_json_path, const jb_options* opt,
+                               const char* image_path, int* from_cache, jb_tokenizer** out) {
+  if (!dict_path || !emit_json_path || !image_path || !out) return fail(JB_EINVAL, "null argument");
+  if (dict_kind != JB_DICT_FILE_MODE && dict_kind != JB_DICT_PREFIX_MODE && dict_kind != JB_DICT_GOB) return fail(JB_EINVAL, "bad dictionary kind");
+  std::vector<uint8_t> dbytes, ebytes;
+  std::string err;
+  int rc = read_file(dict_path, dbytes, err);
+  if (rc == JB_OK) rc = read_file(emit_json_path, ebytes, err);
+  if (rc != JB_OK) return fail(rc, err);
+  const int ver = (opt && opt->unicode_version == 13) ? 13 : 15;
+  uint8_t key[32];
+  {
+    Sha256 sh;
+    const int64_t meta[4] = {dict_kind, gob_size, ver, (int64_t)JB_VERSION};
+    const uint64_t lens[2] = {dbytes.size(), ebytes.size()};
+    sh.update(meta, sizeof meta);
+    sh.update(lens, sizeof lens);
+    sh.update(dbytes.data(), dbytes.size());
+    sh.update(ebytes.data(), ebytes.size());
+    sh.finish(key);
+  }
+  TableImage img;
+  if (from_cache) *from_cache = 0;
+  if (table_image_load(image_path, key, img, err) == JB_OK) {
+    if (from_cache) *from_cache = 1;
+    return create_from_image(img, opt, out);
+  }
+  // absent, stale or damaged: build from the files and (re)write the image
+  img = TableImage();  // (a damaged image may have been read in part)
+  jb_dict_buf* db = nullptr;
+  rc = dict_kind == JB_DICT_GOB ? jb_dict_load_gob(dbytes.data(), dbytes.size(), &db) : jb_dict_load_text(dbytes.data(), dbytes.size(), dict_kind, &db);
+  if (rc != JB_OK) return rc;
+  if (dict_kind == JB_DICT_GOB) jb_dict_buf_set_size(db, gob_size);
+  jb_emit_buf* eb = nullptr;
+  rc = jb_emit_load_json(ebytes.data(), ebytes.size(), &eb);
+  if (rc != JB_OK) {
+    jb_dict_buf_free(db);
+    return rc;
+  }
+  jb_dict_desc dd;
+  jb_dict_buf_desc(db, &dd);
+  jb_hmm_desc hd;
+  jb_hmm_defaults(&hd);
+  jb_emit_buf_fill(eb, &hd);
+  rc = build_tables(&dd, &hd, ver, img, err);
+  jb_emit_buf_free(eb);
+  jb_dict_buf_free(db);
+  if (rc != JB_OK) return fail(rc, err);
+  std::string werr;
+  table_image_save(img, key, image_path, werr);  // best effort: a read-only directory only costs the rebuild next time
+  return create_from_image(img, opt, out);
 }
 
 int jb_tokenizer_create_from_files(const char* dict_path, int dict_mode, const char* emit_json_path, const jb_options* opt,
@@ -685,11 +748,6 @@ static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
     int r = workspace_reserve(sl->ws, dev_bytes, c.d1 - c.d0, wps, true);
     if (r != JB_OK) return fail(r, "device workspace allocation failed");
     Workspace& ws = sl->ws;
-    ws.seg_max_runes = tk->seg_max_runes;
-  ws.l2_base = tk->table_base;
-  ws.l2_bytes = tk->table_bytes;
-    ws.l2_base = tk->table_base;
-    ws.l2_bytes = tk->table_bytes;
     if (!bits) {
       const uint64_t want = c.nb / 4 + 4096;
       if (ws.out_cap < want) {
@@ -910,9 +968,6 @@ static bool small_prepare(jb_tokenizer* tk, int hmm) {
     memset(sp.h_text, ' ', kSmallBytes + 64);
     for (uint32_t d = 0; d <= kSmallDocs; d++) sp.h_doc[d] = kSmallBytes;
   }
-  sp.ws.seg_max_runes = tk->seg_max_runes;
-  sp.ws.l2_base = tk->table_base;
-  sp.ws.l2_bytes = tk->table_bytes;
   void *d_start = nullptr, *d_end = nullptr, *d_doc_tok = nullptr, *d_cnt = nullptr;
   if (cudaHostGetDevicePointer(&d_start, sp.h_start, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_end, sp.h_end, 0) != cudaSuccess ||
       cudaHostGetDevicePointer(&d_doc_tok, sp.h_doc_tok, 0) != cudaSuccess || cudaHostGetDevicePointer(&d_cnt, sp.h_cnt, 0) != cudaSuccess)
@@ -1155,9 +1210,6 @@ static int cut_device_impl(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nby
   }
   int rc = workspace_reserve(ws, nbytes, ndocs, tk->w_per_slot, false);
   if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
-  ws.seg_max_runes = tk->seg_max_runes;
-  ws.l2_base = tk->table_base;
-  ws.l2_bytes = tk->table_bytes;
   rc = run_pipeline(tk->T, ws, d_text, (uint32_t)nbytes, d_doc_off, ndocs, use_hmm != 0, po, st, tk->path);
   cudaEventRecord(sl.ev, st);
   tk->dev_busy = true;
@@ -1192,16 +1244,6 @@ int jb_cut_device_bits(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nbytes,
 int jb_set_general_only(jb_tokenizer* tk, int on) {
   if (!tk) return JB_EINVAL;
   tk->path = on ? PATH_GENERAL : PATH_DEFAULT;
-  return JB_OK;
-}
-int jb_set_path(jb_tokenizer* tk, int path) {
-  if (!tk || path < PATH_DEFAULT || path > PATH_ROUTE2) return fail(JB_EINVAL, "path must be 0 (default), 1 (general), 2 (seg), 3 (k_route) or 4 (k_route2)");
-  tk->path = path;
-  return JB_OK;
-}
-int jb_set_seg_max_runes(jb_tokenizer* tk, uint32_t max_runes) {
-  if (!tk) return JB_EINVAL;
-  tk->seg_max_runes = max_runes;
   return JB_OK;
 }
 int jb_profile_enable(jb_tokenizer* tk, int on) {
@@ -1254,9 +1296,6 @@ int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, u
   int rc = workspace_reserve(s.ws, nbytes, 1, tk->w_per_slot, true);
   if (rc != JB_OK) return fail(rc, "device workspace allocation failed");
   Workspace& ws = s.ws;
-  ws.seg_max_runes = tk->seg_max_runes;
-  ws.l2_base = tk->table_base;
-  ws.l2_bytes = tk->table_bytes;
   uint64_t off[2] = {0, nbytes};
   CUDA_TRY(cudaMemcpy(ws.text, han_text, nbytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(ws.doc_off64, off, 16, cudaMemcpyHostToDevice));
@@ -1265,7 +1304,7 @@ int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, u
   dbg_out.d_doc_tok_off = ws.out_doc_tok;
   dbg_out.d_n_tokens = ws.out_ntok;
   if (tk->path != PATH_GENERAL) {
-    // streaming path (k_route, or k_seg with PATH_SEG): per rune, index = lead byte / 3.
+    // streaming path (k_route): per rune, index = lead byte / 3.
     // Only for text whose runes all have 3 bytes (a 4-byte rune sends its block to k_wide, which records nothing).
     const uint64_t nr = nbytes / 3;
     if (nr * 3 != nbytes) return fail(JB_EINVAL, "jb_debug_route on the streaming path needs 3-byte runes only");

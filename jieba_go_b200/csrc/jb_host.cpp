@@ -694,4 +694,168 @@ int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int ver, Tabl
   return JB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// SHA-256 (FIPS 180-4) and the table-image file
+// ------------------------------------------------------------------------------------------
+static const uint32_t kShaK[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+    0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+    0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+    0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+    0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+    0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+static inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static void sha_block(uint32_t h[8], const uint8_t* p) {
+  uint32_t w[64];
+  for (int i = 0; i < 16; i++) w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
+  for (int i = 16; i < 64; i++) {
+    const uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3), s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+    w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+  }
+  uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+  for (int i = 0; i < 64; i++) {
+    const uint32_t t1 = hh + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + kShaK[i] + w[i];
+    const uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+    hh = g, g = f, f = e, e = d + t1, d = c, c = b, b = a, a = t1 + t2;
+  }
+  h[0] += a, h[1] += b, h[2] += c, h[3] += d, h[4] += e, h[5] += f, h[6] += g, h[7] += hh;
+}
+Sha256::Sha256() {
+  static const uint32_t init[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  memcpy(h, init, sizeof h);
+}
+void Sha256::update(const void* data, size_t n) {
+  const uint8_t* p = (const uint8_t*)data;
+  len += n;
+  if (fill) {
+    const size_t take = std::min(n, 64 - fill);
+    memcpy(buf + fill, p, take);
+    fill += take, p += take, n -= take;
+    if (fill < 64) return;
+    sha_block(h, buf);
+    fill = 0;
+  }
+  for (; n >= 64; p += 64, n -= 64) sha_block(h, p);
+  if (n) {
+    memcpy(buf, p, n);
+    fill = n;
+  }
+}
+void Sha256::finish(uint8_t out[32]) {
+  const uint64_t bits = len * 8;
+  const uint8_t one = 0x80, zero = 0;
+  update(&one, 1);
+  while (fill != 56) update(&zero, 1);
+  uint8_t lb[8];
+  for (int i = 0; i < 8; i++) lb[i] = (uint8_t)(bits >> (56 - 8 * i));
+  update(lb, 8);
+  for (int i = 0; i < 8; i++) {
+    out[4 * i] = (uint8_t)(h[i] >> 24), out[4 * i + 1] = (uint8_t)(h[i] >> 16), out[4 * i + 2] = (uint8_t)(h[i] >> 8), out[4 * i + 3] = (uint8_t)h[i];
+  }
+}
+
+namespace {
+const char kImgMagic[8] = {'J', 'B', 'T', 'I', '0', '0', '0', '2'};  // bump when JbFirst / JbEntry / the hash change
+struct ImgHeader {
+  char magic[8];
+  uint8_t key[32];
+  uint64_t n_first, n_entries, n_emit, n_emit_supp_rune, n_emit_supp, n_han_bits, n_supp;
+  double neg_log_total, start[4], trans[4][2];
+  uint32_t max_delta, pad;
+  uint64_t n_han_keys, n_dropped_keys, n_unreachable_keys;
+  uint64_t payload_fnv;  // FNV-1a over the payload, 8 bytes at a time
+};
+uint64_t fnv64(uint64_t h, const void* data, size_t n) {
+  const uint8_t* p = (const uint8_t*)data;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t v;
+    memcpy(&v, p + i, 8);
+    h = (h ^ v) * 0x100000001B3ull;
+  }
+  for (; i < n; i++) h = (h ^ p[i]) * 0x100000001B3ull;
+  return h;
+}
+template <typename F>
+void each_array(TableImage& img, F f) {
+  f(img.first), f(img.entries), f(img.emit), f(img.emit_supp_rune), f(img.emit_supp), f(img.han_bits), f(img.supp_lo), f(img.supp_hi);
+}
+}  // namespace
+
+int table_image_save(const TableImage& cimg, const uint8_t key[32], const char* path, std::string& err) {
+  TableImage& img = const_cast<TableImage&>(cimg);
+  ImgHeader hd;
+  memset(&hd, 0, sizeof hd);
+  memcpy(hd.magic, kImgMagic, 8);
+  memcpy(hd.key, key, 32);
+  hd.n_first = img.first.size(), hd.n_entries = img.entries.size(), hd.n_emit = img.emit.size();
+  hd.n_emit_supp_rune = img.emit_supp_rune.size(), hd.n_emit_supp = img.emit_supp.size(), hd.n_han_bits = img.han_bits.size();
+  hd.n_supp = img.supp_lo.size();
+  hd.neg_log_total = img.neg_log_total;
+  memcpy(hd.start, img.start, sizeof hd.start);
+  memcpy(hd.trans, img.trans, sizeof hd.trans);
+  hd.max_delta = img.max_delta;
+  hd.n_han_keys = img.n_han_keys, hd.n_dropped_keys = img.n_dropped_keys, hd.n_unreachable_keys = img.n_unreachable_keys;
+  uint64_t h = 0xCBF29CE484222325ull;
+  each_array(img, [&](auto& v) { h = fnv64(h, v.data(), v.size() * sizeof(v[0])); });
+  hd.payload_fnv = h;
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) {
+    err = std::string("cannot write ") + tmp;
+    return JB_EIO;
+  }
+  bool ok = fwrite(&hd, sizeof hd, 1, f) == 1;
+  each_array(img, [&](auto& v) { ok = ok && (v.empty() || fwrite(v.data(), sizeof(v[0]), v.size(), f) == v.size()); });
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) {  // (rename: a reader never sees half a file)
+    remove(tmp.c_str());
+    err = std::string("cannot write ") + path;
+    return JB_EIO;
+  }
+  return JB_OK;
+}
+
+int table_image_load(const char* path, const uint8_t key[32], TableImage& img, std::string& err) {
+  FILE* f = fopen(path, "rb");
+  if (!f) {
+    err = std::string("no table image at ") + path;
+    return JB_EIO;
+  }
+  ImgHeader hd;
+  bool ok = fread(&hd, sizeof hd, 1, f) == 1;
+  if (!ok || memcmp(hd.magic, kImgMagic, 8) != 0 || memcmp(hd.key, key, 32) != 0) {
+    fclose(f);
+    err = "table image is of another format version or was built from other inputs";
+    return JB_EFORMAT;
+  }
+  const uint64_t lim = 1ull << 31;
+  if (hd.n_first != 65536 || hd.n_entries > lim || (hd.n_entries & (hd.n_entries - 1)) || hd.n_entries < 2 || hd.n_emit != 65536 * 4 || hd.n_emit_supp_rune > lim ||
+      hd.n_emit_supp != hd.n_emit_supp_rune * 4 || hd.n_han_bits != 2048 || hd.n_supp > JB_MAX_SUPP_RANGES || hd.max_delta > JB_MAX_DELTA) {
+    fclose(f);
+    err = "table image header is inconsistent";
+    return JB_EFORMAT;
+  }
+  img.first.resize(hd.n_first), img.entries.resize(hd.n_entries), img.emit.resize(hd.n_emit), img.emit_supp_rune.resize(hd.n_emit_supp_rune);
+  img.emit_supp.resize(hd.n_emit_supp), img.han_bits.resize(hd.n_han_bits), img.supp_lo.resize(hd.n_supp), img.supp_hi.resize(hd.n_supp);
+  uint64_t h = 0xCBF29CE484222325ull;
+  each_array(img, [&](auto& v) {
+    ok = ok && (v.empty() || fread(v.data(), sizeof(v[0]), v.size(), f) == v.size());
+    if (ok) h = fnv64(h, v.data(), v.size() * sizeof(v[0]));
+  });
+  uint8_t extra;
+  ok = ok && fread(&extra, 1, 1, f) == 0;  // nothing after the payload
+  fclose(f);
+  if (!ok || h != hd.payload_fnv) {
+    err = "table image is truncated or damaged";
+    return JB_EFORMAT;
+  }
+  img.neg_log_total = hd.neg_log_total;
+  memcpy(img.start, hd.start, sizeof hd.start);
+  memcpy(img.trans, hd.trans, sizeof hd.trans);
+  img.max_delta = hd.max_delta;
+  img.n_han_keys = hd.n_han_keys, img.n_dropped_keys = hd.n_dropped_keys, img.n_unreachable_keys = hd.n_unreachable_keys;
+  return JB_OK;
+}
+
 }  // namespace jb

@@ -63,4 +63,19 @@ void hmm_defaults(jb_hmm_desc* h);
 int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int unicode_version, TableImage& img,
                  std::string& err);
 
+// Cached table image: what prefix_dictionary.gob is to dict.txt in the reference (tokenizer.go:439-458, a pre-built
+// form of the parsed dictionary), one step further -- the device tables themselves.  `key` = SHA-256 of everything the
+// image depends on; a file with another key, another format version or a damaged payload is refused (JB_EFORMAT).
+struct Sha256 {
+  uint32_t h[8];
+  uint64_t len = 0;
+  uint8_t buf[64];
+  size_t fill = 0;
+  Sha256();
+  void update(const void* data, size_t n);
+  void finish(uint8_t out[32]);
+};
+int table_image_save(const TableImage& img, const uint8_t key[32], const char* path, std::string& err);
+int table_image_load(const char* path, const uint8_t key[32], TableImage& img, std::string& err);
+
 }  // namespace jb

@@ -1310,7 +1310,7 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
 
 const char* const kProfKernelNames[kNumProfKernels] = {"k_docstart+memset",
                                                        "k_scan",
-                                                       "k_route (+k_wide; k_seg with PATH_SEG)",
+                                                       "k_route (+k_wide)",
                                                        "k_emit (k_tile_scan+k_resolve_deferred on a side stream)",
                                                        "general pipeline (flagged batches)",
                                                        "k_rank_count",
@@ -1374,16 +1374,6 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       if (!ws.ev[i]) cudaEventCreate(&ws.ev[i]);
   }
   PROF(0);
-  if (getenv("JB_L2WIN") && atoi(getenv("JB_L2WIN")) == 3 && ws.l2_base) {  // EXPERIMENT: round 1's stream-wide persisting window
-    cudaStreamAttrValue av;
-    memset(&av, 0, sizeof av);
-    av.accessPolicyWindow.base_ptr = const_cast<void*>(ws.l2_base);
-    av.accessPolicyWindow.num_bytes = ws.l2_bytes;
-    av.accessPolicyWindow.hitRatio = 1.0f;
-    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-  }
   cudaMemsetAsync(ws.counters, 0, C_NUM * sizeof(uint32_t), st);
   cudaMemsetAsync(ws.ds_bits, 0, ((uint64_t)nwords + 4) * 4, st);
   cudaMemsetAsync(ws.s_bits, 0, ((uint64_t)nwords + 4) * 4, st);
@@ -1476,47 +1466,19 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
                   ws.e_bits);
         if (forked) cudaEventRecord(ws.ev_join, sx);
       }
-      const bool legacy = path != PATH_SEG;  // lane-per-block kernels for every block
-      if (!legacy) {
-        SegArgs sg;
-        sg.text = d_text;
-        sg.n = n;
-        sg.tile_last_hs = ws.tile_last_hs;
-        sg.blocks = ws.ends;
-        sg.blocks_cap = ws.blocks_cap;
-        sg.counters = ws.counters;
-        sg.long_blocks = ws.walks;  // (the general path's walk list: unused unless the batch is flagged, and then rebuilt)
-        sg.long_cap = ws.blocks_cap;
-        sg.max_runes = ws.seg_max_runes ? std::min(ws.seg_max_runes, kSgMaxRunes) : kSgMaxRunes;
-        sg.wide_list = ws.wide_list;
-        sg.wide_cap = ws.wide_cap;
-        sg.s_bits = ws.s_bits;
-        sg.e_bits = ws.e_bits;
-        sg.dbg_R = ws.dbg_R;
-        sg.dbg_D = ws.dbg_D;
-        launch_seg(T, sg, use_hmm, g_num_sms, st);
-        g_launches.fetch_add(1);
-      }
-      // k_route / k_emit: every block, or (PATH_SEG) the blocks k_seg left
       RouteArgs ra;
       ra.text = d_text;
       ra.tile_last_hs = ws.tile_last_hs;
-      ra.blocks = legacy ? ws.ends : ws.walks;
+      ra.blocks = ws.ends;
       ra.blocks_cap = ws.blocks_cap;
-      ra.count_idx = legacy ? C_N_BLK : C_N_LONG;
       ra.dbg_R = ws.dbg_R;
       ra.dbg_D = ws.dbg_D;
-      {
-        static const int env_route = getenv("JB_ROUTE") ? atoi(getenv("JB_ROUTE")) : 0;  // A/B measurements: 1 k_route, 2 k_route2
-        ra.chunked = path == PATH_ROUTE2 || (path != PATH_ROUTE1 && env_route != 1 && (env_route == 2 || kDefaultChunkedRoute));
-      }
       ra.counters = ws.counters;
       ra.path = ws.path;
       ra.wide_list = ws.wide_list;
       ra.wide_cap = ws.wide_cap;
       ra.min_chunk = 16;  // measured on 10k-rune blocks: fuller warps beat more warps (instruction issue is per warp)
-      const TableWindow tw{ws.l2_base, ws.l2_bytes};
-      launch_route(T, ra, g_num_sms, st, tw);
+      launch_route(T, ra, g_num_sms, st);
       g_launches.fetch_add(1);
       {
         WideArgs wa2;
@@ -1537,16 +1499,15 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       PROF(3);
       EmitArgs ea;
       ea.text = d_text;
-      ea.blocks = legacy ? ws.ends : ws.walks;
+      ea.blocks = ws.ends;
       ea.blocks_cap = ws.blocks_cap;
-      ea.count_idx = legacy ? C_N_BLK : C_N_LONG;
       ea.counters = ws.counters;
       ea.path = ws.path;
       ea.bp = ws.bp;
       ea.s_bits = ws.s_bits;
       ea.e_bits = ws.e_bits;
       ea.min_chunk = 1;
-      launch_emit(T, ea, use_hmm, g_num_sms, st, tw);
+      launch_emit(T, ea, use_hmm, g_num_sms, st);
       g_launches.fetch_add(1);
       if (forked) cudaStreamWaitEvent(st, ws.ev_join, 0);
       PROF(4);

@@ -28,8 +28,6 @@ enum Counter {
   C_N_WIDE = 6,    // Han blocks with a 4-byte rune, handed to k_wide
   C_N_DEFER = 7,   // gated non-Han tokens waiting for the tile-summary scan
   C_FLAGS = 8,     // bit0: the batch must be redone by the general pipeline
-  C_N_LONG = 9,    // Han blocks k_seg left to k_route / k_emit
-  C_CUR_SEG = 10,  // work cursor of k_seg
   C_N_BLK = 12,    // Han blocks listed by k_scan for k_route / k_emit
   C_CUR_ROUTE = 13,  // work cursors of k_route / k_emit
   C_CUR_EMIT = 14,
@@ -49,9 +47,6 @@ struct Workspace {
   // side stream for the tile-summary scan (forked after k_scan, joined before the ranking)
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  // the dictionary tables (one allocation): kernels that probe them are launched with an L2 access-policy window
-  const void* l2_base = nullptr;
-  size_t l2_bytes = 0;
   // capacity
   uint64_t cap_bytes = 0;
   uint32_t w_per_tile = 0;  // candidate weights reserved per tile
@@ -84,7 +79,6 @@ struct Workspace {
   double* dbg_proba = nullptr;   // optional: selected route value per slot (general path)
   double* dbg_R = nullptr;       // optional: selected route value / word length per rune (streaming path)
   uint8_t* dbg_D = nullptr;
-  uint32_t seg_max_runes = 0;    // test knob: blocks longer than this go to k_route / k_emit (0: default)
   // outputs for host-memory batches
   uint32_t* out_start = nullptr;
   uint32_t* out_end = nullptr;
@@ -116,12 +110,11 @@ struct PipeOut {
 
 // Enqueue the whole Cut pipeline for one batch on `stream`.
 //   d_text[nbytes], d_doc_off[ndocs+1] (uint64, absolute; doc_off[0] is subtracted, out.pos0 added) on device.
-//   path: PATH_DEFAULT k_scan -> k_route -> k_emit (lane per block); PATH_GENERAL skip the fast path and run the general
-//   kernels on everything; PATH_SEG k_scan -> k_seg (CTA-cooperative, shared-memory candidates; k_route / k_emit only for
-//   the blocks it leaves).
+//   path: PATH_DEFAULT k_scan -> k_route -> k_emit (the streaming path); PATH_GENERAL skip it and run the general
+//   kernels on everything.
 int run_pipeline(const JbTables& T, Workspace& ws, const uint8_t* d_text, uint32_t nbytes, const uint64_t* d_doc_off,
                  uint64_t ndocs, bool use_hmm, const PipeOut& out, cudaStream_t stream, int path = 0);
-enum { PATH_DEFAULT = 0, PATH_GENERAL = 1, PATH_SEG = 2, PATH_ROUTE1 = 3, PATH_ROUTE2 = 4 };
+enum { PATH_DEFAULT = 0, PATH_GENERAL = 1 };
 
 // Second phase when d_start/d_end were NULL in run_pipeline (count first, then scatter).
 int run_scatter(Workspace& ws, uint32_t nbytes, uint64_t ndocs, uint32_t* d_start, uint32_t* d_end, uint64_t cap_tokens,

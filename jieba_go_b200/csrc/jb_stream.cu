@@ -4,11 +4,6 @@
 // viterbi T:668-730, stateTransitionRoute T:736-756, cutHMM T:273-285  (T = /root/reference/tokenizer.go).
 #include "jb_stream.cuh"
 
-#include <stdlib.h>
-#include <string.h>
-
-#include <algorithm>
-
 #include "../../include/jieba_b200.h"
 
 namespace jb {
@@ -467,7 +462,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   constexpr uint32_t PPW = 32 / PB;  // path entries per word
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t nblocks = min(A.counters[A.count_idx], A.blocks_cap);
+  const uint32_t nblocks = min(A.counters[C_N_BLK], A.blocks_cap);
   if (A.counters[C_FLAGS] & 1u) return;  // the general pipeline redoes this batch
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kRtThreads / 32);
@@ -696,371 +691,18 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   }
 }
 
-// ==========================================================================================
-// k_route2: the same work as k_route (buildDag + calcDagProba + maxIndexProba, one lane per Han block, right to
-// left), but FOUR POSITIONS PER LOOP ITERATION per lane, in straight-line code:
-//   * the chunk's 12 bytes of text -> 4 runes; their 4 first-rune entries (T:468-472) are fetched together;
-//   * then, level by level, the hash entries of the 2-, 3- and 4-rune keys of all four positions (each level only
-//     where the level before matched and its Bloom filter lets the next rune through, as buildDag's loop would
-//     go on, T:473-482): up to four independent loads in flight per lane and level;
-//   * then the four selector steps in order (pieceFreq + next.proba into maxIndexProba's (prev, best) pair,
-//     T:519-529, 565-578), reading route values of this very chunk back from the ring.
-// A position whose chain is not settled by that -- a displaced hash entry (linear probing goes on), or keys of
-// five and more runes -- is routed by route_generic at its turn: the reference's loop as it stands, probe by probe.
-// Compared with k_route the per-position bookkeeping of the lane's state machine is paid once per four runes, and a
-// lane has four times as many table loads in flight (what long blocks, with few lanes, are bound by).
-// ==========================================================================================
-constexpr int kR2C = 4;
-constexpr uint32_t kR2Sent = 0xFFFFu;
-
-template <int RING, int PB>
-__global__ void __launch_bounds__(kRtThreads, 4) k_route2(const JbTables T, const RouteArgs A) {
-  constexpr int RR = 2 * RING;  // rune ring: lookback of a key (< RING) + the runes of the chunk written ahead
-  __shared__ double ring[RING][kRtThreads];
-  __shared__ uint16_t rr[RR][kRtThreads];
-  constexpr uint32_t M = RING - 1, MR = RR - 1;
-  constexpr uint32_t PPW = 32 / PB;  // path entries per word
-  const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t nblocks = min(A.counters[A.count_idx], A.blocks_cap);
-  if (A.counters[C_FLAGS] & 1u) return;  // the general pipeline redoes this batch
-  const uint32_t nwarps = gridDim.x * (kRtThreads / 32);
-  const uint32_t chunk = min((uint32_t)kRtQueue, max(A.min_chunk, (nblocks + nwarps - 1) / nwarps));
-  const uint4* __restrict__ first = reinterpret_cast<const uint4*>(T.first);
-  const uint4* __restrict__ entries = reinterpret_cast<const uint4*>(T.entries);
-  const uint32_t hmask = T.hash_mask;
-  const uintptr_t tbase = reinterpret_cast<uintptr_t>(A.text);
-  const uintptr_t tfloor = tbase & ~(uintptr_t)3;  // no aligned word below this one is read
-  double* const sring = &ring[0][tid];
-  uint16_t* const srr = &rr[0][tid];
-  uint32_t qh = 0, qt = 0;
-  bool exhausted = false, active = false;
-  uint32_t bi = 0, p = 0, kq = 0, e3i = 0, nr = 0;  // block index, lead byte of the chunk's rightmost rune, runes done, end / 3, runes
-  uint32_t pv1 = kR2Sent, pv2 = kR2Sent, pv3 = kR2Sent, pv4 = kR2Sent;  // the four runes to the right of the chunk
-  uint32_t acc = 0, accw = 0xFFFFFFFFu;
-
-  auto Rat = [&](uint32_t k) -> double { return sring[(k & M) * kRtThreads]; };
-  auto hand_to_wide = [&]() {
-    const uint32_t wi = atomicAdd(&A.counters[C_N_WIDE], 1u);
-    if (wi < A.wide_cap) A.wide_list[wi] = A.blocks[bi].x;  // (still the block's last rune)
-    else atomicOr(&A.counters[C_FLAGS], 1u);
-    A.blocks[bi].y = 0;  // nothing for k_emit
-    if (acc) atomicOr(&A.path[accw], acc);  // (path entries of the abandoned part are never read)
-    acc = 0;
-    accw = 0xFFFFFFFFu;
-    active = false;
-  };
-  // the reference's loop for one position (kqc runes to its right, all of them routed): T:468-482 + T:515-529 + T:565-578
-  auto route_generic = [&](uint32_t kqc, uint32_t r0, uint32_t& best_d, double& best_v) {
-    const uint4 f = ldg_keep(first + r0);
-    double v = __longlong_as_double(((long long)f.y << 32) | (long long)f.x) + (kqc ? Rat(kqc - 1u) : 0.0);
-    double prev_v = v;
-    uint32_t last_d = 1u;
-    best_d = v >= JB_MINF ? 1u : 0u;
-    best_v = v;
-    if (!(f.z & JB_FIRST_GATE)) {
-      uint32_t hs = JB_PARENT_FIRST(r0), parent = JB_PARENT_FIRST(r0), child = f.w;
-      for (uint32_t L = 1; L <= kqc;) {  // for j := range textRunes[i:] (T:473)
-        const uint32_t rl = srr[((kqc - L) & MR) * kRtThreads];
-        const bool may = L == 1 ? ((child >> jb_bloom_bit(rl)) & 1u) : ((child >> jb_bloom11(rl)) & 1u);
-        if (!may) break;
-        double pw;
-        uint32_t prb;
-        const int ps = jb_probe_edge(T.entries, hmask, hs, parent, rl, &pw, &prb);
-        if (ps < 0) break;  // !found -> break (T:476-478)
-        L++;
-        if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481)
-          v = pw + (L > kqc ? 0.0 : Rat(kqc - L));
-          if (v >= prev_v) {
-            best_d = L;
-            best_v = v;
-          }
-          prev_v = v;
-          last_d = L;
-        }
-        parent = (uint32_t)ps;
-        child = prb >> 21;
-      }
-    }
-    if (best_d == 0u) {  // best.index == -1 -> return prev (T:574-576)
-      best_d = last_d;
-      best_v = prev_v;
-    }
-  };
-
-  for (;;) {
-    // ---- refill idle lanes from the warp's queue of block indexes ----
-    const uint32_t nm = __ballot_sync(FULL, !active);
-    if (nm) {
-      if (qh == qt && !exhausted) {
-        uint32_t b0 = 0;
-        if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_ROUTE], chunk);
-        b0 = __shfl_sync(FULL, b0, 0);
-        if (b0 >= nblocks) exhausted = true;
-        else {
-          qh = b0;
-          qt = min(b0 + chunk, nblocks);
-        }
-      }
-      if (!active) {
-        const uint32_t mine = qh + __popc(nm & lt_mask);
-        if (mine < qt) {
-          bi = mine;
-          const uint2 bd = A.blocks[bi];
-          e3i = bd.x / 3u;
-          nr = bd.y;
-          if (nr == kWideBlock) {  // ends with a 4-byte rune
-            const uint32_t wi = atomicAdd(&A.counters[C_N_WIDE], 1u);
-            if (wi < A.wide_cap) A.wide_list[wi] = bd.x;
-            else atomicOr(&A.counters[C_FLAGS], 1u);
-            A.blocks[bi].y = 0;  // nothing for k_emit
-          } else {
-            if (nr == 0) {  // the block began in an earlier k_scan tile: the nearest tile with a block start holds it
-              uint32_t t = bd.x / (uint32_t)kScTileBytes, sp;
-              do sp = __ldg(A.tile_last_hs + --t);
-              while (sp == 0xFFFFFFFFu);
-              nr = (bd.x - sp) / 3u + 1u;
-            }
-            p = bd.x;
-            kq = 0;
-            pv1 = pv2 = pv3 = pv4 = kR2Sent;
-            active = true;
-          }
-        }
-      }
-      qh = min(qt, qh + (uint32_t)__popc(nm));
-      if (exhausted && __all_sync(FULL, !active)) break;
-    }
-    if (active) {
-      // ---- the chunk: positions c = 0 (rightmost) .. nc - 1 stand on the runes at bytes p - 3c ----
-      const uint32_t nc = min((uint32_t)kR2C, nr - kq);
-      uint32_t r[kR2C];
-      bool act[kR2C], bad = false;
-      {
-        // 12 bytes [p - 9, p + 3) out of four aligned words
-        const uintptr_t a0 = tbase + p - 9u, aw = a0 & ~(uintptr_t)3;
-        const uint32_t s = (uint32_t)(a0 & 3);
-        uint32_t W[5];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          // (no word below the text's first one: a partial chunk at the very start; the last word only when it holds a byte of the chunk)
-          const bool need = aw + 4u * k >= tfloor && (k < 3 || s != 0u);
-          W[k] = need ? __ldg(reinterpret_cast<const uint32_t*>(aw + 4u * k)) : 0u;
-        }
-        W[4] = 0u;
-#pragma unroll
-        for (int c = 0; c < kR2C; c++) {
-          const uint32_t off = s + 9u - 3u * c, k = off >> 2;  // k is one of two consecutive words
-          const uint32_t klo = (9u - 3u * c) >> 2;
-          const uint32_t lo = k == klo ? W[klo] : W[klo + 1], hi = k == klo ? W[klo + 1] : W[klo + 2 > 4 ? 4 : klo + 2];
-          const uint32_t x = __funnelshift_r(lo, hi, (off & 3u) * 8u);
-          act[c] = (uint32_t)c < nc;
-          r[c] = act[c] ? (((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu)) : kR2Sent;
-          bad |= act[c] && (x & 0xF0u) != 0xE0u;  // inside a Han block every rune has 3 bytes -- or 4 (k_wide)
-        }
-      }
-      if (bad) {
-        hand_to_wide();
-      } else {
-        uint4 f[kR2C];
-#pragma unroll
-        for (int c = 0; c < kR2C; c++) {
-          f[c] = make_uint4(0u, 0u, JB_FIRST_GATE, 0u);
-          if (act[c]) {
-            srr[((kq + c) & MR) * kRtThreads] = (uint16_t)r[c];
-            f[c] = ldg_keep(first + r[c]);  // termFreq[string(iRune)] (T:468)
-          }
-        }
-        // the runes 1 .. 4 to the right of each position
-        const uint32_t n1[kR2C] = {pv1, r[0], r[1], r[2]}, n2[kR2C] = {pv2, pv1, r[0], r[1]}, n3[kR2C] = {pv3, pv2, pv1, r[0]},
-                       n4[kR2C] = {pv4, pv3, pv2, pv1};
-        double w2[kR2C], w3[kR2C], w4[kR2C];
-        uint32_t cm[kR2C];   // candidate lengths 2..4 (bits 1..3)
-        uint32_t trouble = 0;  // positions routed by route_generic
-        uint32_t hh[kR2C], par[kR2C];
-        bool go[kR2C];
-        uint4 e[kR2C];
-        // ---- level 2: gate + Bloom of the first-rune entry (T:469-472), then the 2-rune key ----
-#pragma unroll
-        for (int c = 0; c < kR2C; c++) {
-          cm[c] = 0;
-          go[c] = act[c] && !(f[c].z & JB_FIRST_GATE) && n1[c] != kR2Sent && ((f[c].w >> jb_bloom_bit(n1[c])) & 1u);
-          hh[c] = jb_hash_next(JB_PARENT_FIRST(r[c]), n1[c]);
-          par[c] = JB_PARENT_FIRST(r[c]);
-          e[c] = make_uint4(0u, 0u, JB_PARENT_EMPTY, 0u);
-          if (go[c]) e[c] = __ldg(entries + (hh[c] & hmask));
-        }
-#pragma unroll
-        for (int c = 0; c < kR2C; c++) {
-          const bool m = go[c] && e[c].z == par[c] && JB_RB_RUNE(e[c].w) == n1[c];
-          if (go[c] && !m && e[c].z != JB_PARENT_EMPTY && (e[c].w & JB_RB_CONT)) trouble |= 1u << c;  // displaced: linear probing goes on
-          w2[c] = __longlong_as_double(((long long)e[c].y << 32) | (long long)e[c].x);
-          if (m && jb_w_positive(w2[c])) cm[c] |= 2u;  // val > 0 -> edge (T:479-481)
-          go[c] = m && n2[c] != kR2Sent && (((e[c].w >> 21) >> jb_bloom11(n2[c])) & 1u);  // some key extends it by the next rune
-          par[c] = hh[c] & hmask;
-          hh[c] = jb_hash_next(hh[c], n2[c]);
-        }
-        // ---- level 3 ----
-#pragma unroll
-        for (int c = 0; c < kR2C; c++) {
-          e[c] = make_uint4(0u, 0u, JB_PARENT_EMPTY, 0u);
-          if (go[c]) e[c] = __ldg(entries + (hh[c] & hmask));
-        }
-#pragma unroll
-        for (int c = 0; c < kR2C; c++) {
-          const bool m = go[c] && e[c].z == par[c] && JB_RB_RUNE(e[c].w) == n2[c];
-          if (go[c] && !m && e[c].z != JB_PARENT_EMPTY && (e[c].w & JB_RB_CONT)) trouble |= 1u << c;
-          w3[c] = __longlong_as_double(((long long)e[c].y << 32) | (long long)e[c].x);
-          if (m && jb_w_positive(w3[c])) cm[c] |= 4u;
-          go[c] = m && n3[c] != kR2Sent && (((e[c].w >> 21) >> jb_bloom11(n3[c])) & 1u);
-          par[c] = hh[c] & hmask;
-          hh[c] = jb_hash_next(hh[c], n3[c]);
-        }
-        // ---- level 4; a chain that would go on to five runes is left to route_generic ----
-#pragma unroll
-        for (int c = 0; c < kR2C; c++) {
-          e[c] = make_uint4(0u, 0u, JB_PARENT_EMPTY, 0u);
-          if (go[c]) e[c] = __ldg(entries + (hh[c] & hmask));
-        }
-#pragma unroll
-        for (int c = 0; c < kR2C; c++) {
-          const bool m = go[c] && e[c].z == par[c] && JB_RB_RUNE(e[c].w) == n3[c];
-          if (go[c] && !m && e[c].z != JB_PARENT_EMPTY && (e[c].w & JB_RB_CONT)) trouble |= 1u << c;
-          w4[c] = __longlong_as_double(((long long)e[c].y << 32) | (long long)e[c].x);
-          if (m && jb_w_positive(w4[c])) cm[c] |= 8u;
-          if (m && n4[c] != kR2Sent && (((e[c].w >> 21) >> jb_bloom11(n4[c])) & 1u)) trouble |= 1u << c;
-        }
-        // ---- the selector, position by position ----
-#pragma unroll
-        for (int c = 0; c < kR2C; c++) {
-          if (act[c]) {
-            const uint32_t kqc = kq + c;
-            uint32_t best_d;
-            double best_v;
-            if ((trouble >> c) & 1u) {
-              route_generic(kqc, r[c], best_d, best_v);
-            } else {
-              // candidates in ascending length: each is compared with the previous one, the first with minFloat (T:565-578)
-              double v = __longlong_as_double(((long long)f[c].y << 32) | (long long)f[c].x) + (kqc ? Rat(kqc - 1u) : 0.0);
-              double prev_v = v;
-              uint32_t last_d = 1u;
-              best_d = v >= JB_MINF ? 1u : 0u;
-              best_v = v;
-              if (cm[c] & 2u) {
-                v = w2[c] + (kqc >= 2u ? Rat(kqc - 2u) : 0.0);  // {j, 0.0} at the end of the block (T:522)
-                if (v >= prev_v) {
-                  best_d = 2u;
-                  best_v = v;
-                }
-                prev_v = v;
-                last_d = 2u;
-              }
-              if (cm[c] & 4u) {
-                v = w3[c] + (kqc >= 3u ? Rat(kqc - 3u) : 0.0);
-                if (v >= prev_v) {
-                  best_d = 3u;
-                  best_v = v;
-                }
-                prev_v = v;
-                last_d = 3u;
-              }
-              if (cm[c] & 8u) {
-                v = w4[c] + (kqc >= 4u ? Rat(kqc - 4u) : 0.0);
-                if (v >= prev_v) {
-                  best_d = 4u;
-                  best_v = v;
-                }
-                prev_v = v;
-                last_d = 4u;
-              }
-              if (best_d == 0u) {  // best.index == -1 -> return prev (T:574-576)
-                best_d = last_d;
-                best_v = prev_v;
-              }
-            }
-            sring[(kqc & M) * kRtThreads] = best_v;
-            const uint32_t idx = e3i - kqc, pwd = idx / PPW;
-            if (pwd != accw) {
-              if (acc) atomicOr(&A.path[accw], acc);
-              acc = 0;
-              accw = pwd;
-            }
-            acc |= (best_d - 1u) << ((idx % PPW) * PB);
-            if (A.dbg_R) {
-              A.dbg_R[idx] = best_v;
-              A.dbg_D[idx] = (uint8_t)best_d;
-            }
-          }
-        }
-        kq += nc;
-        if (kq == nr) {  // the first rune of the block is done
-          if (acc) atomicOr(&A.path[accw], acc);
-          acc = 0;
-          accw = 0xFFFFFFFFu;
-          A.blocks[bi] = make_uint2(p - 3u * (nc - 1u), nr);
-          active = false;
-        } else {
-          p -= 3u * kR2C;
-          pv4 = r[0];
-          pv3 = r[1];
-          pv2 = r[2];
-          pv1 = r[3];
-        }
-      }
-    }
-    __syncwarp();
-  }
-}
-
-// Launch with an L2 access-policy window as a LAUNCH attribute (nothing of the caller's stream is changed): accesses
-// to the dictionary tables are "normal", everything else the kernel touches -- the one-touch text, the path and the
-// bitmaps -- is "streaming", i.e. first to be evicted, so gigabytes of text do not wash the tables out of L2.
-// (A miss on a table line is a DRAM round trip on the critical path of a lane; long blocks, with few lanes, feel every one.)
-template <typename... KArgs, typename... Args>
-static void launch_windowed(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, TableWindow tw, Args... args) {
-  static const int mode = getenv("JB_L2WIN") ? atoi(getenv("JB_L2WIN")) : 2;
-  static int max_win = -1;
-  if (max_win < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess) max_win = 0;
-  }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  if (mode != 0 && tw.base && tw.bytes && max_win > 0) {
-    at[0].id = cudaLaunchAttributeAccessPolicyWindow;
-    at[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(tw.base);
-    at[0].val.accessPolicyWindow.num_bytes = std::min<size_t>(tw.bytes, (size_t)max_win);
-    at[0].val.accessPolicyWindow.hitRatio = 1.0f;
-    at[0].val.accessPolicyWindow.hitProp = mode == 1 ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
-    at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-  }
-  cudaLaunchKernelEx(&cfg, kernel, args...);
-}
-
-int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st, TableWindow tw) {
-  // Shared memory that the resident CTAs do not take is L1 for the dictionary tables, and the kernels are bound by
-  // the latency of their table loads: with 20.5 KB per CTA the driver's default carveout leaves ~84 KB of L1
-  // (k_route 6.4 ms/GB); with 24.5 KB per CTA (32-bit runes) it had to take the whole array (9.0 ms/GB).
+int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st) {
+  // Shared memory that the 8 resident CTAs do not take is L1 for the dictionary tables, and the kernel is bound by
+  // the latency of its table loads: with 20.5 KB per CTA the driver's default carveout leaves ~84 KB of L1
+  // (6.4 ms/GB); with 24.5 KB per CTA (32-bit runes) it had to take the whole array (9.0 ms/GB).  Forcing other
+  // carveouts or fewer CTAs measured slower.
   const bool r16 = T.max_delta <= 16;
-  if (A.chunked) {
-    const unsigned grid = (unsigned)num_sms * 4u;
-    if (r16) launch_windowed(k_route2<16, 4>, grid, kRtThreads, st, tw, T, A);
-    else launch_windowed(k_route2<32, 8>, grid, kRtThreads, st, tw, T, A);
-  } else {
-    const unsigned grid = (unsigned)num_sms * 8u;
-    if (A.dbg_R) {
-      if (r16) launch_windowed(k_route<16, 4, true>, grid, kRtThreads, st, tw, T, A);
-      else launch_windowed(k_route<32, 8, true>, grid, kRtThreads, st, tw, T, A);
-    } else if (r16) launch_windowed(k_route<16, 4, false>, grid, kRtThreads, st, tw, T, A);
-    else launch_windowed(k_route<32, 8, false>, grid, kRtThreads, st, tw, T, A);
-  }
+  const unsigned grid = (unsigned)num_sms * 8u;
+  if (A.dbg_R) {  // jb_debug_route: the instantiation that also records every selected route value
+    if (r16) k_route<16, 4, true><<<grid, kRtThreads, 0, st>>>(T, A);
+    else k_route<32, 8, true><<<grid, kRtThreads, 0, st>>>(T, A);
+  } else if (r16) k_route<16, 4, false><<<grid, kRtThreads, 0, st>>>(T, A);
+  else k_route<32, 8, false><<<grid, kRtThreads, 0, st>>>(T, A);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1076,7 +718,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   if (A.counters[C_FLAGS] & 1u) return;
-  const uint32_t nblocks = min(A.counters[A.count_idx], A.blocks_cap);
+  const uint32_t nblocks = min(A.counters[C_N_BLK], A.blocks_cap);
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kEmThreads / 32);
   const uint32_t chunk = min(32u, max(A.min_chunk, (nblocks + nwarps - 1) / nwarps));
@@ -1262,15 +904,15 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   }
 }
 
-int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st, TableWindow tw) {
+int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st) {
   const bool r16 = T.max_delta <= 16;
   const unsigned grid = (unsigned)num_sms * (hmm ? 9u : 16u);  // resident CTAs per SM by register count (56 / 30)
   if (r16) {
-    if (hmm) launch_windowed(k_emit<true, 4>, grid, kEmThreads, st, tw, T, A);
-    else launch_windowed(k_emit<false, 4>, grid, kEmThreads, st, tw, T, A);
+    if (hmm) k_emit<true, 4><<<grid, kEmThreads, 0, st>>>(T, A);
+    else k_emit<false, 4><<<grid, kEmThreads, 0, st>>>(T, A);
   } else {
-    if (hmm) launch_windowed(k_emit<true, 8>, grid, kEmThreads, st, tw, T, A);
-    else launch_windowed(k_emit<false, 8>, grid, kEmThreads, st, tw, T, A);
+    if (hmm) k_emit<true, 8><<<grid, kEmThreads, 0, st>>>(T, A);
+    else k_emit<false, 8><<<grid, kEmThreads, 0, st>>>(T, A);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

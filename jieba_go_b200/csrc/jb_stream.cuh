@@ -45,7 +45,6 @@ struct RouteArgs {
   const uint32_t* tile_last_hs;
   uint2* blocks;          // in: (last rune, runes or 0 when the block began in an earlier tile); out: (lead byte of the first rune, runes)
   uint32_t blocks_cap;
-  uint32_t count_idx;     // counters[] index of the number of entries of `blocks` (C_N_BLK: k_scan's list, C_N_LONG: k_seg's)
   uint32_t* counters;
   uint32_t* path;         // chosen word length - 1 per rune, index = lead byte / 3
   uint32_t* wide_list;    // lead byte of the last rune of every block with a 4-byte Han rune, for k_wide
@@ -53,33 +52,12 @@ struct RouteArgs {
   uint32_t min_chunk;     // blocks a warp takes from the queue at least (few long blocks: lanes per warp vs warps per SM)
   double* dbg_R;          // optional (jb_debug_route): selected route value / word length per rune, index = lead byte / 3
   uint8_t* dbg_D;
-  bool chunked;           // k_route2 (four positions per iteration) instead of k_route
-};
-
-// k_seg: the Han blocks of k_scan's list, a few dozen at a time per CTA, entirely in shared memory
-struct SegArgs {
-  const uint8_t* text;
-  uint32_t n;
-  const uint32_t* tile_last_hs;
-  const uint2* blocks;    // k_scan's list: (lead byte of the last rune, runes or 0 = began in an earlier tile)
-  uint32_t blocks_cap;
-  uint32_t* counters;
-  uint2* long_blocks;     // out: blocks left to k_route / k_emit (longer than max_runes, or a round that ran out of room)
-  uint32_t long_cap;
-  uint32_t max_runes;     // <= kSgMaxRunes
-  uint32_t* wide_list;
-  uint32_t wide_cap;
-  uint32_t* s_bits;
-  uint32_t* e_bits;
-  double* dbg_R;
-  uint8_t* dbg_D;
 };
 
 struct EmitArgs {
   const uint8_t* text;
   const uint2* blocks;
   uint32_t blocks_cap;
-  uint32_t count_idx;
   uint32_t* counters;
   const uint32_t* path;
   uint8_t* bp;            // Viterbi back-pointers / state flags per rune, index = lead byte / 3
@@ -102,19 +80,10 @@ struct WideArgs {
   uint32_t* e_bits;
 };
 
-constexpr bool kDefaultChunkedRoute = false;  // which of k_route / k_route2 the default path uses
-constexpr uint32_t kSgMaxRunes = 1024;  // Han blocks up to this many runes are cut by k_seg
-
-int launch_seg(const JbTables& T, const SegArgs& A, bool hmm, int num_sms, cudaStream_t st);
 int launch_wide(const JbTables& T, const WideArgs& A, bool hmm, int num_sms, cudaStream_t st);
 int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st);
-// tables: the window of device memory that holds the dictionary tables (see launch_cfg in jb_stream.cu)
-struct TableWindow {
-  const void* base;
-  size_t bytes;
-};
-int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st, TableWindow tw);
-int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st, TableWindow tw);
+int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st);
+int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st);
 inline uint32_t scan_tiles(uint32_t n) { return (n + kScTileBytes - 1) / kScTileBytes; }
 
 #if defined(__CUDACC__)

@@ -62,8 +62,31 @@ class Tokenizer:
             arrs = _emit_dict_arrays(emit)
         return cls(db, arrs, **kw)
 
+    @classmethod
+    def from_files_cached(cls, dict_path, kind, emit_json, image_path, gob_size=JIEBA_DICT_SIZE, device=-1, unicode_version=15,
+                          max_batch_bytes=0):
+        """NewTokenizer / NewJiebaTokenizer with the cached table image (jb_tokenizer_create_cached): kind 0 / 1 = dict.txt
+        in file / prefix mode, 2 = prefix_dictionary.gob.  A read-only tokenizer: no dictionary is kept on the host, so
+        add_word / lookup are not available.  .from_cache tells whether the image was used."""
+        self = cls.__new__(cls)
+        self._L = _capi.lib()
+        self._dict_buf = None
+        self._emit = None
+        self._opt = Options(device, unicode_version, max_batch_bytes)
+        self._lock = threading.RLock()
+        h = C.c_void_p()
+        used = C.c_int(0)
+        check(self._L.jb_tokenizer_create_cached(str(dict_path).encode(), int(kind), int(gob_size), str(emit_json).encode(),
+                                                 C.byref(self._opt), str(image_path).encode(), C.byref(used), C.byref(h)),
+              "jb_tokenizer_create_cached")
+        self._h = h
+        self.from_cache = bool(used.value)
+        return self
+
     # ---- lifetime -------------------------------------------------------------------------
     def _rebuild(self):
+        if self._dict_buf is None:
+            raise _capi.JiebaB200Error("a tokenizer created from a cached table image keeps no dictionary on the host: add_word needs one of the other constructors")
         L = self._L
         dd = DictDesc()
         L.jb_dict_buf_desc(self._dict_buf, C.byref(dd))
@@ -80,9 +103,7 @@ class Tokenizer:
         if old:
             L.jb_tokenizer_destroy(old)
         if getattr(self, "_path_mode", 0):
-            L.jb_set_path(self._h, self._path_mode)
-        if getattr(self, "_seg_max_runes", 0):
-            L.jb_set_seg_max_runes(self._h, self._seg_max_runes)
+            L.jb_set_general_only(self._h, self._path_mode)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -100,15 +121,8 @@ class Tokenizer:
 
     def set_general_only(self, on):
         """Bypass the streaming fast path (the general kernels then cut every block); for tests."""
-        self.set_path(1 if on else 0)
-
-    def set_path(self, path, seg_max_runes=0):
-        """Kernel path of the Han blocks: 0 default (k_route/k_emit), 1 general kernels, 2 k_seg (k_route/k_emit only
-        for blocks longer than 1024 runes or seg_max_runes); for tests."""
-        self._path_mode = int(path)
-        self._seg_max_runes = int(seg_max_runes)
-        check(self._L.jb_set_path(self._h, self._path_mode), "jb_set_path")
-        check(self._L.jb_set_seg_max_runes(self._h, self._seg_max_runes), "jb_set_seg_max_runes")
+        self._path_mode = int(bool(on))
+        check(self._L.jb_set_general_only(self._h, self._path_mode), "jb_set_general_only")
 
     @property
     def handle(self):

@@ -284,3 +284,53 @@ def test_real_data_harness_mechanics(tmp_path, monkeypatch, small_synth):
     assert ptk.pd.build_dag(runes) == ctk.build_dag("".join(map(chr, runes)))
     assert ptk.hmm.viterbi(runes) == ctk.hmm.viterbi("".join(map(chr, runes)))
     monkeypatch.setattr(realdata, "_cache", None)
+
+
+# ---- cached table image (jb_tokenizer_create_cached) ------------------------------------------------
+def test_sha256_matches_hashlib():
+    import hashlib
+    L = _capi.lib()
+    rng = np.random.default_rng(5)
+    for n in [0, 1, 3, 55, 56, 57, 63, 64, 65, 119, 120, 1000, 100_003]:
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        out = C.create_string_buffer(32)
+        L.jb_debug_sha256(data, n, out)
+        assert out.raw == hashlib.sha256(data).digest(), n
+
+
+def test_table_image_cache_lifecycle_without_device(tmp_path, small_synth):
+    """No GPU here: every call ends with JB_ECUDA at the upload, but the host half (parse, build, write / read back the
+    image, key check) has run by then, and from_cache tells which way it went."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present (tests/test_gpu_parity.py covers the cached constructor there)")
+    sd, emit = small_synth
+    L = _capi.lib()
+    dp, ep, ip = tmp_path / "dict.txt", tmp_path / "prob_emit.json", tmp_path / "tables.img"
+    dp.write_bytes(sd.dict_txt())
+    ep.write_bytes(synth.emit_json(emit))
+
+    def create(kind=1):
+        h = C.c_void_p()
+        used = C.c_int(-1)
+        rc = L.jb_tokenizer_create_cached(str(dp).encode(), kind, 0, str(ep).encode(), None, str(ip).encode(), C.byref(used), C.byref(h))
+        assert rc == -4, L.jb_last_error()   # JB_ECUDA: no device
+        return used.value
+
+    assert create() == 0 and ip.exists()          # built from the files, image written
+    size = ip.stat().st_size
+    assert size > 65536 * 16
+    assert create() == 1                          # read back
+    assert create(kind=0) == 0                    # another loader mode: another key, rebuilt and rewritten
+    assert create(kind=0) == 1
+    assert create() == 0                          # ... and back
+    raw = bytearray(ip.read_bytes())
+    raw[len(raw) // 2] ^= 0x40                    # damage the payload
+    ip.write_bytes(bytes(raw))
+    assert create() == 0
+    assert create() == 1
+    ip.write_bytes(ip.read_bytes()[: size // 3])  # truncate
+    assert create() == 0
+    dp.write_bytes(sd.dict_txt() + "\u9f98\u9f98 7 n\n".encode())   # the dictionary changed: stale image
+    assert create() == 0
+    assert create() == 1

@@ -12,10 +12,7 @@ from helpers import c_oracle_tokenizer, emit_arrays, fuzz_docs, pack_docs  # noq
 pytestmark = pytest.mark.gpu
 
 
-# default streaming path (k_scan/k_route/k_emit) / k_seg (CTA-cooperative) / the same with blocks over 12 runes handed to
-# k_route + k_emit / general kernels only
-PATHS = ["stream", "route1", "route2", "seg", "seg12", "general"]
-_PATH_ARGS = {"stream": (0, 0), "route1": (3, 0), "route2": (4, 0), "seg": (2, 0), "seg12": (2, 12), "general": (1, 0)}
+PATHS = ["stream", "general"]  # default streaming fast path (k_scan/k_route/k_emit) / general kernels only
 
 
 def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="stream", **kw):
@@ -25,7 +22,8 @@ def _gpu_tokenizer(sd_or_lines, emit, mode=1, path="stream", **kw):
     else:
         data = sd_or_lines.dict_txt()
     tk = Tokenizer.from_dict_text(data, mode, emit, **kw)
-    tk.set_path(*_PATH_ARGS[path])
+    if path == "general":
+        tk.set_general_only(True)
     return tk
 
 
@@ -139,7 +137,7 @@ def test_device_dictionary_matches_term_freq(synth_pair):
 @pytest.mark.parametrize("runes", [1, 2, 7, 300, 1024, 1025, 3000])
 def test_route_values_bit_exact(small_synth, path, runes):
     """float64 route values R[i] = maxIndexProba(dagProba[i]) (T:502-548, 565-578), bit for bit, from the kernel that
-    cuts the block on each path: k_route (`stream`; `seg` beyond 1024 runes, `seg12` beyond 12), k_seg, k_route_dp (`general`)."""
+    cuts the block on each path: k_route (`stream`: the kernel behind every benchmark number) and k_route_dp (`general`)."""
     sd, emit = small_synth
     tk = _gpu_tokenizer(sd, emit, 1, path=path)
     ora = c_oracle_tokenizer(sd, emit, 1)
@@ -620,3 +618,27 @@ def test_ten_thousand_short_strings_in_one_batch(synth_pair):
     for i in rng.integers(0, len(texts), 400).tolist() + [0, len(texts) - 1]:
         assert got[i] == ora.cut_strings(texts[i], True), texts[i]
     assert sum(len(g) for g in got) == sum(len(ora.cut_strings(s, True)) for s in texts[:2000]) + sum(len(g) for g in got[2000:])
+
+
+# ---- cached table image --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", [0, 1])
+def test_cached_table_image_constructor(tmp_path, small_synth, kind):
+    """jb_tokenizer_create_cached: built + written on the first call, read back on the second; both cut like the
+    tokenizer built the ordinary way (and like the oracle in the same loader mode)."""
+    from jieba_go_b200.tokenizer import Tokenizer
+    sd, emit = small_synth
+    dp, ep, ip = tmp_path / "dict.txt", tmp_path / "prob_emit.json", tmp_path / "tables.img"
+    dp.write_bytes(sd.dict_txt())
+    ep.write_bytes(synth.emit_json(emit))
+    a = Tokenizer.from_files_cached(dp, kind, ep, ip)
+    b = Tokenizer.from_files_cached(dp, kind, ep, ip)
+    assert not a.from_cache and b.from_cache
+    ora = c_oracle_tokenizer(sd, emit, kind)
+    text, doc_off = synth.make_corpus(sd, "oov", 400_000, synth.SEED_BASE + 90)
+    t, off = text.numpy(), doc_off.numpy().astype(np.uint64)
+    for hmm in (False, True):
+        want = ora.cut_batch(t, off, hmm, 4)
+        _assert_same(a.cut_batch(t, off, hmm), want, t, off)
+        _assert_same(b.cut_batch(t, off, hmm), want, t, off)
+    with pytest.raises(Exception):
+        b.add_word("甲乙", 5)   # read-only: no host dictionary
