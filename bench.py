@@ -405,11 +405,11 @@ def main():
         e_dt, chk = time_e2e(lambda: call_bits(h_np))
         assert chk[0] == n_tok and chk[1] == n_tok
         e2e = (e_dt, nbytes + 8 * (ndocs + 1), 2 * 4 * ((nbytes + 31) // 32) + 8 * (ndocs + 1))
-        a_dt, chk = time_e2e(call_arrays, warm=1)
+        a_dt, chk = time_e2e(call_arrays, warm=2)
         assert chk[0] == n_tok
         e2e_extra["e2e_arrays"] = (a_dt, nbytes + 8 * (ndocs + 1), 8 * n_tok + 8 * (ndocs + 1))
         pageable = np.array(h_np, copy=True)  # ordinary (pageable) host memory, like a Go string
-        p_dt, chk = time_e2e(lambda: call_bits(pageable), warm=1)
+        p_dt, chk = time_e2e(lambda: call_bits(pageable), warm=2)
         assert chk[0] == n_tok
         e2e_extra["e2e_pageable"] = (p_dt, nbytes + 8 * (ndocs + 1), e2e[2])
         del h_text, pageable

@@ -43,7 +43,8 @@ struct WsSlot {
   Workspace ws;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;
-  uint64_t* h_cnt = nullptr;  // pinned: token count + status of the batch in flight
+  uint64_t* h_cnt = nullptr;  // pinned: token count + status of the batch in flight; [2]: Han blocks (low word)
+  cudaEvent_t ev_nblk = nullptr;
   uint64_t* h_doc = nullptr;  // pinned staging of the batch's document offsets (the caller's array is pageable:
   uint64_t h_doc_cap = 0;     //  an async copy from it would block the host until the stream gets there)
   uint8_t* h_text = nullptr;  // pinned staging of the batch's text, only when the caller's text is pageable
@@ -77,6 +78,7 @@ struct jb_tokenizer {
   void* table_base = nullptr;
   size_t table_bytes = 0;
   uint64_t max_batch = 128ull << 20;
+  bool max_batch_given = false;  // jb_options.max_batch_bytes was set: the sub-batch size is the caller's, never grown
   double w_per_slot = 3.0;
   int path = PATH_DEFAULT;  // PATH_GENERAL: tests
   std::mutex mu;
@@ -351,7 +353,10 @@ static int create_from_image(const TableImage& img, const jb_options* opt, jb_to
   int rc = JB_OK;
   jb_tokenizer* tk = new jb_tokenizer();
   tk->device = dev;
-  if (opt && opt->max_batch_bytes) tk->max_batch = opt->max_batch_bytes;
+  if (opt && opt->max_batch_bytes) {
+    tk->max_batch = opt->max_batch_bytes;
+    tk->max_batch_given = true;
+  }
   if (tk->max_batch > (1ull << 31) - (1ull << 20)) tk->max_batch = (1ull << 31) - (1ull << 20);
   JbTables& T = tk->T;
   memset(&T, 0, sizeof T);
@@ -490,6 +495,7 @@ static void free_slot(WsSlot* s) {
   workspace_free(s->ws);
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->ev) cudaEventDestroy(s->ev);
+  if (s->ev_nblk) cudaEventDestroy(s->ev_nblk);
   if (s->h_cnt) cudaFreeHost(s->h_cnt);
   if (s->h_doc) cudaFreeHost(s->h_doc);
   if (s->h_text) cudaFreeHost(s->h_text);
@@ -631,7 +637,7 @@ static WsSlot* take_slot(jb_tokenizer* tk) {
     slot = new WsSlot();
     if (cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming) != cudaSuccess ||
-        cudaMallocHost(&slot->h_cnt, 16) != cudaSuccess) {
+        cudaMallocHost(&slot->h_cnt, 32) != cudaSuccess || cudaEventCreateWithFlags(&slot->ev_nblk, cudaEventDisableTiming) != cudaSuccess) {
       delete slot;
       return nullptr;
     }
@@ -679,7 +685,7 @@ static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
                      jb_result* res, std::vector<EdgeWord>* edges, uint64_t* n_tok_out) {
   CUDA_TRY(cudaSetDevice(tk->device));  // (nothing acquired yet)
   const uint64_t g0 = doc_off[0];
-  // plan: greedy batches of whole documents
+  // plan: greedy batches of whole documents, one at a time (the size of the next one may change, see below)
   struct Chunk {
     uint64_t d0, d1, nb, base;
     uint64_t nt;
@@ -689,21 +695,27 @@ static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
   // Sub-batch sizes ramp up from 16 MiB and down again towards the end: the first H2D copy and the last D2H copy
   // are the only ones no kernel hides, so they are kept short (a document larger than the target still goes whole).
   const uint64_t kRamp0 = 16ull << 20;
-  uint64_t ramp = kRamp0;
-  for (uint64_t d0 = d_lo; d0 < d_hi;) {
-    const uint64_t remaining = doc_off[d_hi] - doc_off[d0];
-    const uint64_t target = std::min<uint64_t>(tk->max_batch, std::min<uint64_t>(ramp, std::max<uint64_t>(kRamp0, remaining / 2)));
+  uint64_t ramp = kRamp0, batch_cap = tk->max_batch, next_doc = d_lo;
+  bool long_blocks = false;  // (see below: few, long Han blocks -> few, large sub-batches)
+  auto plan_next = [&]() -> bool {
+    if (next_doc >= d_hi) return false;
+    const uint64_t d0 = next_doc, remaining = doc_off[d_hi] - doc_off[d0];
+    const uint64_t target = long_blocks ? batch_cap : std::min<uint64_t>(batch_cap, std::min<uint64_t>(ramp, std::max<uint64_t>(kRamp0, remaining / 2)));
     uint64_t d1 = d0 + 1;
     while (d1 < d_hi && doc_off[d1 + 1] - doc_off[d0] <= target) d1++;
     chunks.push_back(Chunk{d0, d1, doc_off[d1] - doc_off[d0], 0, 0, bits ? (uint32_t)((doc_off[d0] - g0) & 31) : 0u});
-    d0 = d1;
-    ramp = std::min<uint64_t>(ramp * 2, tk->max_batch);
-  }
+    next_doc = d1;
+    ramp = std::min<uint64_t>(ramp * 2, batch_cap);
+    return true;
+  };
+  // (an upper bound of the number of sub-batches, for the pinned edge words)
+  // (two consecutive sub-batches always hold more than one target's worth of bytes, and the target never falls below this)
+  const uint64_t min_target = std::max<uint64_t>(1, std::min<uint64_t>(kRamp0, tk->max_batch));
+  const uint64_t max_chunks = std::min<uint64_t>(d_hi - d_lo, 2 * ((d_hi > d_lo ? doc_off[d_hi] - doc_off[d_lo] : 0) / min_target + 1) + 2) + 4;
   const bool pageable = d_hi > d_lo && doc_off[d_hi] > doc_off[d_lo] && !host_ptr_is_pinned(text + doc_off[d_lo]);
   const int copy_threads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 4));
   constexpr size_t kPipeSlots = 3;  // measured: 5 slots are slower (31.9 vs 28.1 ms per GB end to end)
   WsSlot* slots[kPipeSlots] = {};
-  for (size_t i = 0; i < kPipeSlots && i < std::max<size_t>(chunks.size(), 1); i++) slots[i] = take_slot(tk);
   uint32_t* h_edge = nullptr;  // pinned: first bitmap word (start, end) of every sub-batch
   size_t h_edge_bytes = 0;
   auto done = [&](int code) {
@@ -717,13 +729,11 @@ static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
     pin_free(h_edge, h_edge_bytes);
     return code;
   };
-  for (size_t i = 0; i < kPipeSlots && i < std::max<size_t>(chunks.size(), 1); i++)
-    if (!slots[i]) return done(fail(JB_ECUDA, "stream / event creation failed"));
   double wps = tk->w_per_slot;
   const uint64_t total_bytes = d_hi > d_lo ? doc_off[d_hi] - doc_off[d_lo] : 0;
   int rc = JB_OK;
   if (bits) {
-    h_edge = (uint32_t*)pin_alloc(chunks.size() * 8 + 8, &h_edge_bytes);
+    h_edge = (uint32_t*)pin_alloc(max_chunks * 8 + 8, &h_edge_bytes);
     if (!h_edge) return done(fail(JB_ENOMEM, "pinned host allocation failed"));
   } else {
     rc = result_grow(res, total_bytes / 6 + 1024);  // typical: one token per ~7 bytes; grows if needed
@@ -742,6 +752,8 @@ static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
   };
   auto enqueue = [&](size_t ci) -> int {
     Chunk& c = chunks[ci];
+    if (!slots[ci % kPipeSlots] && !(slots[ci % kPipeSlots] = take_slot(tk))) return fail(JB_ECUDA, "stream / event creation failed");
+    if (ci >= max_chunks) return fail(JB_ELIMIT, "internal: more sub-batches than planned for");
     WsSlot* sl = slots[ci % kPipeSlots];
     cudaStream_t st = sl->stream;
     const uint64_t dev_bytes = c.nb + c.pad;
@@ -799,7 +811,10 @@ static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
       po.d_end = ws.out_end;
       po.cap_tokens = ws.out_cap;
     }
+    ws.h_nblk = ci == 0 ? reinterpret_cast<uint32_t*>(sl->h_cnt + 2) : nullptr;
+    ws.ev_nblk = sl->ev_nblk;
     r = run_pipeline(tk->T, ws, ws.text, (uint32_t)dev_bytes, ws.doc_off64, c.d1 - c.d0, use_hmm != 0, po, st, tk->path);
+    ws.h_nblk = nullptr;
     if (r != JB_OK) return fail(r, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     tl_rec(ci, 2, st);
     CUDA_TRY(cudaMemcpyAsync(sl->h_cnt, ws.out_ntok, 16, cudaMemcpyDeviceToHost, st));
@@ -825,10 +840,10 @@ static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
 
   uint64_t base = 0;
   size_t next_enq = 0;
-  for (size_t ci = 0; ci < chunks.size(); ci++) {
+  for (size_t ci = 0;; ci++) {
     // keep the next batches enqueued ahead; a slot is reused by batch j + kPipeSlots: its copies must be done
     // before that batch overwrites the buffers
-    while (next_enq < chunks.size() && next_enq < ci + kPipeSlots) {
+    while (next_enq < ci + kPipeSlots && (next_enq < chunks.size() || plan_next())) {
       if (next_enq >= kPipeSlots) {
         Chunk& pc = chunks[next_enq - kPipeSlots];
         cudaError_t se = cudaStreamSynchronize(slots[next_enq % kPipeSlots]->stream);
@@ -839,7 +854,21 @@ static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
       }
       rc = enqueue(next_enq++);
       if (rc != JB_OK) return done(rc);
+      if (next_enq == 1 && !tk->max_batch_given && tk->path == PATH_DEFAULT && next_doc < d_hi) {
+        // LONG BLOCKS.  A Han block is routed by one lane, so a sub-batch of few, long blocks takes as long as its longest
+        // block whatever its size (10k-rune blocks: ~30 ms for 16 MiB as for 1 GiB), and the pipeline would pay that once
+        // per 128 MiB.  k_scan's block count of the first sub-batch is on the host half a millisecond after its copy: with
+        // more than 2 KiB per block on average the rest goes in sub-batches of up to 512 MiB.
+        if (cudaEventSynchronize(slots[0]->ev_nblk) == cudaSuccess) {
+          const uint32_t nblk = *reinterpret_cast<uint32_t*>(slots[0]->h_cnt + 2);
+          if (chunks[0].nb / (nblk ? nblk : 1u) >= 2048 && chunks[0].nb >= (1u << 20)) {
+            batch_cap = 512ull << 20;
+            long_blocks = true;
+          }
+        }
+      }
     }
+    if (ci >= chunks.size()) break;
     Chunk& c = chunks[ci];
     WsSlot* sl = slots[ci % kPipeSlots];
     cudaStream_t st = sl->stream;

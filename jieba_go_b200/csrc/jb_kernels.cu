@@ -1442,6 +1442,10 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       sc.blocks_cap = ws.blocks_cap;
       launch_scan(T, sc, st);
       g_launches.fetch_add(1);
+      if (ws.h_nblk && ws.ev_nblk) {  // the host sizes the following sub-batches by the mean block length
+        cudaMemcpyAsync(ws.h_nblk, ws.counters + C_N_BLK, 4, cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(ws.ev_nblk, st);
+      }
       PROF(2);
       // the gated non-Han tokens that k_scan deferred only need the tile summaries: a one-CTA scan and a tiny kernel,
       // run on a side stream under k_route instead of leaving the GPU idle for them
@@ -1477,7 +1481,7 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       ra.path = ws.path;
       ra.wide_list = ws.wide_list;
       ra.wide_cap = ws.wide_cap;
-      ra.min_chunk = 16;  // measured on 10k-rune blocks: fuller warps beat more warps (instruction issue is per warp)
+      ra.min_chunk = 32;  // few, long blocks: full warps (measured on 10k-rune blocks: 18.4 ms/GB with 32 lanes per warp, 28.6 with 16, 28.0 with 8: the cost of an iteration does not depend on how many lanes it serves)
       launch_route(T, ra, g_num_sms, st);
       g_launches.fetch_add(1);
       {
@@ -1506,7 +1510,7 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       ea.bp = ws.bp;
       ea.s_bits = ws.s_bits;
       ea.e_bits = ws.e_bits;
-      ea.min_chunk = 1;
+      ea.min_chunk = 1;  // (k_emit: no measurable difference between 1 and 32 lanes per warp on 10k-rune blocks)
       launch_emit(T, ea, use_hmm, g_num_sms, st);
       g_launches.fetch_add(1);
       if (forked) cudaStreamWaitEvent(st, ws.ev_join, 0);

@@ -76,6 +76,9 @@ struct Workspace {
   uint32_t* tile_first_doc = nullptr;  // per rank tile: first document index with doc_off >= the tile's first byte
   uint32_t* rank_cnt = nullptr;  // per rank tile: token count, then exclusive prefix
   uint32_t* counters = nullptr;  // Counter
+  // optional: the number of Han blocks goes to this (pinned) host word right after k_scan, ev_nblk is recorded behind it
+  uint32_t* h_nblk = nullptr;
+  cudaEvent_t ev_nblk = nullptr;
   double* dbg_proba = nullptr;   // optional: selected route value per slot (general path)
   double* dbg_R = nullptr;       // optional: selected route value / word length per rune (streaming path)
   uint8_t* dbg_D = nullptr;

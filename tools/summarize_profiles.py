@@ -13,7 +13,7 @@ want = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'sm__inst_executed.
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__issue_active.avg.pct_of_peak_sustained_active'] + ['smsp__average_warps_issue_stalled_%s_per_issue_active.ratio' % x for x in (
             'long_scoreboard', 'short_scoreboard', 'wait', 'barrier', 'branch_resolving', 'not_selected', 'math_pipe_throttle', 'lg_throttle', 'mio_throttle')]
-caps = [('k_route', 2), ('k_scan', 2), ('k_emit', 2), ('k_rank_scatter', 2), ('k_emit', 3), ('k_route', 3)]
+caps = [('k_route', 2), ('k_scan', 2), ('k_emit', 2), ('k_rank_scatter', 2), ('k_emit', 3), ('k_route', 3), ('k_route', 4)]
 out, traffic = [['capture', 'kernel', 'metric', 'unit', 'value']], []
 for k, c in caps:
     rep = 'gpurun_out/%s_%s_c%d.ncu-rep' % (tag, k, c)
@@ -28,12 +28,16 @@ for k, c in caps:
     tob = lambda n: float(vals[n][1].replace(',', '')) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[vals[n][0]]
     nb = json.loads([l for l in open('gpurun_out/%s_bench_config%d.json' % (tag, c)) if l.startswith('{')][-1])['config']['bytes_per_gpu_per_step']
     traffic.append({'kernel': k, 'config': c, 'input_bytes': nb, 'dram_read_bytes': tob('dram__bytes_read.sum'), 'dram_write_bytes': tob('dram__bytes_write.sum'),
+                    'l2_hit_rate_pct': float(vals['lts__t_sector_hit_rate.pct'][1]), 'l1_hit_rate_pct': float(vals['l1tex__t_sector_hit_rate.pct'][1]),
+                    'lts_throughput_pct': float(vals['lts__throughput.avg.pct_of_peak_sustained_elapsed'][1]),
                     'capture': 'profiles/%s_ncu_full_summary.csv (%s_c%d)' % (tag, k, c)})
 csv.writer(open('profiles/%s_ncu_full_summary.csv' % tag, 'w')).writerows(out)
 json.dump(traffic, open('profiles/ncu_traffic.json', 'w'), indent=1)
 shutil.copy('gpurun_out/%s_ncu_launches_config2.csv' % tag, 'profiles/')
 for c in ('config2', 'config3', 'config4', 'reference_arm'):
     open('profiles/%s_bench_%s.json' % (tag, c), 'w').write([l for l in open('gpurun_out/%s_bench_%s.json' % (tag, c)) if l.startswith('{')][-1])
+for extra in ('latency.json', 'pcie_1gpu.json'):
+    if os.path.exists('gpurun_out/%s_%s' % (tag, extra)): shutil.copy('gpurun_out/%s_%s' % (tag, extra), 'profiles/%s_%s' % (tag, extra))
 hot = subprocess.run('python tools/ncu_lines.py gpurun_out/%s_k_route_c2.ncu-rep k_routeILi16 jb_stream.cu 45' % tag, shell=True, capture_output=True, text=True).stdout
 open('profiles/%s_k_route_source_hotspots.txt' % tag, 'w').write('k_route<16,4>, config 2 (1e9 B), ncu --set full, per CUDA source line (tools/ncu_lines.py)\n' + hot)
 for t in traffic: print(t['kernel'], t['config'], round(t['dram_read_bytes'] / 1e6), round(t['dram_write_bytes'] / 1e6))
