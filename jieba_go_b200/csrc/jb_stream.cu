@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   // A position that needs more probes than the two prefetched ones stays for further iterations (one dependent
   // probe each, in flight in e2); meanwhile its selector state is parked in the registers of f / e3 / h2 / h3.
   bool chain = false;
-  uint32_t cs = 0;  // L | home-slot flag << 7 | maxlen << 8 | best_d << 16 | last_d << 24
+  uint32_t cs = 0;  // L | home-slot flag << 7 | maxlen << 8 | best_d << 16
 
   // the lane now stands on the rune at p: decode it from the window, issue its table loads (first = true: last
   // rune of a block, nothing to its right)
@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
           }
           p = bd.x + tmis;
           kq = 0;
+          sring[M * kRtThreads] = 0.0;  // R[-1]: {j, 0.0} at the end of the block (T:522) -- cell M is not written before rune M
           wc = p >> 3;
           const uint2 t0 = __ldg(text8 + wc);
           w0 = t0.x;
@@ -562,8 +563,8 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     // the next entry of its prefix chain in e2 and its selector state parked in f / e3 / h2 / h3 / cs.
     // Candidates in ascending length: pieceFreq + nextBestPiece.proba (T:519-529) into maxIndexProba's running
     // (prev, best) pair: each candidate is compared with the previous one, first with minFloat (T:565-578). ----
-    double best_v, last_v, prev_v;  // (all of these are written before they are read whenever the lane is active)
-    uint32_t best_d, last_d, L, parent, slot, hs, maxlen;
+    double best_v, prev_v;  // (all of these are written before they are read whenever the lane is active)
+    uint32_t best_d, L, parent, slot, hs, maxlen;
     bool more = false, home = false;  // home: the next probe looks at the home slot of its key
     if (active) {
       const bool chained = chain, fresh = !chain;
@@ -578,13 +579,15 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       const double wt1 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
       const double wtA = __longlong_as_double(((long long)e2.y << 32) | (long long)e2.x);
       const double wt3 = __longlong_as_double(((long long)e3.y << 32) | (long long)e3.x);
-      // candidate (i, i+1) of a fresh lane, or the parked selector state
-      const double v1 = wt1 + (kq >= 1u ? RA : 0.0);  // {j, 0.0} at the end of the block (T:522)
+      // candidate (i, i+1) of a fresh lane, or the parked selector state.  (R[-1] = 0.0 sits in the ring: no special
+      // case for a word that ends the block.)  maxIndexProba's "best.index == -1 -> return prev" (T:574-576) needs no
+      // (last) pair here: weights are finite or -Inf and never NaN (negative counts are rejected), so the first
+      // candidate fails v >= minFloat only when it is -Inf, any further candidate then passes v >= -Inf, and the
+      // fallback can only fire for a position whose ONLY candidate is the single rune -- it returns that one.
+      const double v1 = wt1 + RA;
       best_v = chained ? __hiloint2double((int)e3.y, (int)e3.x) : v1;
-      last_v = chained ? __hiloint2double((int)e3.w, (int)e3.z) : v1;
       prev_v = chained ? wt1 : v1;
       best_d = chained ? ((cs >> 16) & 0xFFu) : ((v1 >= JB_MINF) ? 1u : 0u);
-      last_d = chained ? (cs >> 24) : 1u;
       // which entries buildDag looks at (T:469-482), and what it finds
       const bool gA = chained || (!(f.z & JB_FIRST_GATE) && maxlen > 1u && ((f.w >> jb_bloom_bit(rA)) & 1u));
       const bool mA = gA && e2.z == parA && JB_RB_RUNE(e2.w) == rA;
@@ -592,26 +595,22 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       const bool xA = gA && !mA && e2.z != JB_PARENT_EMPTY && (!homeA || (e2.w & JB_RB_CONT));
       const uint32_t LA = L0 + 1u;
       const bool cA = mA && jb_w_positive(wtA);  // val > 0 -> edge (T:479-481)
-      const double vA = wtA + (LA > kq ? 0.0 : RB);
+      const double vA = wtA + RB;
       const bool bA = cA && vA >= prev_v;
       best_d = bA ? LA : best_d;
       best_v = bA ? vA : best_v;
       prev_v = cA ? vA : prev_v;
-      last_d = cA ? LA : last_d;
-      last_v = cA ? vA : last_v;
       const bool contA = mA && LA < maxlen && (((e2.w >> 21) >> jb_bloom11(rB)) & 1u);  // some key extends the prefix by rB
       // the 3-rune prefix of a fresh lane is here already
       const bool gB = contA && fresh;
       const bool mB = gB && e3.z == slotA && JB_RB_RUNE(e3.w) == rB;
       const bool xB = gB && !mB && e3.z != JB_PARENT_EMPTY && (e3.w & JB_RB_CONT);
       const bool cB = mB && jb_w_positive(wt3);
-      const double vB = wt3 + (kq >= 3u ? RC : 0.0);
+      const double vB = wt3 + RC;
       const bool bB = cB && vB >= prev_v;
       best_d = bB ? 3u : best_d;
       best_v = bB ? vB : best_v;
       prev_v = cB ? vB : prev_v;
-      last_d = cB ? 3u : last_d;
-      last_v = cB ? vB : last_v;
       const bool contB = mB && maxlen > 3u && (((e3.w >> 21) >> jb_bloom11(rC)) & 1u);
       // anything beyond goes on in later iterations, one dependent probe each
       const bool deeperA = contA && chained;
@@ -627,14 +626,12 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     if (active && more) {  // park the selector state, issue the next probe
       e3.x = (uint32_t)__double2loint(best_v);
       e3.y = (uint32_t)__double2hiint(best_v);
-      e3.z = (uint32_t)__double2loint(last_v);
-      e3.w = (uint32_t)__double2hiint(last_v);
       f.x = (uint32_t)__double2loint(prev_v);
       f.y = (uint32_t)__double2hiint(prev_v);
       f.z = parent;
       h2 = hs;
       h3 = slot;
-      cs = L | (home ? 0x80u : 0u) | (maxlen << 8) | (best_d << 16) | (last_d << 24);
+      cs = L | (home ? 0x80u : 0u) | (maxlen << 8) | (best_d << 16);
       e2 = __ldg(entries + slot);
       chain = true;
     }
@@ -642,10 +639,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     if (active && !more) {
       chain = false;
       // ---- commit the position ----
-      if (best_d == 0) {  // best.index == -1 -> return prev (T:574-576)
-        best_d = last_d;
-        best_v = last_v;
-      }
+      best_d = max(best_d, 1u);  // best.index == -1 -> return prev (T:574-576): the lone single-rune candidate, see above
       sring[(kq & M) * kRtThreads] = best_v;
       const uint32_t idx = e3i - kq, pwd = idx / PPW;
       if (pwd != accw) {
