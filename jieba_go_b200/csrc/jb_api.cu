@@ -380,6 +380,8 @@ static int create_from_image(const TableImage& img, const jb_options* opt, jb_to
     return rc;
   }
   T.hash_mask = (uint32_t)(img.entries.size() - 1);
+  T.hash_shift = 32;
+  for (size_t c = img.entries.size(); c > 1; c >>= 1) T.hash_shift--;
   T.n_emit_supp = (uint32_t)img.emit_supp_rune.size();
   T.n_supp = (uint32_t)img.supp_lo.size();
   for (uint32_t i = 0; i < T.n_supp; i++) {

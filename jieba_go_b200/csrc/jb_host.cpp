@@ -623,6 +623,8 @@ int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int ver, Tabl
   while (cap < 3 * n_hash + 16) cap <<= 1;
   img.entries.assign(cap, JbEntry{0.0, JB_PARENT_EMPTY, 0u});
   const uint32_t hmask = (uint32_t)(cap - 1);
+  uint32_t hshift = 32;
+  for (size_t c = cap; c > 1; c >>= 1) hshift--;
   std::vector<uint32_t> order(keys.size());
   for (uint32_t i = 0; i < keys.size(); i++) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a2, uint32_t b2) { return keys[a2].runes.size() < keys[b2].runes.size(); });
@@ -656,7 +658,7 @@ int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int ver, Tabl
     // home slot: fold over the key's runes (jb_common.h)
     uint32_t hs = k.runes[0] < 0x10000 ? JB_PARENT_FIRST(k.runes[0]) : jb_hash_next(JB_PARENT_ROOT, k.runes[0]);
     for (size_t j = 1; j < L; j++) hs = jb_hash_next(hs, k.runes[j]);
-    uint32_t sidx = hs & hmask;
+    uint32_t sidx = jb_hash_slot(hs, hshift);
     if (img.entries[sidx].parent != JB_PARENT_EMPTY) img.entries[sidx].rb |= JB_RB_CONT;  // displaced from its home slot
     while (img.entries[sidx].parent != JB_PARENT_EMPTY) sidx = (sidx + 1) & hmask;
     img.entries[sidx].w = k.freq > 0 ? k.w : -INFINITY;
@@ -755,7 +757,7 @@ void Sha256::finish(uint8_t out[32]) {
 }
 
 namespace {
-const char kImgMagic[8] = {'J', 'B', 'T', 'I', '0', '0', '0', '2'};  // bump when JbFirst / JbEntry / the hash change
+const char kImgMagic[8] = {'J', 'B', 'T', 'I', '0', '0', '0', '3'};  // bump when JbFirst / JbEntry / the hash change
 struct ImgHeader {
   char magic[8];
   uint8_t key[32];

@@ -431,7 +431,7 @@ __device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, 
       } else {
         double pw;
         uint32_t prb;
-        int ps = jb_probe_edge(T.entries, T.hash_mask, hs, JB_PARENT_ROOT, r0, &pw, &prb);
+        int ps = jb_probe_edge(T.entries, T.hash_mask, T.hash_shift, hs, JB_PARENT_ROOT, r0, &pw, &prb);
         if (ps >= 0 && jb_w_positive(pw)) {
           wv[0] = pw;
           info = (uint32_t)JB_MAX_DELTA << 8;
@@ -459,7 +459,7 @@ __device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, 
           if (!may) break;
           double pw;
           uint32_t prb;
-          int ps = jb_probe_edge(T.entries, T.hash_mask, hs, parent, rl, &pw, &prb);
+          int ps = jb_probe_edge(T.entries, T.hash_mask, T.hash_shift, hs, parent, rl, &pw, &prb);
           if (ps < 0) break;  // !found -> break (tokenizer.go:476-478)
           L++;
           qi += len;
@@ -501,7 +501,7 @@ __device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, 
           if (r0 >= 0x10000) {
             double pw;
             uint32_t prb;
-            parent = (uint32_t)jb_probe_edge(T.entries, T.hash_mask, hs2, JB_PARENT_ROOT, r0, &pw, &prb);
+            parent = (uint32_t)jb_probe_edge(T.entries, T.hash_mask, T.hash_shift, hs2, JB_PARENT_ROOT, r0, &pw, &prb);
           }
           int qi = i + len0;
           while (o < cnt) {
@@ -509,7 +509,7 @@ __device__ void split_tile(const JbTables& T, const SplitArgs& A, SplitSmem& S, 
             uint32_t rl = d_decode(&S.t.sb[qi], len);
             double pw;
             uint32_t prb;
-            int ps = jb_probe_edge(T.entries, T.hash_mask, hs2, parent, rl, &pw, &prb);
+            int ps = jb_probe_edge(T.entries, T.hash_mask, T.hash_shift, hs2, parent, rl, &pw, &prb);
             if (ps < 0) break;
             qi += len;
             if (jb_w_positive(pw)) wtile[excl + o++] = pw;
@@ -1208,13 +1208,13 @@ __global__ void k_debug_lookup(const JbTables T, const uint32_t* runes, int L, i
     parent = JB_PARENT_FIRST(r0);
   } else {
     uint32_t rb;
-    int ps = jb_probe_edge(T.entries, T.hash_mask, hs, JB_PARENT_ROOT, r0, &cw, &rb);
+    int ps = jb_probe_edge(T.entries, T.hash_mask, T.hash_shift, hs, JB_PARENT_ROOT, r0, &cw, &rb);
     k = ps < 0 ? 0 : (jb_w_positive(cw) ? 2 : 1);
     parent = (uint32_t)ps;
   }
   for (int j = 1; j < L && k != 0; j++) {
     uint32_t rb;
-    int ps = jb_probe_edge(T.entries, T.hash_mask, hs, parent, runes[j], &cw, &rb);
+    int ps = jb_probe_edge(T.entries, T.hash_mask, T.hash_shift, hs, parent, runes[j], &cw, &rb);
     k = ps < 0 ? 0 : (jb_w_positive(cw) ? 2 : 1);
     parent = (uint32_t)ps;
   }

@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   const uint2* __restrict__ text8 = reinterpret_cast<const uint2*>(A.text - tmis);
   const uint4* __restrict__ first = reinterpret_cast<const uint4*>(T.first);
   const uint4* __restrict__ entries = reinterpret_cast<const uint4*>(T.entries);
-  const uint32_t hmask = T.hash_mask;
+  const uint32_t hmask = T.hash_mask, hshift = T.hash_shift;
   double* const sring = &ring[0][tid];   // this lane's ring cells: index * kRtThreads
   uint16_t* const srr = &rr[0][tid];
   uint32_t qh = 0, qt = 0;
@@ -500,9 +500,9 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     f = ldg_keep(first + r0);
     if (!first_rune) {  // (with one rune to the right the 3-rune slot is computed from a stale rune: loaded, never looked at)
       h2 = jb_hash_next(JB_PARENT_FIRST(r0), r1);
-      e2 = __ldg(entries + (h2 & hmask));
+      e2 = __ldg(entries + (h2 >> hshift));
       h3 = jb_hash_next(h2, srr[((kq - 2u) & M) * kRtThreads]);
-      e3 = __ldg(entries + (h3 & hmask));
+      e3 = __ldg(entries + (h3 >> hshift));
     }
     return (x & 0xF0u) == 0xE0u;  // inside a Han block every rune has 3 bytes -- or 4 (k_wide)
   };
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       const uint32_t L0 = chained ? (cs & 0x7Fu) : 1u;  // runes of the prefix matched so far
       maxlen = chained ? ((cs >> 8) & 0xFFu) : min(min((f.z >> 8) & 0xFFu, 31u), kq + 1u);
       const uint32_t parA = chained ? f.z : JB_PARENT_FIRST(r0);
-      const uint32_t slotA = chained ? h3 : (h2 & hmask), slot3 = h3 & hmask;
+      const uint32_t slotA = chained ? h3 : (h2 >> hshift), slot3 = h3 >> hshift;
       const bool homeA = fresh || (cs & 0x80u);
       const uint32_t kA = ((kq - L0) & M) * kRtThreads, kB = ((kq - L0 - 1u) & M) * kRtThreads, kC = ((kq - 3u) & M) * kRtThreads;
       const double RA = sring[kA], RB = sring[kB], RC = sring[kC];
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       parent = contB ? slot3 : ((deeperA || xB) ? slotA : parA);
       const uint32_t hn = jb_hash_next(contB ? h3 : h2, contB ? rC : rB);
       hs = home ? hn : (xB ? h3 : h2);
-      slot = home ? (hn & hmask) : (((xB ? slot3 : slotA) + 1u) & hmask);
+      slot = home ? (hn >> hshift) : (((xB ? slot3 : slotA) + 1u) & hmask);
     }
     __syncwarp();
     if (active && more) {  // park the selector state, issue the next probe
@@ -998,7 +998,7 @@ __global__ void __launch_bounds__(128) k_wide(const JbTables T, const WideArgs A
       } else {
         double pw;
         uint32_t prb;
-        const int ps = jb_probe_edge(T.entries, T.hash_mask, hs, JB_PARENT_ROOT, r0, &pw, &prb);
+        const int ps = jb_probe_edge(T.entries, T.hash_mask, T.hash_shift, hs, JB_PARENT_ROOT, r0, &pw, &prb);
         if (ps >= 0 && jb_w_positive(pw)) {
           w0 = pw;
           info = (uint32_t)JB_MAX_DELTA << 8;
@@ -1024,7 +1024,7 @@ __global__ void __launch_bounds__(128) k_wide(const JbTables T, const WideArgs A
           if (!may) break;
           double pw;
           uint32_t prb;
-          const int ps = jb_probe_edge(T.entries, T.hash_mask, hs, parent, rl, &pw, &prb);
+          const int ps = jb_probe_edge(T.entries, T.hash_mask, T.hash_shift, hs, parent, rl, &pw, &prb);
           if (ps < 0) break;
           L++;
           pos += cx.len_at(pos);
