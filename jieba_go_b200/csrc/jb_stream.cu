@@ -479,6 +479,9 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   bool exhausted = false, active = false;
   uint32_t bi = 0, p = 0, kq = 0, e3i = 0, nr = 0;  // block index, lead byte of the current rune (+ tmis), runes to its right, end / 3, runes (0: unknown)
   uint32_t r0 = 0;                                  // the current rune
+  // the three route values and runes to the right of the current one (a fresh lane needs nothing else from the rings)
+  double R1 = 0.0, R2 = 0.0;
+  uint32_t q12 = 0;  // rune 1 to the right | rune 2 to the right << 16
   uint4 f = make_uint4(0, 0, 0, 0), e2 = f, e3 = f; // in flight: first-rune entry, entries of the 2- and 3-rune prefixes
   uint32_t h2 = 0, h3 = 0;                          // their hash states
   uint32_t w0 = 0, w1 = 0, wn = 0, wc = 0xFFFFFFFFu;  // text window: 8-byte word wc in (w0, w1), first 4 bytes of word wc + 1 in wn
@@ -494,14 +497,14 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   auto setup_pos = [&](const bool first_rune) -> bool {
     const uint32_t o = p & 7u;
     const uint32_t x = __funnelshift_r(o & 4u ? w1 : w0, o & 4u ? wn : w1, (o & 3u) * 8u);
-    const uint32_t r1 = r0;
+    q12 = (q12 << 16) | r0;
     r0 = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
     srr[(kq & M) * kRtThreads] = (uint16_t)r0;
     f = ldg_keep(first + r0);
     if (!first_rune) {  // (with one rune to the right the 3-rune slot is computed from a stale rune: loaded, never looked at)
-      h2 = jb_hash_next(JB_PARENT_FIRST(r0), r1);
+      h2 = jb_hash_next(JB_PARENT_FIRST(r0), q12 & 0xFFFFu);
       e2 = __ldg(entries + (h2 >> hshift));
-      h3 = jb_hash_next(h2, srr[((kq - 2u) & M) * kRtThreads]);
+      h3 = jb_hash_next(h2, q12 >> 16);
       e3 = __ldg(entries + (h3 >> hshift));
     }
     return (x & 0xF0u) == 0xE0u;  // inside a Han block every rune has 3 bytes -- or 4 (k_wide)
@@ -543,6 +546,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
           p = bd.x + tmis;
           kq = 0;
           sring[M * kRtThreads] = 0.0;  // R[-1]: {j, 0.0} at the end of the block (T:522) -- cell M is not written before rune M
+          R1 = 0.0;
           wc = p >> 3;
           const uint2 t0 = __ldg(text8 + wc);
           w0 = t0.x;
@@ -573,9 +577,20 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       const uint32_t parA = chained ? f.z : JB_PARENT_FIRST(r0);
       const uint32_t slotA = chained ? h3 : (h2 >> hshift), slot3 = h3 >> hshift;
       const bool homeA = fresh || (cs & 0x80u);
-      const uint32_t kA = ((kq - L0) & M) * kRtThreads, kB = ((kq - L0 - 1u) & M) * kRtThreads, kC = ((kq - 3u) & M) * kRtThreads;
-      const double RA = sring[kA], RB = sring[kB], RC = sring[kC];
-      const uint32_t rA = srr[kA], rB = srr[kB], rC = srr[kC];  // the runes after a prefix of L0, L0 + 1, 3 runes
+      // route values / runes 1, 2, 3 positions to the right: registers for a fresh lane; a chained lane (L0 >= 2) reads the
+      // rings at L0 and L0 + 1
+      double RA = R1, RB = R2;
+      uint32_t rA = q12 & 0xFFFFu, rB = q12 >> 16;  // the runes after a prefix of L0, L0 + 1 (and 3: rC) runes
+      const uint32_t kC = ((kq - 3u) & M) * kRtThreads;
+      const double RC = sring[kC];
+      const uint32_t rC = srr[kC];
+      if (chained) {
+        const uint32_t kA = ((kq - L0) & M) * kRtThreads, kB = ((kq - L0 - 1u) & M) * kRtThreads;
+        RA = sring[kA];
+        RB = sring[kB];
+        rA = srr[kA];
+        rB = srr[kB];
+      }
       const double wt1 = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
       const double wtA = __longlong_as_double(((long long)e2.y << 32) | (long long)e2.x);
       const double wt3 = __longlong_as_double(((long long)e3.y << 32) | (long long)e3.x);
@@ -587,14 +602,16 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       const double v1 = wt1 + RA;
       best_v = chained ? __hiloint2double((int)e3.y, (int)e3.x) : v1;
       prev_v = chained ? wt1 : v1;
-      best_d = chained ? ((cs >> 16) & 0xFFu) : ((v1 >= JB_MINF) ? 1u : 0u);
+      // (v1 >= minFloat fails only for -Inf: route values of real text stay above -1e11, nowhere near -3.14e100; the
+      // test is done on the high word, as are the freq > 0 tests below: -Inf is the only weight with these bits)
+      best_d = chained ? ((cs >> 16) & 0xFFu) : ((uint32_t)__double2hiint(v1) != 0xFFF00000u ? 1u : 0u);
       // which entries buildDag looks at (T:469-482), and what it finds
       const bool gA = chained || (!(f.z & JB_FIRST_GATE) && maxlen > 1u && ((f.w >> jb_bloom_bit(rA)) & 1u));
       const bool mA = gA && e2.z == parA && JB_RB_RUNE(e2.w) == rA;
       // a foreign entry: linear probing goes on (past the home slot only if a key was displaced from it); empty: break
       const bool xA = gA && !mA && e2.z != JB_PARENT_EMPTY && (!homeA || (e2.w & JB_RB_CONT));
       const uint32_t LA = L0 + 1u;
-      const bool cA = mA && jb_w_positive(wtA);  // val > 0 -> edge (T:479-481)
+      const bool cA = mA && e2.y != 0xFFF00000u;  // val > 0 -> edge (T:479-481): a freq-0 key carries -Inf
       const double vA = wtA + RB;
       const bool bA = cA && vA >= prev_v;
       best_d = bA ? LA : best_d;
@@ -605,7 +622,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       const bool gB = contA && fresh;
       const bool mB = gB && e3.z == slotA && JB_RB_RUNE(e3.w) == rB;
       const bool xB = gB && !mB && e3.z != JB_PARENT_EMPTY && (e3.w & JB_RB_CONT);
-      const bool cB = mB && jb_w_positive(wt3);
+      const bool cB = mB && e3.y != 0xFFF00000u;
       const double vB = wt3 + RC;
       const bool bB = cB && vB >= prev_v;
       best_d = bB ? 3u : best_d;
@@ -641,6 +658,8 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       // ---- commit the position ----
       best_d = max(best_d, 1u);  // best.index == -1 -> return prev (T:574-576): the lone single-rune candidate, see above
       sring[(kq & M) * kRtThreads] = best_v;
+      R2 = R1;
+      R1 = best_v;
       const uint32_t idx = e3i - kq, pwd = idx / PPW;
       if (pwd != accw) {
         if (acc) atomicOr(&A.path[accw], acc);
