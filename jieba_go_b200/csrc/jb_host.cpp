@@ -618,6 +618,11 @@ int build_tables(const jb_dict_desc* dict, const jb_hmm_desc* hmm, int ver, Tabl
     }
   }
 
+  // a gated first rune (missing, or freq 0: T:469-472) starts no chain: its filter is empty, so the probe kernels need
+  // no separate gate test
+  for (auto& f : img.first)
+    if (f.info & JB_FIRST_GATE) f.child = 0;
+
   // hash table of trie edges: insert shorter keys first so that every parent id is known
   size_t cap = 64;
   while (cap < 3 * n_hash + 16) cap <<= 1;
@@ -757,7 +762,7 @@ void Sha256::finish(uint8_t out[32]) {
 }
 
 namespace {
-const char kImgMagic[8] = {'J', 'B', 'T', 'I', '0', '0', '0', '3'};  // bump when JbFirst / JbEntry / the hash change
+const char kImgMagic[8] = {'J', 'B', 'T', 'I', '0', '0', '0', '4'};  // bump when JbFirst / JbEntry / the hash change
 struct ImgHeader {
   char magic[8];
   uint8_t key[32];

@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
   // A position that needs more probes than the two prefetched ones stays for further iterations (one dependent
   // probe each, in flight in e2); meanwhile its selector state is parked in the registers of f / e3 / h2 / h3.
   bool chain = false;
-  uint32_t cs = 0;  // L | home-slot flag << 7 | maxlen << 8 | best_d << 16
+  uint32_t cs = 0;  // L | home-slot flag << 7 | best_d << 16
 
   // the lane now stands on the rune at p: decode it from the window, issue its table loads (first = true: last
   // rune of a block, nothing to its right)
@@ -568,12 +568,14 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     // Candidates in ascending length: pieceFreq + nextBestPiece.proba (T:519-529) into maxIndexProba's running
     // (prev, best) pair: each candidate is compared with the previous one, first with minFloat (T:565-578). ----
     double best_v, prev_v;  // (all of these are written before they are read whenever the lane is active)
-    uint32_t best_d, L, parent, slot, hs, maxlen;
+    uint32_t best_d, L, parent, slot, hs;
     bool more = false, home = false;  // home: the next probe looks at the home slot of its key
     if (active) {
       const bool chained = chain, fresh = !chain;
       const uint32_t L0 = chained ? (cs & 0x7Fu) : 1u;  // runes of the prefix matched so far
-      maxlen = chained ? ((cs >> 8) & 0xFFu) : min(min((f.z >> 8) & 0xFFu, 31u), kq + 1u);
+      // A key of LA runes needs LA - 1 runes to the right of this one: kq of them exist (beyond the block's end the rings
+      // hold stale runes).  Nothing else bounds the chain: a gated first rune has an empty Bloom filter (jb_host.cpp), and
+      // where no longer key exists the entry's filter is empty too.
       const uint32_t parA = chained ? f.z : JB_PARENT_FIRST(r0);
       const uint32_t slotA = chained ? h3 : (h2 >> hshift), slot3 = h3 >> hshift;
       const bool homeA = fresh || (cs & 0x80u);
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       // test is done on the high word, as are the freq > 0 tests below: -Inf is the only weight with these bits)
       best_d = chained ? ((cs >> 16) & 0xFFu) : ((uint32_t)__double2hiint(v1) != 0xFFF00000u ? 1u : 0u);
       // which entries buildDag looks at (T:469-482), and what it finds
-      const bool gA = chained || (!(f.z & JB_FIRST_GATE) && maxlen > 1u && ((f.w >> jb_bloom_bit(rA)) & 1u));
+      const bool gA = chained || (kq >= 1u && ((f.w >> jb_bloom_bit(rA)) & 1u));
       const bool mA = gA && e2.z == parA && JB_RB_RUNE(e2.w) == rA;
       // a foreign entry: linear probing goes on (past the home slot only if a key was displaced from it); empty: break
       const bool xA = gA && !mA && e2.z != JB_PARENT_EMPTY && (!homeA || (e2.w & JB_RB_CONT));
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       best_d = bA ? LA : best_d;
       best_v = bA ? vA : best_v;
       prev_v = cA ? vA : prev_v;
-      const bool contA = mA && LA < maxlen && (((e2.w >> 21) >> jb_bloom11(rB)) & 1u);  // some key extends the prefix by rB
+      const bool contA = mA && LA <= kq && (((e2.w >> 21) >> jb_bloom11(rB)) & 1u);  // some key extends the prefix by rB
       // the 3-rune prefix of a fresh lane is here already
       const bool gB = contA && fresh;
       const bool mB = gB && e3.z == slotA && JB_RB_RUNE(e3.w) == rB;
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       best_d = bB ? 3u : best_d;
       best_v = bB ? vB : best_v;
       prev_v = cB ? vB : prev_v;
-      const bool contB = mB && maxlen > 3u && (((e3.w >> 21) >> jb_bloom11(rC)) & 1u);
+      const bool contB = mB && kq >= 3u && (((e3.w >> 21) >> jb_bloom11(rC)) & 1u);
       // anything beyond goes on in later iterations, one dependent probe each
       const bool deeperA = contA && chained;
       more = xA || deeperA || xB || contB;
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
       f.z = parent;
       h2 = hs;
       h3 = slot;
-      cs = L | (home ? 0x80u : 0u) | (maxlen << 8) | (best_d << 16);
+      cs = L | (home ? 0x80u : 0u) | (best_d << 16);
       e2 = __ldg(entries + slot);
       chain = true;
     }
