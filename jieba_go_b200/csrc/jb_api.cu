@@ -32,6 +32,20 @@ static int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess) return fail(JB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// Entry points that select the tokenizer's device put the caller's current device back when they return.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 struct jb_dict_buf {
   HostDict d;
 };
@@ -349,6 +363,7 @@ static int create_from_image(const TableImage& img, const jb_options* opt, jb_to
   int dev = opt ? opt->device : -1;
   if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
   if (dev >= ndev) return fail(JB_EINVAL, "device ordinal out of range");
+  DeviceGuard dg;
   CUDA_TRY(cudaSetDevice(dev));
   int rc = JB_OK;
   jb_tokenizer* tk = new jb_tokenizer();
@@ -505,6 +520,7 @@ static void free_slot(WsSlot* s) {
 
 void jb_tokenizer_destroy(jb_tokenizer* tk) {
   if (!tk) return;
+  DeviceGuard dg;
   cudaSetDevice(tk->device);
   for (WsSlot* s : tk->free_ws) {
     free_slot(s);
@@ -685,6 +701,7 @@ struct EdgeWord {  // a bitmap word shared by two sub-batches / shards: OR-ed in
 //                  Words that straddle two sub-batches come back in `edges`.
 static int cut_range(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_off, uint64_t d_lo, uint64_t d_hi, int use_hmm, bool bits,
                      jb_result* res, std::vector<EdgeWord>* edges, uint64_t* n_tok_out) {
+  DeviceGuard dg;
   CUDA_TRY(cudaSetDevice(tk->device));  // (nothing acquired yet)
   const uint64_t g0 = doc_off[0];
   // plan: greedy batches of whole documents, one at a time (the size of the next one may change, see below)
@@ -1045,6 +1062,7 @@ static int cut_small(jb_tokenizer* tk, const uint8_t* text, const uint64_t* doc_
   SmallPath& sp = tk->small;
   std::unique_lock<std::mutex> lk(sp.mu, std::try_to_lock);
   if (!lk.owns_lock()) return 0;
+  DeviceGuard dg;
   if (cudaSetDevice(tk->device) != cudaSuccess) return 0;
   const int hmm = use_hmm ? 1 : 0;
   if (!small_prepare(tk, hmm)) return 0;
@@ -1226,6 +1244,7 @@ static int cut_device_impl(jb_tokenizer* tk, const uint8_t* d_text, uint64_t nby
                            const PipeOut& po, void* cuda_stream) {
   if (!tk || !d_doc_off || !po.d_n_tokens || (nbytes && !d_text)) return fail(JB_EINVAL, "null argument");
   if (nbytes >= (1ull << 31)) return fail(JB_ELIMIT, "the device entry points handle < 2 GiB per call");
+  DeviceGuard dg;
   CUDA_TRY(cudaSetDevice(tk->device));
   std::lock_guard<std::mutex> g(tk->dev_mu);
   WsSlot& sl = tk->dev_ws;
@@ -1289,6 +1308,7 @@ int jb_profile_read(jb_tokenizer* tk, double* ms_total, uint64_t* steps, int res
   if (!tk || !ms_total) return JB_EINVAL;
   std::lock_guard<std::mutex> g(tk->dev_mu);
   Workspace& ws = tk->dev_ws.ws;
+  DeviceGuard dg;
   cudaSetDevice(tk->device);
   profile_collect(ws);
   for (int i = 0; i < kNumProfKernels; i++) ms_total[i] = ws.prof_ms[i];
@@ -1309,6 +1329,7 @@ int jb_debug_lookup(jb_tokenizer* tk, const uint8_t* key, uint64_t len, double* 
     runes.push_back(r);
     i += wd;
   }
+  DeviceGuard dg;
   if (cudaSetDevice(tk->device) != cudaSuccess) return JB_ECUDA;
   int kind = 0;
   double wv = 0;
@@ -1320,6 +1341,7 @@ int jb_debug_lookup(jb_tokenizer* tk, const uint8_t* key, uint64_t len, double* 
 
 int jb_debug_route(jb_tokenizer* tk, const uint8_t* han_text, uint64_t nbytes, uint32_t* best_end, double* best_proba, uint64_t cap) {
   if (!tk || !han_text || !nbytes) return fail(JB_EINVAL, "null argument");
+  DeviceGuard dg;
   CUDA_TRY(cudaSetDevice(tk->device));
   std::lock_guard<std::mutex> g(tk->dev_mu);
   WsSlot& s = tk->dev_ws;
