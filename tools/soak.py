@@ -35,6 +35,9 @@ for rnd in range(n_rounds):
                 g = tk.cut_batch(t, d, hmm)
                 o = ora.cut_batch(t, d, hmm, 8)
                 ok = np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[3])
+                with tk.cut_batch_bits(t, d, hmm) as r:   # the bitmap result format, expanded on the host
+                    bs, be = r.expand(4)
+                    ok = ok and np.array_equal(r.doc_tok_off, o[3]) and np.array_equal(bs, o[0]) and np.array_equal(be, o[1])
                 if not ok:
                     bad += 1
                     print("MISMATCH round %d mode %d case %d hmm %s (n_words %d max_len %d)" % (rnd, mode, ci, hmm, n_words, max_len), flush=True)
