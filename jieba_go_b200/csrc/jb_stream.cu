@@ -16,6 +16,32 @@ namespace jb {
 enum : uint32_t { SC_HAN = 1, SC_ALNUM = 2, SC_SPACE = 3, SC_OTHER = 4, SC_INVALID = 5 };
 #define SCLS(c, len) (uint8_t)(((c) << 3) | (len))
 
+// ---- bulk asynchronous copy global -> shared (the TMA engine's 1-D form) with an mbarrier for completion ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 struct ScanSmem {
   uint8_t sb[kScRegion];
   uint32_t dsw[kScThreads + 2];  // dsw[j] <-> global word t0/32 - 2 + j; lane wj's own word is dsw[wj + 1]
@@ -29,7 +55,9 @@ struct ScanSmem {
   uint32_t wsum[kScThreads / 32];
   uint32_t ends_base;
   int last_hs;  // tile-local byte of the last Han-block start in the tile, -1: none
+  uint64_t mbar;  // completion of the tile's bulk copy
 };
+static_assert(kScRegion % 16 == 0 && kScLeft % 16 == 0 && kScTileBytes % 16 == 0, "bulk copies move multiples of 16 bytes between 16-byte aligned addresses");
 
 __device__ __forceinline__ bool s_is_alnum(uint32_t c) { return (c - '0' < 10u) || ((c | 0x20) - 'a' < 26u); }
 // unicode.IsSpace (T:302)
@@ -177,9 +205,19 @@ __global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const 
   ScCtx cx{&S, t0, n};
 
   // ---- stage the bytes (+ halo) and the document-start words -----------------------------------
+  // An interior tile of a 16-byte aligned text is ONE bulk asynchronous copy (cp.async.bulk, the TMA engine): a single
+  // thread issues it, the mbarrier counts the bytes in, and meanwhile every thread fetches the document-start words and
+  // clears its accumulators.  Tiles at either end of the text (and unaligned texts) are staged by the threads.
+  const int64_t Pr = (int64_t)t0 - kScLeft;
+  const bool bulk = ((reinterpret_cast<uintptr_t>(A.text) & 15) == 0) && Pr >= 0 && Pr + kScRegion <= (int64_t)n;
+  if (bulk) {
+    if (tid == 0) mbar_init(&S.mbar, 1);
+    __syncthreads();
+    if (tid == 0) bulk_load(S.sb, A.text + Pr, (uint32_t)kScRegion, &S.mbar);
+  }
   {
     const bool aligned = ((reinterpret_cast<uintptr_t>(A.text) & 15) == 0);
-    for (int c = tid; c < kScRegion / 16; c += kScThreads) {
+    for (int c = tid; c < (bulk ? 0 : kScRegion / 16); c += kScThreads) {
       const int64_t P = (int64_t)t0 - kScLeft + c * 16;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (aligned && P >= 0 && P + 16 <= (int64_t)n) {
@@ -208,6 +246,7 @@ __global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const 
       S.E[kScThreads] = 0;
     }
   }
+  if (bulk) mbar_wait(&S.mbar, 0);
   __syncthreads();
 
   // ---- stage 1: per 32-byte word, bitmasks of rune starts / Han / alnum / other-token runes ----
