@@ -642,3 +642,22 @@ def test_cached_table_image_constructor(tmp_path, small_synth, kind):
         _assert_same(b.cut_batch(t, off, hmm), want, t, off)
     with pytest.raises(Exception):
         b.add_word("甲乙", 5)   # read-only: no host dictionary
+
+
+def test_host_pool_limit_and_numa_helper(synth_pair):
+    """jb_host_pool_limit releases the pinned result pool; jb_bind_thread_to_device is best effort (single-NUMA VMs: -1)."""
+    import os
+    from jieba_go_b200 import _capi
+    sd, emit, tk, ora = synth_pair
+    L = _capi.lib()
+    text, doc_off = synth.make_corpus(sd, "freq", 1_000_000, synth.SEED_BASE + 95)
+    t, off = text.numpy(), doc_off.numpy().astype(np.uint64)
+    tk.cut_batch(t, off, False)                 # the freed result goes to the pool ...
+    assert L.jb_host_pool_limit(1 << 40) > 0    # ... and is still held
+    assert L.jb_host_pool_limit(0) == 0         # released
+    assert L.jb_host_pool_limit(4 << 30) == 0
+    _assert_same(tk.cut_batch(t, off, False), ora.cut_batch(t, off, False, 4), t, off)   # and the pool fills again
+    before = os.sched_getaffinity(0)
+    node = L.jb_bind_thread_to_device(0)
+    assert node >= -1 and len(os.sched_getaffinity(0)) >= 1
+    os.sched_setaffinity(0, before)
