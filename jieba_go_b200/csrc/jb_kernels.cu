@@ -1250,7 +1250,7 @@ static bool dalloc(T*& p, uint64_t count) {
 }
 
 void workspace_free(Workspace& ws) {
-  void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.rec, ws.gend, ws.wbuf, ws.ends,
+  void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.m_bits, ws.segs, ws.land, ws.longs, ws.rec, ws.gend, ws.wbuf, ws.ends,
                   ws.walks, ws.tile_sum, ws.tile_ctx, ws.deferred, ws.tile_last_hs, ws.tile_first_doc, ws.wide_list, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
@@ -1272,7 +1272,11 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     cap = (cap + kRankBytes) / kRankBytes * kRankBytes;
     uint64_t ntiles = cap / kTileBytes + 2;
     uint64_t nwords = cap / 32 + 8;
-    ok = ok && dalloc(ws.ds_bits, nwords) && dalloc(ws.s_bits, nwords) && dalloc(ws.e_bits, nwords);
+    ok = ok && dalloc(ws.ds_bits, nwords) && dalloc(ws.s_bits, nwords) && dalloc(ws.e_bits, nwords) && dalloc(ws.m_bits, nwords);
+    // a long block has >= 512 runes and is cut every 256: at most 1.5 segments per 256 runes = 768 bytes
+    ws.segs_cap = (uint32_t)(cap / 512 + 8);
+    ws.longs_cap = (uint32_t)(cap / 1536 + 8);
+    ok = ok && dalloc(ws.segs, (uint64_t)ws.segs_cap) && dalloc(ws.land, (uint64_t)ws.segs_cap) && dalloc(ws.longs, (uint64_t)ws.longs_cap);
     ok = ok && dalloc(ws.rec, ntiles * kTileSlots + 64) && dalloc(ws.gend, ntiles * (kTileSlots / 32) + 8);
     ok = ok && dalloc(ws.wbuf, ntiles * (uint64_t)wpt + 4096);
     ok = ok && dalloc(ws.ends, ntiles * kTileSlots + 8) && dalloc(ws.walks, ntiles * kTileSlots + 8);
@@ -1427,6 +1431,7 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       // ---- fast path: k_scan -> k_route -> k_emit (jb_stream.cu) ----------------------------------
       const uint32_t nt1 = scan_tiles(n);
       cudaMemsetAsync(ws.path, 0, ((uint64_t)n / 12 + 16) * 4, st);
+      if (use_hmm && n >= 1536) cudaMemsetAsync(ws.m_bits, 0, ((uint64_t)nwords + 4) * 4, st);  // (only long blocks leave marks)
       ScanArgs sc;
       sc.text = d_text;
       sc.n = n;
@@ -1510,9 +1515,17 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       ea.bp = ws.bp;
       ea.s_bits = ws.s_bits;
       ea.e_bits = ws.e_bits;
-      ea.min_chunk = 1;  // (k_emit: no measurable difference between 1 and 32 lanes per warp on 10k-rune blocks)
-      launch_emit(T, ea, use_hmm, g_num_sms, st);
-      g_launches.fetch_add(1);
+      ea.m_bits = ws.m_bits;
+      ea.min_chunk = 1;
+      ea.segs = ws.segs;
+      ea.segs_cap = ws.segs_cap;
+      ea.land = ws.land;
+      ea.longs = ws.longs;
+      ea.longs_cap = ws.longs_cap;
+      {
+        const int nl = launch_emit(T, ea, use_hmm, g_num_sms, st, n, ws.ds_bits);
+        if (nl > 0) g_launches.fetch_add(nl);
+      }
       if (forked) cudaStreamWaitEvent(st, ws.ev_join, 0);
       PROF(4);
       if (!out.no_general) JB_LAUNCH(k_fallback_reset, (unsigned)g_num_sms * 4, 256, 0, st, ws.counters, ws.s_bits, ws.e_bits, nwords + 4);

@@ -28,6 +28,9 @@ enum Counter {
   C_N_WIDE = 6,    // Han blocks with a 4-byte rune, handed to k_wide
   C_N_DEFER = 7,   // gated non-Han tokens waiting for the tile-summary scan
   C_FLAGS = 8,     // bit0: the batch must be redone by the general pipeline
+  C_N_SEG = 9,     // segments of long Han blocks (k_emit -> k_land / k_chain / k_emit)
+  C_N_LONG = 10,   // long Han blocks
+  C_CUR_SEG = 11,  // work cursor of k_emit over the segments
   C_N_BLK = 12,    // Han blocks listed by k_scan for k_route / k_emit
   C_CUR_ROUTE = 13,  // work cursors of k_route / k_emit
   C_CUR_EMIT = 14,
@@ -58,6 +61,11 @@ struct Workspace {
   uint32_t* ds_bits = nullptr;   // document-start bitmap
   uint32_t* s_bits = nullptr;    // token-start bitmap
   uint32_t* e_bits = nullptr;    // token-end bitmap (bit at the token's last byte)
+  uint32_t* m_bits = nullptr;    // single-rune pieces of the route (HMM: k_emit<2> -> k_runs)
+  uint2* segs = nullptr;         // long Han blocks cut into segments: (first byte, runes)
+  unsigned long long* land = nullptr;  // per segment: landing offsets of its first 16 runes
+  uint2* longs = nullptr;        // per long block: (first segment, segments)
+  uint32_t segs_cap = 0, longs_cap = 0;
   uint32_t* rec = nullptr;       // per-slot records
   uint32_t* gend = nullptr;      // per 32-slot group: end offset of its weights in wbuf
   double* wbuf = nullptr;        // candidate weights

@@ -4,6 +4,8 @@
 // viterbi T:668-730, stateTransitionRoute T:736-756, cutHMM T:273-285  (T = /root/reference/tokenizer.go).
 #include "jb_stream.cuh"
 
+#include <stdlib.h>
+
 #include "../../include/jieba_b200.h"
 
 namespace jb {
@@ -765,21 +767,35 @@ int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_
 // ==========================================================================================
 constexpr int kEmThreads = 128;
 
-template <bool HMM, int PB>
+// MODE 0: HMM off.  MODE 1: HMM on, Viterbi inside the walk (one lane carries a block's runs one after the other).
+// MODE 2: HMM on, the walk only -- multi-rune pieces become tokens, single-rune pieces are MARKED in m_bits (bit at the
+// rune's lead byte) and k_runs routes every run of marked runes on its own lane afterwards.  This is how the SEGMENTS of
+// long blocks are emitted (below): a run of single runes may cross a segment boundary, a mark may not care.
+//
+// Long blocks.  One lane per block walks a 10k-rune block hop by hop while most of the machine idles.  The walk is a
+// pointer chase k -> k + d(k), but it is the same chase from wherever it is entered: k_emit<0/1> therefore only CUTS a
+// block of kLongRunes runes or more into segments of kSegRunes runes (A.segs, A.longs); k_land computes, per segment and
+// for each of its first 16 runes, where the walk entered there leaves the segment; k_chain threads the true entry
+// through a block's segments; and a second k_emit launch (MODE 2 or 0) walks the segments, one lane each.
+constexpr uint32_t kSegRunes = 256, kLongRunes = 2 * kSegRunes;
+
+template <int MODE, int PB>
 __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const EmitArgs A) {
+  constexpr bool HMM = MODE == 1;
   constexpr uint32_t PPW = 32 / PB, PMASK = (1u << PB) - 1u;
   constexpr uint32_t kRegRun = 24;  // the four best paths of runs up to this length are carried in registers
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   if (A.counters[C_FLAGS] & 1u) return;
-  const uint32_t nblocks = min(A.counters[C_N_BLK], A.blocks_cap);
+  const uint32_t nblocks = min(A.counters[A.count_idx], A.blocks_cap);
   // few blocks (long ones): spread them over all warps instead of filling a few warps
   const uint32_t nwarps = gridDim.x * (kEmThreads / 32);
   const uint32_t chunk = min(32u, max(A.min_chunk, (nblocks + nwarps - 1) / nwarps));
   const uintptr_t tbase = reinterpret_cast<uintptr_t>(A.text);
-  BitAcc2 sa, ea;  // HMM off: every lane emits a token per iteration, merged per 32-byte word
+  BitAcc2 sa, ea, ma;  // HMM off: every lane emits a token per iteration, merged per 32-byte word
   sa.init(A.s_bits);
   ea.init(A.e_bits);
+  ma.init(A.m_bits);
   // HMM on: the lanes that emit in a given iteration are few and spread over several code sites; the per-lane word
   // accumulator then costs more than it saves: straight atomics
   auto set_s = [&](uint32_t q) {
@@ -805,7 +821,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
     if (nm) {
       if (qh == qt && !exhausted) {
         uint32_t b0 = 0;
-        if (lane == 0) b0 = atomicAdd(&A.counters[C_CUR_EMIT], chunk);
+        if (lane == 0) b0 = atomicAdd(&A.counters[A.cursor_idx], chunk);
         b0 = __shfl_sync(FULL, b0, 0);
         if (b0 >= nblocks) exhausted = true;
         else {
@@ -824,6 +840,18 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           run_n = 0;
           pt = 0xFFFFFFFFu;
           active = npos != 0;  // 0: the block went to k_wide
+          if (MODE != 2 && A.segs && npos >= kLongRunes) {  // a long block: cut it into segments for the second launch
+            const uint32_t nseg = (npos + kSegRunes - 1) / kSegRunes;
+            const uint32_t s0 = atomicAdd(&A.counters[C_N_SEG], nseg), li = atomicAdd(&A.counters[C_N_LONG], 1u);
+            if (s0 + nseg <= A.segs_cap && li < A.longs_cap) {
+              for (uint32_t j = 0; j < nseg; j++)
+                A.segs[s0 + j] = make_uint2(P0 + 3u * kSegRunes * j, min(kSegRunes, npos - kSegRunes * j));
+              A.longs[li] = make_uint2(s0, nseg);
+              active = false;
+            } else {
+              atomicOr(&A.counters[C_FLAGS], 1u);  // (the lists are sized so that this cannot happen)
+            }
+          }
         }
       }
       qh = min(qt, qh + (uint32_t)__popc(nm));
@@ -941,7 +969,9 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
         }
         run_n = 0;
       }
-      if (!single) {
+      if (MODE == 2 && d == 1u) {
+        ma.set(P0 + 3u * k);
+      } else if (!single) {
         set_s(P0 + 3u * k);
         set_e(P0 + 3u * (k + d) - 1u);
       }
@@ -950,6 +980,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
         if (!HMM) {
           sa.flush();
           ea.flush();
+          if (MODE == 2) ma.flush();
         }
         active = false;
       }
@@ -958,17 +989,281 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   }
 }
 
-int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st) {
+// ==========================================================================================
+// k_runs: cutZh's HMM half (T:228-253) with one lane per RUN of single-rune pieces instead of one lane per block.
+// Used for the long blocks that k_emit cuts into segments (a run may cross a segment boundary).
+// Runs are independent of each other (viterbi starts afresh for each, T:238,246) and k_emit<2> has marked their runes in
+// m_bits, so they are found position-parallel: a marked rune starts a run iff the rune before it (3 bytes back, same
+// document) is not marked.  A warp takes 32 words of the bitmap (1 KiB of text), collects the run starts in shared
+// memory and hands them out to its lanes; a lane walks its run rune by rune -- emission row, one Viterbi step
+// (stateTransitionRoute T:736-756: strict > from minFloat, list order), the four best paths carried as bit masks as in
+// k_emit<1> -- until the next rune is not marked, then applies viterbi's tail (T:723-729) and cutHMM (T:273-285).
+// (For short blocks k_emit<1> is faster -- 3.97 against 6.5 ms/GB on config 3 -- because few lanes of a warp are on a
+// Viterbi step at the same time here; for 10k-rune blocks the order is reversed.)
+// ==========================================================================================
+constexpr int kRunThreads = 128;
+constexpr int kRunWords = 8;                     // bitmap words per lane and chunk: a warp gathers the runs of 8 KiB of text
+constexpr int kRunQueue = 32 * kRunWords * 11;   // run starts per warp and chunk: at most 11 three-byte runes start in a 32-byte word
+
+__global__ void __launch_bounds__(kRunThreads) k_runs(const JbTables T, const EmitArgs A, uint32_t n, const uint32_t* __restrict__ ds_bits) {
+  constexpr uint32_t kRegRun = 24;
+  __shared__ uint16_t queue[kRunThreads / 32][kRunQueue];  // byte offsets inside the chunk
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((A.counters[C_FLAGS] & 1u) || A.counters[C_N_SEG] == 0) return;  // marks only come from the segments of long blocks
+  const uintptr_t tbase = reinterpret_cast<uintptr_t>(A.text);
+  const uint32_t nwords = (n + 31) / 32, nchunks = (nwords + 32 * kRunWords - 1) / (32 * kRunWords);
+  uint16_t* const q = queue[warp];
+  auto set_s = [&](uint32_t p) { atomicOr(&A.s_bits[p >> 5], 1u << (p & 31)); };
+  auto set_e = [&](uint32_t p) { atomicOr(&A.e_bits[p >> 5], 1u << (p & 31)); };
+  auto marked = [&](uint32_t p) -> bool {  // a single-rune piece starts at byte p, and p does not start a document
+    if (p >= n) return false;
+    const uint32_t w = p >> 5, b = 1u << (p & 31);
+    return (__ldg(A.m_bits + w) & b) && !(__ldg(ds_bits + w) & b);
+  };
+  for (uint32_t chunk = blockIdx.x * (kRunThreads / 32) + warp; chunk < nchunks; chunk += gridDim.x * (kRunThreads / 32)) {
+    // a lane looks at kRunWords consecutive words
+    const uint32_t w0 = (chunk * 32 + lane) * kRunWords, cbase = chunk * 32 * kRunWords * 32;
+    uint32_t starts[kRunWords], cnt = 0;
+    {
+      uint32_t prev = (w0 && w0 < nwords) ? __ldg(A.m_bits + w0 - 1) : 0u;
+#pragma unroll
+      for (int j = 0; j < kRunWords; j++) {
+        const uint32_t w = w0 + j;
+        const uint32_t mw = w < nwords ? __ldg(A.m_bits + w) : 0u, dw = w < nwords ? __ldg(ds_bits + w) : 0u;
+        // the rune 3 bytes back is marked too and no document starts here: the run goes on; else it starts here
+        starts[j] = mw & ~(((mw << 3) | (prev >> 29)) & ~dw);
+        cnt += __popc(starts[j]);
+        prev = mw;
+      }
+    }
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += v;
+    }
+    const uint32_t total = __shfl_sync(FULL, inc, 31);
+    {
+      uint32_t o = inc - cnt;
+#pragma unroll
+      for (int j = 0; j < kRunWords; j++) {
+        uint32_t m = starts[j];
+        while (m) {
+          q[o++] = (uint16_t)((lane * kRunWords + j) * 32u + (uint32_t)__ffs(m) - 1u);
+          m &= m - 1;
+        }
+      }
+    }
+    __syncwarp();
+    // The lanes take runs from the queue as they finish (ballot order), so that in every iteration all of them do the
+    // same thing: one Viterbi step (T:688-719).  A run that ends is flushed by its lane alone.
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t qnext = 0, p0 = 0, p = 0, run_n = 0;
+    bool active = false;
+    double V[4] = {0.0, 0.0, 0.0, 0.0};
+    // viterbi's fullPath (T:715-716) in bit form, per state: bits 0..23 = which runes of its best path are E or S
+    // (token ends), bits 24..31 = the path's length (a route with from == "" restarts it)
+    uint32_t pm[4] = {0, 0, 0, 0};
+    for (;;) {
+      const uint32_t idle = __ballot_sync(FULL, !active);
+      if (idle) {
+        const uint32_t mine = qnext + __popc(idle & lt_mask);
+        if (!active && mine < total) {
+          p0 = p = cbase + q[mine];
+          run_n = 0;
+          active = true;
+        }
+        qnext = min(total, qnext + (uint32_t)__popc(idle));
+        if (__all_sync(FULL, !active)) break;
+      }
+      if (active) {
+        const uintptr_t ap = tbase + p, a4 = ap & ~(uintptr_t)3;
+        const uint32_t xl = __ldg(reinterpret_cast<const uint32_t*>(a4));
+        const uint32_t xh = (ap & 3) >= 2 ? __ldg(reinterpret_cast<const uint32_t*>(a4 + 4)) : 0u;  // (never a word past the text)
+        const uint32_t x = __funnelshift_r(xl, xh, (uint32_t)(ap & 3) * 8u);
+        const uint32_t cp = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
+        const double2* ep = reinterpret_cast<const double2*>(T.emit + (size_t)cp * 4);
+        const double2 e0 = __ldg(ep), e1 = __ldg(ep + 1);
+        const double em[4] = {e0.x, e0.y, e1.x, e1.y};
+        if (run_n == 0) {
+#pragma unroll
+          for (int s = 0; s < 4; s++) V[s] = T.start[s] + em[s];
+          pm[0] = pm[1] = 1u << 24;
+          pm[2] = pm[3] = (1u << 24) | 1u;
+        } else {
+          double W[4];
+          uint32_t code = 0, npm[4];
+          const uint32_t step = (1u << 24) | (run_n < kRegRun ? (1u << run_n) : 0u);  // one more entry; E and S end a token
+#pragma unroll
+          for (int s = 0; s < 4; s++) {
+            const int pa = (s == 0 || s == 3) ? 2 : 0, pb = (s == 0 || s == 3) ? 3 : 1;
+            const double r0 = V[pa] + T.trans[s][0], r1 = V[pb] + T.trans[s][1];
+            double best = JB_MINF;
+            uint32_t from = 0;
+            if (r0 > best) {
+              best = r0;
+              from = 1;
+            }
+            if (r1 > best) {
+              best = r1;
+              from = 2;
+            }
+            W[s] = best + em[s];
+            code |= from << (2 * s);
+            // fullPath[s] = fullPath[route.from] + [s]; fullPath[""] is nil (T:715-716)
+            npm[s] = (from == 0 ? 0u : (from == 1 ? pm[pa] : pm[pb])) + (s >= 2 ? step : (1u << 24));
+          }
+#pragma unroll
+          for (int s = 0; s < 4; s++) {
+            V[s] = W[s];
+            pm[s] = npm[s];
+          }
+          A.bp[p / 3u] = (uint8_t)code;  // only read back for runs longer than the register window
+        }
+        run_n++;
+        if (marked(p + 3u)) {
+          p += 3u;
+        } else {
+          // ---- viterbi's tail (T:723-729) + cutHMM (T:273-285) ----
+          if (run_n == 1) {
+            set_s(p0);
+            set_e(p0 + 2u);
+          } else if (run_n <= kRegRun) {
+            const uint32_t pf = V[2] > V[3] ? pm[2] : pm[3];  // T:723-729
+            const uint32_t plen = pf >> 24;
+            // path[j] applies to rune j (T:277-283): a short path drops the run's tail
+            const uint32_t lm = (1u << plen) - 1u;
+            const uint32_t es = ((pf & 0xFFFFFFu) >> (run_n - plen)) & lm;
+            const uint32_t startm = ((es << 1) | 1u) & lm;
+            or_span(A.s_bits, p0, spread3(startm), spread3(startm >> 16));
+            or_span(A.e_bits, p0 + 2u, spread3(es), spread3(es >> 16));
+          } else {
+            const uint32_t i0 = p0 / 3u;
+            int st2 = V[2] > V[3] ? 2 : 3;
+            uint32_t kb = run_n - 1, plen = 0;
+            for (;;) {  // back-trace; stops early where route.from == "" (T:715-716)
+              const uint8_t code = A.bp[i0 + kb];
+              A.bp[i0 + kb] = (uint8_t)(st2 >= 2 ? 0x80 : 0);  // the state of this path entry is E or S
+              plen++;
+              if (kb == 0) break;
+              const int c = (code >> (2 * st2)) & 3;
+              if (c == 0) break;
+              st2 = (st2 == 0 || st2 == 3) ? (c == 1 ? 2 : 3) : (c == 1 ? 0 : 1);
+              kb--;
+            }
+            const uint32_t shift = run_n - plen;
+            bool prev_es = true;
+            for (uint32_t j2 = 0; j2 < plen; j2++) {
+              const bool es = A.bp[i0 + shift + j2] & 0x80;
+              const uint32_t qq = p0 + 3u * j2;
+              if (prev_es) set_s(qq);
+              if (es) set_e(qq + 2u);
+              prev_es = es;
+            }
+          }
+          active = false;
+        }
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+}
+
+// ==========================================================================================
+// k_land: one lane per segment.  land(t) = where the walk k -> k + d(k) entered at rune t of the segment first steps
+// at or past the segment's end, as an offset 0..15 into the next segment: land(t) = land(t + d(t)), with land(S + i) = i.
+// Right to left with the sixteen values that follow t kept as nibbles of one 64-bit word W (nibble i = land(t + 1 + i)):
+// land(t) is nibble d(t) - 1 of W, and W shifts by one nibble.  After rune 0, W holds land(0..15): all a segment's
+// possible entries (a word is at most 16 runes on this path: PB == 4).
+// ==========================================================================================
+__global__ void __launch_bounds__(256) k_land(const EmitArgs A) {
+  if (A.counters[C_FLAGS] & 1u) return;
+  const uint32_t nseg = min(A.counters[C_N_SEG], A.segs_cap);
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += gridDim.x * blockDim.x) {
+    const uint2 desc = A.segs[s];
+    unsigned long long W = 0xFEDCBA9876543210ull;
+    if (desc.y == kSegRunes) {  // (a shorter segment is its block's last: nothing to enter after it)
+      const uint32_t i0 = desc.x / 3u;
+      uint32_t i = i0 + kSegRunes - 1u, pw = __ldg(A.path + (i >> 3));
+      for (;;) {
+        const uint32_t d1 = (pw >> ((i & 7u) * 4u)) & 15u;
+        W = (W << 4) | ((W >> (4u * d1)) & 15ull);
+        if (i == i0) break;
+        i--;
+        if ((i & 7u) == 7u) pw = __ldg(A.path + (i >> 3));
+      }
+    }
+    A.land[s] = W;
+  }
+}
+
+// k_chain: one warp per long block threads the entry through its segments: entry(0) = 0, entry(j + 1) = nibble entry(j)
+// of land[j].  32 segments' words are loaded at a time; every lane follows the chain over them with shuffles.  A
+// segment that is entered at rune e > 0 begins there.
+__global__ void __launch_bounds__(128) k_chain(const EmitArgs A) {
+  if (A.counters[C_FLAGS] & 1u) return;
+  const uint32_t nlong = min(A.counters[C_N_LONG], A.longs_cap);
+  const uint32_t lane = threadIdx.x & 31u, nwarps = gridDim.x * (blockDim.x / 32u);
+  for (uint32_t li = blockIdx.x * (blockDim.x / 32u) + (threadIdx.x >> 5); li < nlong; li += nwarps) {
+    const uint2 lg = A.longs[li];
+    uint32_t e = 0;
+    for (uint32_t base = 0; base < lg.y; base += 32u) {
+      const uint32_t idx = base + lane, cnt = min(32u, lg.y - base);
+      const unsigned long long Wl = idx < lg.y ? A.land[lg.x + idx] : 0ull;
+      uint32_t my = 0;
+      for (uint32_t i = 0; i < cnt; i++) {
+        const unsigned long long Wi = __shfl_sync(FULL, Wl, (int)i);
+        if (lane == i) my = e;
+        e = (uint32_t)(Wi >> (4u * e)) & 15u;
+      }
+      if (idx < lg.y && my) {
+        uint2 d = A.segs[lg.x + idx];
+        d.x += 3u * my;
+        d.y = d.y > my ? d.y - my : 0u;
+        A.segs[lg.x + idx] = d;
+      }
+    }
+  }
+}
+
+int launch_emit(const JbTables& T, const EmitArgs& A0, bool hmm, int num_sms, cudaStream_t st, uint32_t n, const uint32_t* ds_bits) {
   const bool r16 = T.max_delta <= 16;
+  EmitArgs A = A0;
+  A.count_idx = C_N_BLK;
+  A.cursor_idx = C_CUR_EMIT;
+  // segments need d <= 16 (4-bit path entries) and a text that can hold a long block at all
+  const bool split = r16 && A.segs && A.land && A.longs && n >= 3u * kLongRunes;
+  if (!split) A.segs = nullptr;
   const unsigned grid = (unsigned)num_sms * (hmm ? 9u : 16u);  // resident CTAs per SM by register count (56 / 30)
   if (r16) {
-    if (hmm) k_emit<true, 4><<<grid, kEmThreads, 0, st>>>(T, A);
-    else k_emit<false, 4><<<grid, kEmThreads, 0, st>>>(T, A);
+    if (hmm) k_emit<1, 4><<<grid, kEmThreads, 0, st>>>(T, A);
+    else k_emit<0, 4><<<grid, kEmThreads, 0, st>>>(T, A);
   } else {
-    if (hmm) k_emit<true, 8><<<grid, kEmThreads, 0, st>>>(T, A);
-    else k_emit<false, 8><<<grid, kEmThreads, 0, st>>>(T, A);
+    if (hmm) k_emit<1, 8><<<grid, kEmThreads, 0, st>>>(T, A);
+    else k_emit<0, 8><<<grid, kEmThreads, 0, st>>>(T, A);
   }
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  int launches = 1;
+  if (split) {  // each of these returns at once when k_emit found no long block
+    k_land<<<(unsigned)num_sms * 8u, 256, 0, st>>>(A);
+    k_chain<<<(unsigned)num_sms * 8u, 128, 0, st>>>(A);
+    EmitArgs S = A;
+    S.blocks = A.segs;
+    S.blocks_cap = A.segs_cap;
+    S.count_idx = C_N_SEG;
+    S.cursor_idx = C_CUR_SEG;
+    S.segs = nullptr;
+    S.min_chunk = 32;
+    if (hmm) {
+      k_emit<2, 4><<<(unsigned)num_sms * 16u, kEmThreads, 0, st>>>(T, S);
+      k_runs<<<(unsigned)num_sms * 8u, kRunThreads, 0, st>>>(T, S, n, ds_bits);
+      launches += 4;
+    } else {
+      k_emit<0, 4><<<(unsigned)num_sms * 16u, kEmThreads, 0, st>>>(T, S);
+      launches += 3;
+    }
+  }
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 
 

@@ -8,6 +8,8 @@
 //                          update in one state machine -- candidates never leave registers; only the
 //                          chosen word length per rune (4 bits) goes to HBM.
 //   k_emit   (W, H, V, O)  one lane per Han block: findDagPath walk, Viterbi over single-rune runs, token bits.
+//                          Blocks of 512 runes or more are cut into 256-rune segments first (k_land, k_chain) and
+//                          walked one lane per segment; their Viterbi runs go to k_runs, one lane per run.
 //
 //   k_wide   (all rows)    the rare Han blocks that contain a 4-byte rune: one lane restates the reference per block.
 //
@@ -63,7 +65,16 @@ struct EmitArgs {
   uint8_t* bp;            // Viterbi back-pointers / state flags per rune, index = lead byte / 3
   uint32_t* s_bits;
   uint32_t* e_bits;
+  uint32_t* m_bits;       // single-rune pieces marked by k_emit<2> for k_runs (HMM)
   uint32_t min_chunk;
+  // long blocks: segment list (first byte, runes), per segment the landing offsets of its first 16 runes, and per long
+  // block (first segment, segments).  segs == nullptr: blocks of any length are walked by one lane.
+  uint2* segs;
+  uint32_t segs_cap;
+  unsigned long long* land;
+  uint2* longs;
+  uint32_t longs_cap;
+  uint32_t count_idx, cursor_idx;  // counters that hold the length of `blocks` and the work cursor (set by launch_emit)
 };
 
 struct WideArgs {
@@ -83,7 +94,8 @@ struct WideArgs {
 int launch_wide(const JbTables& T, const WideArgs& A, bool hmm, int num_sms, cudaStream_t st);
 int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st);
 int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st);
-int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st);
+// returns the number of kernels launched, or -1
+int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st, uint32_t n, const uint32_t* ds_bits);
 inline uint32_t scan_tiles(uint32_t n) { return (n + kScTileBytes - 1) / kScTileBytes; }
 
 #if defined(__CUDACC__)

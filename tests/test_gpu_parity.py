@@ -305,6 +305,46 @@ def test_long_single_rune_runs(small_synth, path):
         _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 2), text, off)
 
 
+@pytest.mark.parametrize("hmm", [False, True])
+def test_long_blocks_cut_into_segments(medium_pair, hmm):
+    """Han blocks of 512 runes or more are walked segment by segment (k_land / k_chain / k_emit over segments / k_runs):
+    block lengths on either side of the threshold and of every segment-count edge, made of dictionary words (tokens of
+    2..16 runes that straddle the 256-rune boundaries), of unknown runes (single-rune pieces: Viterbi runs that cross
+    the boundaries, also longer than the 24-rune register window) and of both mixed; blocks side by side in one
+    document (separated by ASCII only) and several long blocks per batch."""
+    sd, emit, tk, ora = medium_pair
+    rng = np.random.default_rng(77 + int(hmm))
+    known = set(w.decode() for w in sd.words if len(w) == 3)
+    pool = [chr(c) for c in range(0x4E00, 0x9FA6) if chr(c) not in known]
+    words = [w.decode() for w in sd.words]
+
+    def block(n, p_unknown):
+        out, have = [], 0
+        while have < n:
+            if rng.random() < p_unknown:
+                k = int(rng.integers(1, 40)) if rng.random() < 0.1 else 1
+                piece = "".join(pool[int(i)] for i in rng.integers(0, len(pool), k))
+            else:
+                piece = words[int(rng.integers(0, len(words)))]
+            piece = piece[: n - have]
+            out.append(piece)
+            have += len(piece)
+        return "".join(out)
+
+    docs = []
+    for n in [511, 512, 513, 767, 768, 769, 1023, 1024, 1025, 1279, 1280, 1281, 2048, 4097, 8192 + 255, 8192 + 256, 30000]:
+        for pu in (0.0, 0.3, 1.0):
+            docs.append(block(n, pu).encode())
+    docs.append((block(700, 0.2) + "a" + block(600, 0.5) + " " + block(100, 0.3) + "," + block(513, 0.0)).encode())
+    docs.append(("x" * 7 + block(5000, 0.3)).encode())  # the block does not start on a multiple of 3
+    text, off = pack_docs(docs)
+    _assert_same(tk.cut_batch(text, off, hmm), ora.cut_batch(text, off, hmm, 4), text, off)
+    # and through the small-call path (one document below 8 KiB with a long block in it)
+    one = block(2000, 0.3).encode()
+    t1, o1 = pack_docs([one])
+    _assert_same(tk.cut_batch(t1, o1, hmm), ora.cut_batch(t1, o1, hmm, 1), t1, o1)
+
+
 @pytest.mark.parametrize("path", PATHS)
 def test_keys_longer_than_16_runes(path):
     """A 20- and a 30-rune key: the route ring has 32 cells and path entries take 8 bits (k_route<32,8>)."""
