@@ -1235,7 +1235,15 @@ int launch_emit(const JbTables& T, const EmitArgs& A0, bool hmm, int num_sms, cu
   // segments need d <= 16 (4-bit path entries) and a text that can hold a long block at all
   const bool split = r16 && A.segs && A.land && A.longs && n >= 3u * kLongRunes;
   if (!split) A.segs = nullptr;
-  const unsigned grid = (unsigned)num_sms * (hmm ? 9u : 16u);  // resident CTAs per SM by register count (56 / 30)
+  // one resident wave: CTAs per SM by register count
+  static int occ[2] = {0, 0};
+  if (!occ[hmm]) {
+    int b = 0;
+    if (hmm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_emit<1, 4>, kEmThreads, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_emit<0, 4>, kEmThreads, 0);
+    occ[hmm] = b > 0 ? b : 8;
+  }
+  const unsigned grid = (unsigned)num_sms * (unsigned)occ[hmm];
   if (r16) {
     if (hmm) k_emit<1, 4><<<grid, kEmThreads, 0, st>>>(T, A);
     else k_emit<0, 4><<<grid, kEmThreads, 0, st>>>(T, A);

@@ -20,4 +20,9 @@ ncu --set full --clock-control none --import-source on -k regex:^k_emit\$ -s 3 -
   python bench.py --config 3 --steps 2 --warmup 3 --no-e2e --no-cpu --no-config5 > gpurun_out/${TAG}_ncu_k_emit_c3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:^k_route\$ -s 3 -c 1 -o gpurun_out/${TAG}_k_route_c4 \
   python bench.py --config 4 --steps 2 --warmup 3 --no-e2e --no-cpu --no-config5 > gpurun_out/${TAG}_ncu_k_route_c4.log 2>&1
+# config 4: the launch list (k_emit, k_land, k_chain, k_emit over the segments, k_runs) and the segment kernels
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 200 --csv --log-file gpurun_out/${TAG}_ncu_launches_config4.csv \
+  python bench.py --config 4 --steps 2 --warmup 1 --no-e2e --no-cpu --no-config5 > gpurun_out/${TAG}_ncu_launches_c4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:^k_runs\$ -s 3 -c 1 -o gpurun_out/${TAG}_k_runs_c4 \
+  python bench.py --config 4 --steps 2 --warmup 3 --no-e2e --no-cpu --no-config5 > gpurun_out/${TAG}_ncu_k_runs_c4.log 2>&1
 ls -la gpurun_out/${TAG}_* | head -40

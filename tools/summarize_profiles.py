@@ -13,7 +13,7 @@ want = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'sm__inst_executed.
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__issue_active.avg.pct_of_peak_sustained_active'] + ['smsp__average_warps_issue_stalled_%s_per_issue_active.ratio' % x for x in (
             'long_scoreboard', 'short_scoreboard', 'wait', 'barrier', 'branch_resolving', 'not_selected', 'math_pipe_throttle', 'lg_throttle', 'mio_throttle')]
-caps = [('k_route', 2), ('k_scan', 2), ('k_emit', 2), ('k_rank_scatter', 2), ('k_emit', 3), ('k_route', 3), ('k_route', 4)]
+caps = [('k_route', 2), ('k_scan', 2), ('k_emit', 2), ('k_rank_scatter', 2), ('k_emit', 3), ('k_route', 3), ('k_route', 4), ('k_runs', 4)]
 out, traffic = [['capture', 'kernel', 'metric', 'unit', 'value']], []
 for k, c in caps:
     rep = 'gpurun_out/%s_%s_c%d.ncu-rep' % (tag, k, c)
@@ -34,6 +34,7 @@ for k, c in caps:
 csv.writer(open('profiles/%s_ncu_full_summary.csv' % tag, 'w')).writerows(out)
 json.dump(traffic, open('profiles/ncu_traffic.json', 'w'), indent=1)
 shutil.copy('gpurun_out/%s_ncu_launches_config2.csv' % tag, 'profiles/')
+if os.path.exists('gpurun_out/%s_ncu_launches_config4.csv' % tag): shutil.copy('gpurun_out/%s_ncu_launches_config4.csv' % tag, 'profiles/')
 for c in ('config2', 'config3', 'config4', 'reference_arm'):
     open('profiles/%s_bench_%s.json' % (tag, c), 'w').write([l for l in open('gpurun_out/%s_bench_%s.json' % (tag, c)) if l.startswith('{')][-1])
 for extra in ('latency.json', 'pcie_1gpu.json'):
