@@ -12,11 +12,14 @@ python tools/pcie_probe.py > gpurun_out/${TAG}_pcie_1gpu.json 2> gpurun_out/${TA
 # launch list of the bench command itself (per-launch times under ncu are cold-cache and serialised)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/${TAG}_ncu_launches_config2.csv \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-config5 > gpurun_out/${TAG}_ncu_launches.log 2>&1
-for K in k_route k_scan k_emit k_rank_scatter; do
+for K in k_route k_scan k_rank_scatter; do
   ncu --set full --clock-control none --import-source on -k regex:^${K}\$ -s 3 -c 1 -o gpurun_out/${TAG}_${K}_c2 \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-config5 > gpurun_out/${TAG}_ncu_${K}.log 2>&1
 done
-ncu --set full --clock-control none --import-source on -k regex:^k_emit\$ -s 3 -c 1 -o gpurun_out/${TAG}_k_emit_c3 \
+# k_emit launches twice per step (blocks, then the segments of long blocks -- none in configs 2 and 3): capture a pair
+ncu --set full --clock-control none --import-source on -k regex:^k_emit\$ -s 6 -c 2 -o gpurun_out/${TAG}_k_emit_c2 \
+  python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-config5 > gpurun_out/${TAG}_ncu_k_emit.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:^k_emit\$ -s 6 -c 2 -o gpurun_out/${TAG}_k_emit_c3 \
   python bench.py --config 3 --steps 2 --warmup 3 --no-e2e --no-cpu --no-config5 > gpurun_out/${TAG}_ncu_k_emit_c3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:^k_route\$ -s 3 -c 1 -o gpurun_out/${TAG}_k_route_c4 \
   python bench.py --config 4 --steps 2 --warmup 3 --no-e2e --no-cpu --no-config5 > gpurun_out/${TAG}_ncu_k_route_c4.log 2>&1

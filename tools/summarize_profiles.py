@@ -19,7 +19,10 @@ for k, c in caps:
     rep = 'gpurun_out/%s_%s_c%d.ncu-rep' % (tag, k, c)
     if not os.path.exists(rep): continue
     rows = list(csv.reader(subprocess.run('ncu -i %s --page raw --csv' % rep, shell=True, capture_output=True, text=True).stdout.split('\n')))
-    h, u, d = rows[0], rows[1], rows[2]
+    h, u = rows[0], rows[1]
+    cand = [r for r in rows[2:] if len(r) == len(h)]
+    ti = h.index('gpu__time_duration.sum')
+    d = max(cand, key=lambda r: float(r[ti].replace(',', '')))  # (k_emit launches twice per step: blocks, then the segments of long blocks)
     vals = {}
     for i, n in enumerate(h):
         if n in want:
