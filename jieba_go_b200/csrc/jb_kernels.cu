@@ -1250,7 +1250,7 @@ static bool dalloc(T*& p, uint64_t count) {
 }
 
 void workspace_free(Workspace& ws) {
-  void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.m_bits, ws.segs, ws.land, ws.longs, ws.lblocks, ws.rec, ws.gend, ws.wbuf, ws.ends,
+  void* ptrs[] = {ws.text, ws.doc_off64, ws.doc_off32, ws.ds_bits, ws.s_bits, ws.e_bits, ws.m_bits, ws.segs, ws.land, ws.longs, ws.rec, ws.gend, ws.wbuf, ws.ends,
                   ws.walks, ws.tile_sum, ws.tile_ctx, ws.deferred, ws.tile_last_hs, ws.tile_first_doc, ws.wide_list, ws.path, ws.bp, ws.rank_cnt, ws.counters, ws.dbg_proba, ws.out_start, ws.out_end,
                   ws.out_doc_tok, ws.out_ntok};
   for (void* p : ptrs)
@@ -1277,14 +1277,8 @@ int workspace_reserve(Workspace& ws, uint64_t nbytes, uint64_t ndocs, double w_p
     ws.segs_cap = (uint32_t)(cap / 512 + 8);
     ws.longs_cap = (uint32_t)(cap / 1536 + 8);
     ok = ok && dalloc(ws.segs, (uint64_t)ws.segs_cap) && dalloc(ws.land, (uint64_t)ws.segs_cap) && dalloc(ws.longs, (uint64_t)ws.longs_cap);
-    // (the long-block stream of k_probe / k_select also lives in rec, gend and wbuf: one u16 per rune, one offset per
-    // 32 runes of a long block -- a block's last group may be partial, hence the extra ntiles -- and the weights)
-    ws.lgroups_cap = (uint32_t)std::min<uint64_t>(ntiles * (kTileSlots / 32 + 1) + 8, 0xFFFFFFF0ull);
-    ok = ok && dalloc(ws.rec, ntiles * kTileSlots + 64) && dalloc(ws.gend, (uint64_t)ws.lgroups_cap);
-    ws.pool_cap = ntiles * (uint64_t)wpt + 4096;
-    ok = ok && dalloc(ws.wbuf, ws.pool_cap);
-    ws.lblocks_cap = (uint32_t)(cap / (3 * 2048) + 8);
-    ok = ok && dalloc(ws.lblocks, (uint64_t)ws.lblocks_cap);
+    ok = ok && dalloc(ws.rec, ntiles * kTileSlots + 64) && dalloc(ws.gend, ntiles * (kTileSlots / 32) + 8);
+    ok = ok && dalloc(ws.wbuf, ntiles * (uint64_t)wpt + 4096);
     ok = ok && dalloc(ws.ends, ntiles * kTileSlots + 8) && dalloc(ws.walks, ntiles * kTileSlots + 8);
     ok = ok && dalloc(ws.tile_sum, ntiles + 8) && dalloc(ws.tile_ctx, ntiles + 8);
     ws.deferred_cap = (uint32_t)(cap / 64 + 4096);
@@ -1492,34 +1486,9 @@ int run_pipeline(const JbTables& T, Workspace& ws_in, const uint8_t* d_text, uin
       ra.path = ws.path;
       ra.wide_list = ws.wide_list;
       ra.wide_cap = ws.wide_cap;
-      // long blocks go to k_probe / k_select -- not in the small fixed-size batches, whose pool could overflow with no
-      // general kernels enqueued behind them
-      const bool long_route = !out.no_general && n >= 3u * 2048u && T.max_delta <= 16;  // (16-bit length masks)
-      ra.lblocks = long_route ? ws.lblocks : nullptr;
-      ra.lblocks_cap = ws.lblocks_cap;
-      ra.lgroups_cap = ws.lgroups_cap;
       ra.min_chunk = 32;  // few, long blocks: full warps (measured on 10k-rune blocks: 18.4 ms/GB with 32 lanes per warp, 28.6 with 16, 28.0 with 8: the cost of an iteration does not depend on how many lanes it serves)
       launch_route(T, ra, g_num_sms, st);
       g_launches.fetch_add(1);
-      if (long_route) {
-        LongArgs la;
-        la.text = d_text;
-        la.lblocks = ws.lblocks;
-        la.lblocks_cap = ws.lblocks_cap;
-        la.counters = ws.counters;
-        la.masks = reinterpret_cast<uint16_t*>(ws.rec);
-        la.gbase = ws.gend;
-        la.pool = ws.wbuf;
-        la.pool_cap = ws.pool_cap;
-        la.path = ws.path;
-        la.blocks = ws.ends;
-        la.wide_list = ws.wide_list;
-        la.wide_cap = ws.wide_cap;
-        la.dbg_R = ws.dbg_R;
-        la.dbg_D = ws.dbg_D;
-        const int nl = launch_route_long(T, la, g_num_sms, st);
-        if (nl > 0) g_launches.fetch_add(nl);
-      }
       {
         WideArgs wa2;
         wa2.text = d_text;

@@ -34,11 +34,7 @@ enum Counter {
   C_N_BLK = 12,    // Han blocks listed by k_scan for k_route / k_emit
   C_CUR_ROUTE = 13,  // work cursors of k_route / k_emit
   C_CUR_EMIT = 14,
-  C_N_LRT = 15,     // long Han blocks handed to k_probe / k_select
-  C_N_LGRP = 16,    // their 32-position groups
-  C_CUR_PROBE = 17, // k_probe's work cursor
-  C_POOL = 18,      // candidate weights reserved in the pool
-  C_NUM = 24
+  C_NUM = 16
 };
 
 constexpr int kNumProfKernels = 8;
@@ -70,9 +66,6 @@ struct Workspace {
   unsigned long long* land = nullptr;  // per segment: landing offsets of its first 16 runes
   uint2* longs = nullptr;        // per long block: (first segment, segments)
   uint32_t segs_cap = 0, longs_cap = 0;
-  uint4* lblocks = nullptr;      // long Han blocks for k_probe / k_select
-  uint32_t lblocks_cap = 0, lgroups_cap = 0;
-  uint64_t pool_cap = 0;         // entries of wbuf
   uint32_t* rec = nullptr;       // per-slot records
   uint32_t* gend = nullptr;      // per 32-slot group: end offset of its weights in wbuf
   double* wbuf = nullptr;        // candidate weights

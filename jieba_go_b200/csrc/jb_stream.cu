@@ -494,9 +494,6 @@ int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st) {
 // ==========================================================================================
 constexpr int kRtThreads = 128;
 constexpr int kRtQueue = 32;
-// Blocks of this many runes or more are not routed by one lane of k_route: at ~1 us per position a lane's chain of
-// dependent table loads would take milliseconds whatever else the GPU has to do (k_probe / k_select below).
-constexpr uint32_t kLongRoute = 2048;
 
 template <int RING, int PB, bool DBG>
 __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const RouteArgs A) {
@@ -587,18 +584,6 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
             while (sp == 0xFFFFFFFFu);
             nr = (bd.x - sp) / 3u + 1u;
           }
-          bool handed = false;
-          if (A.lblocks && nr >= kLongRoute) {  // a long block: k_probe + k_select route it (below)
-            const uint32_t ng = (nr + 31u) / 32u;
-            const uint32_t li = atomicAdd(&A.counters[C_N_LRT], 1u), g0 = atomicAdd(&A.counters[C_N_LGRP], ng);
-            if (li < A.lblocks_cap && g0 + ng <= A.lgroups_cap) {
-              A.lblocks[li] = make_uint4(bd.x, nr, bi, g0);
-              handed = true;
-            } else if (li < A.lblocks_cap) {
-              A.lblocks[li] = make_uint4(0, 0, 0, 0);  // (an entry k_probe / k_select skip; the block is routed here)
-            }
-          }
-          if (!handed) {
           p = bd.x + tmis;
           kq = 0;
           sring[M * kRtThreads] = 0.0;  // R[-1]: {j, 0.0} at the end of the block (T:522) -- cell M is not written before rune M
@@ -612,7 +597,6 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
           setup_pos(true);
           chain = false;
           active = true;
-          }
           }
         }
       }
@@ -761,198 +745,6 @@ __global__ void __launch_bounds__(kRtThreads, 8) k_route(const JbTables T, const
     }
     __syncwarp();
   }
-}
-
-// ==========================================================================================
-// Long blocks: k_probe + k_select.  In k_route a position costs ~270 dependent instructions and two L2 round trips
-// before its route value is known, and the next position needs that value: a 10k-rune block is a chain of 10k such
-// steps on one lane.  Only the last few instructions of a step depend on the chain -- which entries buildDag finds
-// (T:462-497) depends on the text alone.  So for the blocks k_route hands over:
-//   k_probe   one warp per block, 32 positions per round, every lane enumerates the candidates of its own position
-//             exactly as k_wide does (first-rune entry, then the prefix chain: Bloom test, trie-edge probe, freq > 0)
-//             and the warp appends them to a stream in the order the selector will read them: per position a 16-bit
-//             mask of candidate lengths, and the candidates' weights (f64), compacted with a warp prefix sum;
-//   k_select  one lane per block, right to left: pieceFreq + next.proba (T:519-529) and maxIndexProba (T:565-578)
-//             over the recorded candidates; the route ring is its only state, the stream its only (sequential,
-//             chain-independent) input.
-// The stream lives in the general pipeline's buffers (per-slot records, group offsets, candidate weights), which
-// are idle unless a batch is flagged -- and a flagged batch is redone from scratch.
-// ==========================================================================================
-constexpr uint32_t kPoolChunk = 8192;  // weights a warp reserves from the pool at a time (a round needs <= 512)
-
-__global__ void __launch_bounds__(128) k_probe(const JbTables T, const LongArgs A) {
-  __shared__ double cw[16][128];  // the candidates' weights of each lane's position
-  if (A.counters[C_FLAGS] & 1u) return;
-  const uint32_t nl = min(A.counters[C_N_LRT], A.lblocks_cap);
-  const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  const uint8_t* __restrict__ text = A.text;
-  for (;;) {
-    uint32_t li = 0;
-    if (lane == 0) li = atomicAdd(&A.counters[C_CUR_PROBE], 1u);
-    li = __shfl_sync(FULL, li, 0);
-    if (li >= nl) break;
-    const uint4 lb = A.lblocks[li];
-    const uint32_t last = lb.x, nr = lb.y, g0 = lb.w, e3i = last / 3u;
-    uint32_t pcur = 0, pleft = 0;
-    bool wide = false;
-    for (uint32_t j = 0; j * 32u < nr; j++) {
-      const uint32_t kq = j * 32u + lane;  // runes to the right of this lane's position
-      const bool valid = kq < nr;
-      const uint32_t p = last - 3u * (valid ? kq : 0u);
-      const uint32_t b0 = text[p];
-      if (__any_sync(FULL, valid && (b0 & 0xF0u) != 0xE0u)) {  // stepped into a 4-byte Han rune: the block is k_wide's
-        wide = true;
-        break;
-      }
-      uint32_t mask = 0, c = 0;
-      if (valid) {
-        const uint32_t r0 = ((b0 & 0x0Fu) << 12) | ((text[p + 1] & 0x3Fu) << 6) | (text[p + 2] & 0x3Fu);
-        const uint4 f = ldg_keep(reinterpret_cast<const uint4*>(T.first) + r0);  // termFreq[string(iRune)] (T:468-472)
-        cw[0][tid] = __longlong_as_double(((long long)f.y << 32) | (long long)f.x);
-        mask = 1u;
-        c = 1;
-        if (!(f.z & JB_FIRST_GATE)) {
-          const uint32_t maxlen = (f.z >> 8) & 0xFFu;
-          uint32_t child = f.w, parent = JB_PARENT_FIRST(r0), hs = JB_PARENT_FIRST(r0);
-          for (uint32_t L = 1; L < maxlen && L <= kq;) {  // for j := range textRunes[i:] (T:473-482)
-            const uint32_t q = p + 3u * L;
-            const uint32_t rl = ((text[q] & 0x0Fu) << 12) | ((text[q + 1] & 0x3Fu) << 6) | (text[q + 2] & 0x3Fu);
-            const bool may = L == 1 ? ((child >> jb_bloom_bit(rl)) & 1u) : ((child >> jb_bloom11(rl)) & 1u);
-            if (!may) break;
-            double pw;
-            uint32_t prb;
-            const int ps = jb_probe_edge(T.entries, T.hash_mask, T.hash_shift, hs, parent, rl, &pw, &prb);
-            if (ps < 0) break;
-            L++;
-            if (jb_w_positive(pw)) {  // val > 0 -> edge (T:479-481)
-              mask |= 1u << (L - 1u);
-              cw[c++][tid] = pw;
-            }
-            parent = (uint32_t)ps;
-            child = prb >> 21;
-          }
-        }
-      }
-      // append the round's weights to the stream, lane order = the selector's order (right to left)
-      uint32_t inc = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, inc, o);
-        if (lane >= (uint32_t)o) inc += v;
-      }
-      const uint32_t total = __shfl_sync(FULL, inc, 31);
-      if (total > pleft) {
-        if (lane == 0) pcur = atomicAdd(&A.counters[C_POOL], kPoolChunk);
-        pcur = __shfl_sync(FULL, pcur, 0);
-        pleft = kPoolChunk;
-        if ((uint64_t)pcur + kPoolChunk > A.pool_cap) {  // out of candidate space: the general pipeline redoes the batch
-          if (lane == 0) atomicOr(&A.counters[C_FLAGS], 1u);
-          return;
-        }
-      }
-      if (lane == 0) A.gbase[g0 + j] = pcur;
-      if (valid) {
-        A.masks[e3i - kq] = (uint16_t)mask;
-        double* __restrict__ out = A.pool + pcur + (inc - c);
-        for (uint32_t i = 0; i < c; i++) out[i] = cw[i][tid];
-      }
-      pcur += total;
-      pleft -= total;
-    }
-    if (wide && lane == 0) {
-      const uint32_t wi = atomicAdd(&A.counters[C_N_WIDE], 1u);
-      if (wi < A.wide_cap) A.wide_list[wi] = last;
-      else atomicOr(&A.counters[C_FLAGS], 1u);
-      A.blocks[lb.z].y = 0;   // nothing for k_emit
-      A.lblocks[li].y = 0;    // nothing for k_select
-    }
-    __syncwarp();
-  }
-}
-
-template <int PB>
-__global__ void __launch_bounds__(128) k_select(const LongArgs A) {
-  constexpr uint32_t PPW = 32 / PB;
-  __shared__ double ring[16][128];
-  if (A.counters[C_FLAGS] & 1u) return;
-  const uint32_t nl = min(A.counters[C_N_LRT], A.lblocks_cap);
-  const uint32_t tid = threadIdx.x;
-  double* const sring = &ring[0][tid];
-  for (uint32_t li = blockIdx.x * blockDim.x + tid; li < nl; li += gridDim.x * blockDim.x) {
-    const uint4 lb = A.lblocks[li];
-    const uint32_t last = lb.x, nr = lb.y, bi = lb.z, g0 = lb.w, e3i = last / 3u;
-    if (nr == 0) continue;  // handed to k_wide (or never handed over)
-    sring[15 * 128] = 0.0;  // R[-1]: {j, 0.0} at the end of the block (T:522) -- cell 15 is not written before rune 15
-    double R1 = 0.0;        // the route value one rune to the right
-    uint32_t acc = 0, accw = 0xFFFFFFFFu;
-    const double* __restrict__ wp = A.pool;
-    uint32_t pb = 0;
-    // one position ahead: its mask and its first weight (both addresses are known before the chain gets there)
-    uint32_t mask_n = A.masks[e3i];
-    pb = A.gbase[g0];
-    double w_n = wp[pb];
-    for (uint32_t kq = 0; kq < nr; kq++) {
-      uint32_t bits = mask_n >> 1;  // (bit 0, the single rune, is always a candidate)
-      // maxIndexProba (T:565-578) over the candidates in ascending length, as k_wide does it
-      double prev = JB_MINF, best_v = 0.0;
-      uint32_t best_d = 0, last_d = 1;
-      double v = w_n + R1;
-      if (v >= prev) {
-        best_d = 1;
-        best_v = v;
-      }
-      prev = v;
-      pb++;
-      while (bits) {
-        const uint32_t L = (uint32_t)__ffs(bits) + 1u;  // bit L - 2 of `bits` <=> length L
-        bits &= bits - 1u;
-        v = wp[pb++] + sring[((kq - L) & 15u) * 128];
-        last_d = L;
-        if (v >= prev) {
-          best_d = L;
-          best_v = v;
-        }
-        prev = v;
-      }
-      if (best_d == 0) {  // best.index == -1 -> return prev (T:574-576)
-        best_d = last_d;
-        best_v = prev;
-      }
-      // the next position's first loads, before this one's stores; and the stream a few hundred bytes ahead into L1
-      // (32 lanes read 32 streams: without this every line is a DRAM round trip in the middle of the chain)
-      if (kq + 1u < nr) {
-        if (((kq + 1u) & 31u) == 0u) pb = A.gbase[g0 + ((kq + 1u) >> 5)];
-        mask_n = A.masks[e3i - kq - 1u];
-        w_n = wp[pb];
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + pb + 64));
-        if ((kq & 31u) == 0u) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(A.masks + (e3i - kq > 192u ? e3i - kq - 192u : 0u)));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(A.gbase + g0 + (kq >> 5) + 8u));
-        }
-      }
-      sring[(kq & 15u) * 128] = best_v;
-      R1 = best_v;
-      const uint32_t idx = e3i - kq, pwd = idx / PPW;
-      if (pwd != accw) {
-        if (acc) atomicOr(&A.path[accw], acc);
-        acc = 0;
-        accw = pwd;
-      }
-      acc |= (best_d - 1u) << ((idx % PPW) * PB);
-      if (A.dbg_R) {
-        A.dbg_R[idx] = best_v;
-        A.dbg_D[idx] = (uint8_t)best_d;
-      }
-    }
-    if (acc) atomicOr(&A.path[accw], acc);
-    A.blocks[bi] = make_uint2(last - 3u * (nr - 1u), nr);
-  }
-}
-
-int launch_route_long(const JbTables& T, const LongArgs& A, int num_sms, cudaStream_t st) {
-  k_probe<<<(unsigned)num_sms * 8u, 128, 0, st>>>(T, A);
-  k_select<4><<<(unsigned)num_sms * 8u, 128, 0, st>>>(A);  // (only dictionaries with words of <= 16 runes come here)
-  return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
 int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st) {

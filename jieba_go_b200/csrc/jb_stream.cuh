@@ -54,27 +54,6 @@ struct RouteArgs {
   uint32_t min_chunk;     // blocks a warp takes from the queue at least (few long blocks: lanes per warp vs warps per SM)
   double* dbg_R;          // optional (jb_debug_route): selected route value / word length per rune, index = lead byte / 3
   uint8_t* dbg_D;
-  uint4* lblocks;         // optional: blocks of kLongRoute runes or more are listed here (last rune, runes, block index,
-  uint32_t lblocks_cap;   //   first group) for k_probe / k_select instead of being routed by a lane
-  uint32_t lgroups_cap;   // 32-position groups the stream has room for
-};
-
-// k_probe / k_select: the long blocks' candidate stream
-struct LongArgs {
-  const uint8_t* text;
-  uint4* lblocks;
-  uint32_t lblocks_cap;
-  uint32_t* counters;
-  uint16_t* masks;        // per rune (index = lead byte / 3): bit L - 1 <=> a word of L runes starts here (bit 0 always)
-  uint32_t* gbase;        // per 32-position group of a block: where its weights start in the pool
-  double* pool;           // the candidates' weights, position by position right to left, ascending length
-  uint64_t pool_cap;
-  uint32_t* path;
-  uint2* blocks;
-  uint32_t* wide_list;
-  uint32_t wide_cap;
-  double* dbg_R;
-  uint8_t* dbg_D;
 };
 
 struct EmitArgs {
@@ -115,7 +94,6 @@ struct WideArgs {
 int launch_wide(const JbTables& T, const WideArgs& A, bool hmm, int num_sms, cudaStream_t st);
 int launch_scan(const JbTables& T, const ScanArgs& A, cudaStream_t st);
 int launch_route(const JbTables& T, const RouteArgs& A, int num_sms, cudaStream_t st);
-int launch_route_long(const JbTables& T, const LongArgs& A, int num_sms, cudaStream_t st);  // kernels launched, or -1
 // returns the number of kernels launched, or -1
 int launch_emit(const JbTables& T, const EmitArgs& A, bool hmm, int num_sms, cudaStream_t st, uint32_t n, const uint32_t* ds_bits);
 inline uint32_t scan_tiles(uint32_t n) { return (n + kScTileBytes - 1) / kScTileBytes; }
