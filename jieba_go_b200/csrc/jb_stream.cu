@@ -811,6 +811,8 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   uint32_t P0 = 0, i0 = 0, npos = 0, k = 0;
   uint32_t pw = 0, pt = 0xFFFFFFFFu;
   uint32_t run_n = 0, run_s = 0;
+  uint32_t pend = 0xFFFFFFFFu;  // MODE 2: a single rune whose right neighbour is not known yet
+  bool in_run = true;           //         the previous piece was a marked single rune
   double V[4] = {0.0, 0.0, 0.0, 0.0};
   // viterbi's fullPath (T:715-716) in bit form, per state: bits 0..23 = which runes of its best path are E or S
   // (token ends), bits 24..31 = the path's length (a route with from == "" restarts it)
@@ -839,6 +841,8 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           k = 0;
           run_n = 0;
           pt = 0xFFFFFFFFu;
+          pend = 0xFFFFFFFFu;
+          in_run = true;
           active = npos != 0;  // 0: the block went to k_wide
           if (MODE != 2 && A.segs && npos >= kLongRunes) {  // a long block: cut it into segments for the second launch
             const uint32_t nseg = (npos + kSegRunes - 1) / kSegRunes;
@@ -969,14 +973,40 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
         }
         run_n = 0;
       }
-      if (MODE == 2 && d == 1u) {
-        ma.set(P0 + 3u * k);
+      if (MODE == 2) {
+        // A single rune between two multi-rune pieces is a run of one: cutZh emits it as it is (T:246-249), no Viterbi.
+        // Only runs of two or more are marked for k_runs -- and whatever touches the segment's edges, where the
+        // neighbour is another lane's: the segment's first pieces while they are single (in_run starts true), and a
+        // single rune still pending at its end.
+        const uint32_t q = P0 + 3u * k;
+        if (d == 1u) {
+          if (in_run) {
+            ma.set(q);
+          } else if (pend != 0xFFFFFFFFu) {
+            ma.set(pend);
+            ma.set(q);
+            pend = 0xFFFFFFFFu;
+            in_run = true;
+          } else {
+            pend = q;
+          }
+        } else {
+          if (pend != 0xFFFFFFFFu) {
+            set_s(pend);
+            set_e(pend + 2u);
+            pend = 0xFFFFFFFFu;
+          }
+          in_run = false;
+          set_s(q);
+          set_e(q + 3u * d - 1u);
+        }
       } else if (!single) {
         set_s(P0 + 3u * k);
         set_e(P0 + 3u * (k + d) - 1u);
       }
       k += d;
       if (k >= npos) {
+        if (MODE == 2 && pend != 0xFFFFFFFFu) ma.set(pend);
         if (!HMM) {
           sa.flush();
           ea.flush();
