@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
   uint32_t qh = 0, qt = 0;
   bool exhausted = false, active = false;
   uint32_t P0 = 0, i0 = 0, npos = 0, k = 0;
-  uint32_t pw = 0, pt = 0xFFFFFFFFu;
+  uint32_t pw = 0, pw2 = 0, pt = 0xFFFFFFFFu;
   uint32_t run_n = 0, run_s = 0;
   uint32_t pend = 0xFFFFFFFFu;  // MODE 2: a single rune whose right neighbour is not known yet
   bool in_run = true;           //         the previous piece was a marked single rune
@@ -864,9 +864,11 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
     // ---- one piece of findDagPath's walk (T:552-562) per iteration ----
     if (active) {
       const uint32_t pi = i0 + k;
-      if (pi / PPW != pt) {
-        pt = pi / PPW;
-        pw = A.path[pt];
+      if (pi / PPW != pt) {  // the next word of the path is fetched when the lane enters this one
+        const uint32_t t = pi / PPW;
+        pw = (pt != 0xFFFFFFFFu && t == pt + 1u) ? pw2 : A.path[t];
+        pt = t;
+        pw2 = A.path[pt + 1u];
       }
       const uint32_t d = ((pw >> ((pi % PPW) * PB)) & PMASK) + 1u;
       const bool single = HMM && d == 1;
@@ -893,20 +895,13 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
           for (int s = 0; s < 4; s++) {  // stateTransitionRoute (T:736-756): strict > from minFloat, list order
             const int pa = (s == 0 || s == 3) ? 2 : 0, pb = (s == 0 || s == 3) ? 3 : 1;
             const double r0 = V[pa] + T.trans[s][0], r1 = V[pb] + T.trans[s][1];
-            double best = JB_MINF;
-            uint32_t from = 0;
-            if (r0 > best) {
-              best = r0;
-              from = 1;
-            }
-            if (r1 > best) {
-              best = r1;
-              from = 2;
-            }
-            W[s] = best + em[s];
-            code |= from << (2 * s);
+            const bool t0 = r0 > JB_MINF;   // from = 1
+            const double b0 = t0 ? r0 : JB_MINF;
+            const bool t1 = r1 > b0;        // from = 2
+            W[s] = (t1 ? r1 : b0) + em[s];
+            code |= (t1 ? 2u : (t0 ? 1u : 0u)) << (2 * s);
             // fullPath[s] = fullPath[route.from] + [s]; fullPath[""] is nil (T:715-716)
-            npm[s] = (from == 0 ? 0u : (from == 1 ? pm[pa] : pm[pb])) + (s >= 2 ? step : (1u << 24));
+            npm[s] = (t1 ? pm[pb] : (t0 ? pm[pa] : 0u)) + (s >= 2 ? step : (1u << 24));
           }
 #pragma unroll
           for (int s = 0; s < 4; s++) {
@@ -1128,20 +1123,13 @@ __global__ void __launch_bounds__(kRunThreads) k_runs(const JbTables T, const Em
           for (int s = 0; s < 4; s++) {
             const int pa = (s == 0 || s == 3) ? 2 : 0, pb = (s == 0 || s == 3) ? 3 : 1;
             const double r0 = V[pa] + T.trans[s][0], r1 = V[pb] + T.trans[s][1];
-            double best = JB_MINF;
-            uint32_t from = 0;
-            if (r0 > best) {
-              best = r0;
-              from = 1;
-            }
-            if (r1 > best) {
-              best = r1;
-              from = 2;
-            }
-            W[s] = best + em[s];
-            code |= from << (2 * s);
+            const bool t0 = r0 > JB_MINF;   // from = 1
+            const double b0 = t0 ? r0 : JB_MINF;
+            const bool t1 = r1 > b0;        // from = 2
+            W[s] = (t1 ? r1 : b0) + em[s];
+            code |= (t1 ? 2u : (t0 ? 1u : 0u)) << (2 * s);
             // fullPath[s] = fullPath[route.from] + [s]; fullPath[""] is nil (T:715-716)
-            npm[s] = (from == 0 ? 0u : (from == 1 ? pm[pa] : pm[pb])) + (s >= 2 ? step : (1u << 24));
+            npm[s] = (t1 ? pm[pb] : (t0 ? pm[pa] : 0u)) + (s >= 2 ? step : (1u << 24));
           }
 #pragma unroll
           for (int s = 0; s < 4; s++) {
