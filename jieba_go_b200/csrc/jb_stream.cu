@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const 
       // ---- clean word: ASCII and well-formed 3-byte runes only ----
       RS = AS | L3;
       uint32_t SPC = 0;
-      uint32_t m = L3;
+      uint32_t m = L3, rest = 0;
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
@@ -293,13 +293,21 @@ __global__ void __launch_bounds__(kScThreads, 8) k_scan(const JbTables T, const 
         const uint32_t* wq = reinterpret_cast<const uint32_t*>(&S.sb[off & ~3]);
         const uint32_t x = __funnelshift_r(wq[0], wq[1], (off & 3) * 8);
         // U+4E00..U+9F7F straight on the bytes: (lead << 8 | second) in [E4 B8, E9 BD]
-        if (__byte_perm(x, 0u, 0x4401u) - 0xE4B8u <= 0xE9BDu - 0xE4B8u) {
-          HANL |= 1u << b;
-        } else {
-          const uint32_t cp = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
-          if (s_is_han(cp, T)) HANL |= 1u << b;
-          else if (s_is_space(cp)) SPC |= 1u << b;
-        }
+        const bool common = __byte_perm(x, 0u, 0x4401u) - 0xE4B8u <= 0xE9BDu - 0xE4B8u;
+        HANL |= (common ? 1u : 0u) << b;
+        rest |= (common ? 0u : 1u) << b;
+      }
+      // the other 3-byte runes (punctuation, other scripts, rare Han) in a loop of their own: a word has one or none,
+      // so the lanes that have one meet here instead of holding up the loop above one at a time
+      while (rest) {
+        const int b = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int off = base + b;
+        const uint32_t* wq = reinterpret_cast<const uint32_t*>(&S.sb[off & ~3]);
+        const uint32_t x = __funnelshift_r(wq[0], wq[1], (off & 3) * 8);
+        const uint32_t cp = ((x & 0xFu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
+        if (s_is_han(cp, T)) HANL |= 1u << b;
+        else if (s_is_space(cp)) SPC |= 1u << b;
       }
       m = AS;
       while (m) {
