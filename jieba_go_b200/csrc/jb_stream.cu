@@ -814,10 +814,11 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
     if (HMM) atomicOr(&A.e_bits[q >> 5], 1u << (q & 31));
     else ea.set(q);
   };
-  uint32_t qh = 0, qt = 0;
+  uint32_t qh = 0, qt = 0, qbase = 0, qpw = 0;
+  uint2 qdesc = make_uint2(0u, 0u);
   bool exhausted = false, active = false;
   uint32_t P0 = 0, i0 = 0, npos = 0, k = 0;
-  uint32_t pw = 0, pw2 = 0, pt = 0xFFFFFFFFu;
+  uint32_t pw = 0, pw2 = 0, pt = 0;
   uint32_t run_n = 0, run_s = 0;
   uint32_t pend = 0xFFFFFFFFu;  // MODE 2: a single rune whose right neighbour is not known yet
   bool in_run = true;           //         the previous piece was a marked single rune
@@ -835,20 +836,27 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
         b0 = __shfl_sync(FULL, b0, 0);
         if (b0 >= nblocks) exhausted = true;
         else {
-          qh = b0;
+          qh = qbase = b0;
           qt = min(b0 + chunk, nblocks);
+          // the chunk's descriptors in one coalesced load, and each block's first path word behind it: a lane that
+          // takes a block later gets both by shuffle instead of waiting for two dependent loads per block
+          qdesc = b0 + lane < qt ? A.blocks[b0 + lane] : make_uint2(0u, 0u);
+          qpw = A.path[(qdesc.x / 3u) / PPW];
         }
       }
+      const uint32_t mine = qh + __popc(nm & lt_mask);
+      const uint32_t src = (mine - qbase) & 31u;
+      const uint32_t dx = __shfl_sync(FULL, qdesc.x, src), dy = __shfl_sync(FULL, qdesc.y, src), dw = __shfl_sync(FULL, qpw, src);
       if (!active) {
-        const uint32_t mine = qh + __popc(nm & lt_mask);
         if (mine < qt) {
-          const uint2 desc = A.blocks[mine];
-          P0 = desc.x;
-          npos = desc.y;
+          P0 = dx;
+          npos = dy;
           i0 = P0 / 3u;
           k = 0;
           run_n = 0;
-          pt = 0xFFFFFFFFu;
+          pt = i0 / PPW;
+          pw = dw;
+          pw2 = A.path[pt + 1u];
           pend = 0xFFFFFFFFu;
           in_run = true;
           active = npos != 0;  // 0: the block went to k_wide
@@ -874,7 +882,7 @@ __global__ void __launch_bounds__(kEmThreads) k_emit(const JbTables T, const Emi
       const uint32_t pi = i0 + k;
       if (pi / PPW != pt) {  // the next word of the path is fetched when the lane enters this one
         const uint32_t t = pi / PPW;
-        pw = (pt != 0xFFFFFFFFu && t == pt + 1u) ? pw2 : A.path[t];
+        pw = t == pt + 1u ? pw2 : A.path[t];
         pt = t;
         pw2 = A.path[pt + 1u];
       }
