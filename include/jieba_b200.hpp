@@ -57,7 +57,7 @@ using ResultPtr = std::unique_ptr<jb_result, ResultFree>;
 struct Options {
   int device = -1;                // CUDA device ordinal, -1 = current
   int unicode_version = 15;       // \p{Han} table of the Go release being mirrored: 13 (Go 1.18-1.20) or 15 (>= 1.21)
-  uint64_t max_batch_bytes = 0;   // 0 = library default
+  uint64_t max_batch_bytes = 1ull << 30;  // one document must fit one device batch: 1 GiB as in go/tokenizer.go (0 = library default, 128 MiB)
   // Where the reference finds its bundled files (T:441, 654).  NewJiebaTokenizer needs the gob and the JSON, NewTokenizer
   // the JSON only.
   std::string gob_path = "prefix_dictionary.gob";
